@@ -1,0 +1,88 @@
+"""Case tables and seeded input builders shared by ``make_golden.py`` (which needs the
+reference) and the tests (which must not: ``/root/reference`` is absent on the GPU box)."""
+from __future__ import annotations
+
+import numpy as np
+
+import synth
+
+
+def proj_vectors(shape, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal(shape[1]), rng.standard_normal(shape[0])
+
+
+
+LAYER_CASES = {
+    # tag: (node_dim/hidden, lengths of the packed band graph, W, param seed, data seed, graph kind)
+    "h32_band": (32, (9, 5), 3, 11, 12, "band"),
+    "h32_random": (32, (12,), 0, 13, 14, "random"),
+    "h256_band": (256, (24, 16), 5, 15, 16, "band"),
+}
+
+
+
+DECODER_CASES = {
+    # tag: (z_g, z_l, hidden, layers, W, B, L, mask kind, param seed, data seed)
+    "small": (12, 6, 32, 2, 3, 4, 10, "empty_row", 21, 22),
+    "h256_gaps": (64, 32, 256, 2, 8, 3, 48, "gaps", 23, 24),
+    "refdims": (512, 256, 256, 2, 40, 2, 100, "ragged", 25, 26),
+    "nomask": (12, 6, 32, 1, 20, 2, 7, "none", 27, 28),
+}
+
+
+def decoder_inputs(case):
+    z_g, z_l, H, nl, W, B, L, mkind, pseed, dseed = case
+    rng = np.random.default_rng(dseed)
+    zg = synth.f32(rng.standard_normal((B, z_g)))
+    zl = synth.f32(rng.standard_normal((B, L, z_l)))
+    mask = None if mkind == "none" else synth.make_masks(B, L, dseed + 1, mkind)
+    coef = [synth.f32(rng.standard_normal((B, L, 3))) for _ in range(3)]
+    coef.append(synth.f32(rng.standard_normal((B, L, 20))))
+    return zg, zl, mask, coef
+
+
+
+LOSS_WEIGHTS = dict(klw_g=1.0, klw_l=0.5, w_pair=10.0, w_dihedral=20.0, w_rama=400.0, w_bond=500.0,
+                    w_angle=500.0, w_rec=10.0, w_seq=50.0, w_clash=300.0)   # models/vae.py:39-50
+LOSS_CASES = {
+    # tag: (B, L, mask kind, seed, coordinate scale, pair strides)
+    "walk": (4, 24, "gaps", 31, 1.0, (1, 4, 8)),
+    "compact": (3, 17, "ragged", 33, 0.35, (4,)),
+    "full": (2, 33, "full", 35, 0.6, (8,)),
+}
+
+
+def loss_inputs(case):
+    B, L, mkind, seed, scale, _ = case
+    rng = np.random.default_rng(seed)
+    tn, tca, tc = (a * np.float32(scale) for a in synth.make_backbone(B, L, seed + 1))
+    pn, pca, pc = (synth.f32(a + 0.5 * scale * rng.standard_normal(a.shape)) for a in (tn, tca, tc))
+    d = dict(pred_N=pn, pred_CA=pca, pred_C=pc, target_N=tn, target_CA=tca, target_C=tc,
+             pred_seq=synth.f32(rng.standard_normal((B, L, 20)) * 2.0),
+             labels=rng.integers(0, 20, (B, L)).astype(np.int64),
+             mask=synth.make_masks(B, L, seed + 2, mkind),
+             mu_g=synth.f32(rng.standard_normal((B, 16))), lv_g=synth.f32(0.3 * rng.standard_normal((B, 16))),
+             mu_l=synth.f32(rng.standard_normal((B, L, 8))), lv_l=synth.f32(0.3 * rng.standard_normal((B, L, 8))))
+    return d
+
+
+GRAD_INPUTS = ("pred_N", "pred_CA", "pred_C", "pred_seq", "mu_g", "lv_g", "mu_l", "lv_l")
+
+
+
+def kabsch_inputs():
+    rng = np.random.default_rng(41)
+    S, L = 8, 30
+    a = synth.f32(np.cumsum(rng.standard_normal((S, L, 3)) * 2.2, axis=1))
+    q, _ = np.linalg.qr(rng.standard_normal((S, 3, 3)))
+    q[:, :, 0] *= np.sign(np.linalg.det(q))[:, None]              # proper rotations
+    b = np.einsum("slk,sjk->slj", a, q) + 3.0 * rng.standard_normal((S, 1, 3))
+    b = b + np.array([0.05, 0.1, 0.3, 1.0, 2.0, 0.0, 0.2, 5.0])[:, None, None] * rng.standard_normal((S, L, 3))
+    b[6] = b[6] * np.array([1.0, 1.0, -1.0])                     # a reflected copy: d = -1 branch
+    b = synth.f32(b)
+    mask = synth.make_masks(S, L, 43, "gaps")
+    mask[5] = 0                                                   # empty selection -> 0.0
+    return a, b, mask
+
+
