@@ -1,0 +1,195 @@
+/*
+ * pev_b200.h -- C ABI of the B200 (sm_100a) hot path of Protein-Ensemble-VAE:
+ * EGNN decoder message passing, geometric losses, batched Kabsch RMSD.
+ *
+ * The reference (mohit03031999/Protein-Ensemble-VAE) is pure Python on PyTorch and has
+ * no FFI; the boundary a replacement must honour is its Python module / function
+ * signatures.  This header is the layer under those signatures: every
+ * entry point names the reference code it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - row-major, contiguous tensors; float = IEEE binary32; indices int32 unless stated;
+ *   - no allocation, no stream synchronisation, no host callback inside any call;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, non-zero on error (message via pev_last_error(), thread-local);
+ *   - optional pointers may be NULL where stated.
+ */
+#ifndef PEV_B200_H
+#define PEV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEV_ABI_VERSION 1
+
+/* number of base loss terms produced by pev_loss_*; see enum below */
+#define PEV_NUM_TERMS 17
+
+enum pev_term {
+  PEV_T_REC_CA = 0,   /* rmsd_loss(pred_CA, target_CA)          models/losses.py:12-21   */
+  PEV_T_REC_N = 1,    /* rmsd_loss(pred_N, target_N)                                     */
+  PEV_T_REC_C = 2,    /* rmsd_loss(pred_C, target_C)                                     */
+  PEV_T_PAIR = 3,     /* pair_distance_loss                     models/losses.py:24-37   */
+  PEV_T_KL_G = 4,     /* kl_global                              models/losses.py:49-51   */
+  PEV_T_KL_L = 5,     /* kl_local                               models/losses.py:54-57   */
+  PEV_T_DIH_CONS = 6, /* dihedral_consistency_loss              models/losses.py:60-69   */
+  PEV_T_OMEGA = 7,    /* omega_trans_loss                       models/losses.py:136-155 */
+  PEV_T_RAMA = 8,     /* ramachandran_loss                      models/losses.py:72-131  */
+  PEV_T_BOND_NCA = 9, /* bond_length_loss: N-CA                 models/losses.py:335-337 */
+  PEV_T_BOND_CAC = 10,/*                  CA-C                  models/losses.py:340-342 */
+  PEV_T_BOND_CN = 11, /*                  C(i)-N(i+1)           models/losses.py:345-351 */
+  PEV_T_ANG_NCAC = 12,/* bond_angle_loss: N-CA-C                models/losses.py:382-385 */
+  PEV_T_ANG_CNCA = 13,/*                  C(i)-N(i+1)-CA(i+1)   models/losses.py:388-393 */
+  PEV_T_ANG_CACN = 14,/*                  CA(i)-C(i)-N(i+1)     models/losses.py:398-403 */
+  PEV_T_SEQ = 15,     /* sequence_classification_loss           models/losses.py:411-437 */
+  PEV_T_CLASH = 16    /* clash_loss                             models/losses.py:439-517 */
+};
+
+/* ---------------------------------------------------------------- runtime */
+int pev_abi_version(void);
+const char* pev_last_error(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+int64_t pev_launch_count(void);
+
+/* ---------------------------------------------------------------- graph (integer work)
+ * Replaces EGNNDecoder.build_edge_index / degrees, models/en_gnn_decoder.py:174-198, for a
+ * packed batch: conformer b owns nodes [cu_seqlens[b], cu_seqlens[b+1]) and the edges
+ * [edge_base[b], edge_base[b+1]); within a conformer edges i<-j, 0<|i-j|<=W, sorted (i,j).
+ * Outputs: row_ptr[N+1], row[E], col[E] (global node ids), csc_perm[E] = edge ids sorted by
+ * (col,row) -- the band is symmetric so col_ptr == row_ptr --, dinv[N] = 1/deg as float
+ * (0 where deg==0).  edge_base is int64 [B+1]; any output may be NULL. */
+int pev_band_graph_build(const int32_t* cu_seqlens, const int64_t* edge_base, int32_t num_conformers,
+                         int32_t max_neighbors, int64_t num_nodes, int32_t* row_ptr, int32_t* row,
+                         int32_t* col, int32_t* csc_perm, float* dinv, void* stream);
+
+/* ---------------------------------------------------------------- K1 (fp32 form): edge prologue
+ * u[e,:] = A[row e,:] + B[col e,:] + wd * |x_row - x_col|^2 + b1, where AB[N,2H] holds
+ * A = h Wa^T (columns 0..H-1) and B = h Wb^T (columns H..2H-1): the factored first edge
+ * linear of EGNLayer.forward, models/en_gnn_decoder.py:60-65. */
+int pev_edge_prologue_fwd(const float* AB, const float* x, const float* wd, const float* b1,
+                          const int32_t* row, const int32_t* col, int64_t num_edges, int32_t H,
+                          float* u, void* stream);
+/* backward of the above: gAB[N,2H], gx[N,3] (overwritten), gwd_part[N,H] (per-node partial
+ * sums of gu*d2; reduce over nodes for gwd).  Deterministic segmented sums over the CSR row
+ * segments and the CSC column segments; no atomics.  scratch_gd2: float[E]. */
+int pev_edge_prologue_bwd(const float* gu, const float* x, const float* wd, const int32_t* row_ptr,
+                          const int32_t* row, const int32_t* col, const int32_t* col_ptr,
+                          const int32_t* csc_perm, int64_t num_nodes, int64_t num_edges, int32_t H,
+                          float* gAB, float* gx, float* gwd_part, float* scratch_gd2, void* stream);
+
+/* ---------------------------------------------------------------- K2: segmented scatter-sum +
+ * coordinate update.  agg[i,:] = sum_{e in row i} m[e,:] (ascending edge order, plain fp32
+ * adds: bit-identical to the CPU index_add_ of models/en_gnn_decoder.py:68-69) and
+ * x_out = x + (sum_e w_e (x_i - x_col e)) * dinv_i * 0.2 (models/en_gnn_decoder.py:78-86).
+ * dinv may be NULL (degree_inv=None).  agg / x_out may be NULL to skip that half. */
+int pev_scatter_coord_fwd(const float* m, const float* w, const float* x, const float* dinv,
+                          const int32_t* row_ptr, const int32_t* col, int64_t num_nodes, int32_t H,
+                          float* agg, float* x_out, void* stream);
+/* backward: gm[e,:] = gagg[row e,:]; gw[e] = 0.2 dinv_i (gxo_i . rel_e);
+ * gx = gxo + sum_{row=i} w_e c_i - sum_{col=i} w_e c_row(e), c_i = 0.2 dinv_i gxo_i. */
+int pev_scatter_coord_bwd(const float* gagg, const float* gxo, const float* w, const float* x,
+                          const float* dinv, const int32_t* row_ptr, const int32_t* row,
+                          const int32_t* col, const int32_t* col_ptr, const int32_t* csc_perm,
+                          int64_t num_nodes, int64_t num_edges, int32_t H, float* gm, float* gw,
+                          float* gx, void* stream);
+
+/* ---------------------------------------------------------------- K1 (bf16 tensor-core form)
+ * Fused edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79) on tcgen05, H = 256.
+ * Stage 1: a = silu(u) built on the fly from AB/x, v = a W2^T + b2 (bf16 x bf16 -> fp32 in TMEM),
+ *          m = silu(v); writes v as bf16 [E,256] and accumulates agg[N,256] (+= into zeroed fp32).
+ * Stage 2: s = m W5^T + b5, t = silu(s), w = t . w6 + b6; writes w[E] fp32 (and s as bf16 if
+ *          s_out != NULL, for backward).
+ * W2p / W5p are the weights repacked by pev_pack_weight_bf16.  AB is fp32 [N,512]. */
+int pev_pack_weight_bf16(const float* W /*[256,256] row-major (out,in)*/, int32_t transpose,
+                         void* packed /*131072 bytes*/, void* stream);
+int pev_edge_mlp1_fwd_bf16(const float* AB, const float* x, const float* wd, const float* b1,
+                           const void* W2p, const float* b2, const int32_t* row, const int32_t* col,
+                           int64_t num_nodes, int64_t num_edges, void* v_out /*bf16 [E,256]*/,
+                           float* agg /*[N,256], pre-zeroed*/, void* stream);
+int pev_edge_mlp2_fwd_bf16(const void* v /*bf16 [E,256]*/, const void* W5p, const float* b5,
+                           const float* w6, const float* b6, int64_t num_edges,
+                           float* w_out /*[E]*/, void* s_out /*bf16 [E,256] or NULL*/, void* stream);
+/* Generic fused "rows -> GEMM with a resident 256x256 weight -> epilogue" used by the bf16
+ * backward (kernels B1/B2). */
+int pev_edge_bwd1_bf16(const void* s /*bf16 [E,256]*/, const void* v /*bf16 [E,256]*/,
+                       const float* gw /*[E]*/, const float* w6, const void* W5tp,
+                       const float* gagg /*[N,256]*/, const int32_t* row, int64_t num_edges,
+                       void* gs_out /*bf16 [E,256]*/, void* gv_out /*bf16 [E,256]*/, void* stream);
+int pev_edge_bwd2_bf16(const void* gv /*bf16 [E,256]*/, const void* W2tp, const float* AB,
+                       const float* x, const float* wd, const float* b1, const int32_t* row,
+                       const int32_t* col, int64_t num_edges, float* gu_out /*fp32 [E,256]*/,
+                       void* stream);
+
+/* ---------------------------------------------------------------- K3: losses
+ * Forward accumulators: acc_global[2*PEV_NUM_TERMS] doubles (numerator, denominator per term;
+ * pre-zeroed) and acc_sample[B*8] doubles (per conformer: rec_ca, rec_n, rec_c numerators,
+ * sum(mask), clash numerator, clash denominator, 2 spare; pre-zeroed).
+ * pev_loss_finalize turns them into terms[PEV_NUM_TERMS] (float) and
+ * inv_den[PEV_NUM_TERMS + 2B] (float: per-term 1/denominator, then per conformer 1/(B sum(mask_b)),
+ * then per conformer 1/(B (clash pairs_b + 1e-8))) used by the backward kernels.  Any input pointer may be NULL: its terms are skipped. */
+typedef struct pev_loss_args {
+  const float* pred_N;      /* [B,L,3] */
+  const float* pred_CA;
+  const float* pred_C;
+  const float* target_N;
+  const float* target_CA;
+  const float* target_C;
+  const float* mask;        /* [B,L] float 0/1 */
+  const float* target_dih;  /* [B,L,6] or NULL */
+  const float* logits;      /* [B,L,C] or NULL */
+  const int64_t* labels;    /* [B,L] */
+  const float* mu_l;        /* [B,L,D] or NULL */
+  const float* lv_l;
+  const float* mu_g;        /* [B,G] or NULL */
+  const float* lv_g;
+  int32_t B, L, C, D, G;
+  int32_t pair_stride;      /* >0 enables PEV_T_PAIR */
+  int32_t enable_clash;
+  int32_t enable_geometry;  /* bond / angle / dihedral-derived terms from pred_N/CA/C */
+  float clash_dist;         /* 3.2 in the reference (models/losses.py:439) */
+  float soft_margin;        /* 0.5 */
+} pev_loss_args;
+
+int pev_loss_fwd(const pev_loss_args* args_host, double* acc_global, double* acc_sample,
+                 void* stream);
+int pev_loss_finalize(const double* acc_global, const double* acc_sample, int32_t B,
+                      float* terms, float* inv_den, void* stream);
+/* coef[PEV_NUM_TERMS]: upstream gradient per base term (device).  Output gradients
+ * (overwritten; any may be NULL): same shapes as the corresponding inputs. */
+int pev_loss_bwd(const pev_loss_args* args_host, const float* coef, const float* inv_den,
+                 float* g_pred_N, float* g_pred_CA, float* g_pred_C, float* g_logits,
+                 float* g_mu_l, float* g_lv_l, float* g_mu_g, float* g_lv_g, void* stream);
+
+/* compute_dihedrals_from_coords, models/losses.py:235-308: out[B,L,6]. */
+int pev_dihedrals_fwd(const float* N, const float* CA, const float* C, const float* mask, int32_t B,
+                      int32_t L, float* out, void* stream);
+int pev_dihedrals_bwd(const float* N, const float* CA, const float* C, const float* mask,
+                      const float* gout, int32_t B, int32_t L, float* gN, float* gCA, float* gC,
+                      void* stream);
+/* dihedral-space terms on an explicit [B,L,6] tensor: dihedral_consistency_loss,
+ * ramachandran_loss, omega_trans_loss (models/losses.py:60-155).  sums[6] doubles, pre-zeroed:
+ * cons num, cons den, rama num, omega num, sum(mask), spare.  target may be NULL. */
+int pev_dihedral_terms_fwd(const float* dih, const float* target, const float* mask, int32_t B,
+                           int32_t L, double* sums, void* stream);
+/* coef3 = device float[3]: d(loss)/d(term) already divided by the term's denominator. */
+int pev_dihedral_terms_bwd(const float* dih, const float* target, const float* mask,
+                           const float* coef3, int32_t B, int32_t L, float* gdih, void* stream);
+
+/* ---------------------------------------------------------------- K4: batched Kabsch RMSD
+ * Replaces kabsch_rmsd, generate_ensemble_pdbs.py:343-373, for S conformers at once.
+ * a[S,L,3]; b[S or 1,L,3] (b_batch = 0 broadcasts one reference structure); mask[S or 1,L]
+ * float (NULL = all valid).  mode 0: optimal-superposition RMSD (scripts/validation_metrics.py:57-85);
+ * mode 1: bit-for-intent reproduction of the reference's c1 @ R convention.
+ * out[S]; 0.0 for an empty selection as in the reference (:350-351). */
+int pev_kabsch_rmsd(const float* a, const float* b, const float* mask, int32_t S, int32_t L,
+                    int32_t b_batch, int32_t mask_batch, int32_t mode, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEV_B200_H */

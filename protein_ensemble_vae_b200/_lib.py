@@ -1,0 +1,129 @@
+"""ctypes binding of the C ABI in ``include/pev_b200.h`` (``csrc/`` -> ``libpev_b200.so``).
+
+The product path is CUDA-only: :func:`lib` raises if the shared library cannot be
+loaded and :func:`ptr` raises on a non-CUDA tensor.  There is no CPU fallback.
+(``tests/`` may point :data:`_LIB` at ``tests/hostcheck`` -- the kernels' per-thread
+bodies compiled for the host -- to exercise the Python host logic without a GPU;
+nothing in this package does.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpev_b200.so")
+NUM_TERMS = 17
+
+# enum pev_term
+(T_REC_CA, T_REC_N, T_REC_C, T_PAIR, T_KL_G, T_KL_L, T_DIH_CONS, T_OMEGA, T_RAMA, T_BOND_NCA,
+ T_BOND_CAC, T_BOND_CN, T_ANG_NCAC, T_ANG_CNCA, T_ANG_CACN, T_SEQ, T_CLASH) = range(NUM_TERMS)
+
+
+class LossArgs(ctypes.Structure):
+    """``struct pev_loss_args``."""
+    _fields_ = [(n, c_void_p) for n in (
+        "pred_N", "pred_CA", "pred_C", "target_N", "target_CA", "target_C", "mask", "target_dih",
+        "logits", "labels", "mu_l", "lv_l", "mu_g", "lv_g")] + [
+        (n, c_int32) for n in ("B", "L", "C", "D", "G", "pair_stride", "enable_clash", "enable_geometry")
+    ] + [("clash_dist", c_float), ("soft_margin", c_float)]
+
+
+_P, _I, _L = c_void_p, c_int32, c_int64
+_PROTOS = {
+    "pev_abi_version": (c_int32, []),
+    "pev_last_error": (c_char_p, []),
+    "pev_launch_count": (c_int64, []),
+    "pev_band_graph_build": (c_int32, [_P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P]),
+    "pev_edge_prologue_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "pev_edge_prologue_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _P]),
+    "pev_scatter_coord_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    "pev_scatter_coord_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
+    "pev_loss_fwd": (c_int32, [POINTER(LossArgs), _P, _P, _P]),
+    "pev_loss_finalize": (c_int32, [_P, _P, _I, _P, _P, _P]),
+    "pev_loss_bwd": (c_int32, [POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pev_dihedrals_fwd": (c_int32, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "pev_dihedrals_bwd": (c_int32, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "pev_dihedral_terms_fwd": (c_int32, [_P, _P, _P, _I, _I, _P, _P]),
+    "pev_dihedral_terms_bwd": (c_int32, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "pev_kabsch_rmsd": (c_int32, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+}
+# tensor-core entry points: present in libpev_b200.so only (no host restatement)
+_PROTOS_TC = {
+    "pev_pack_weight_bf16": (c_int32, [_P, _I, _P, _P]),
+    "pev_edge_mlp1_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
+    "pev_edge_mlp2_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
+}
+
+
+class Lib:
+    """A loaded shared library exporting (a subset of) the C ABI."""
+
+    def __init__(self, path: str, require_tc: bool = True):
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        protos = dict(_PROTOS)
+        if require_tc:
+            protos.update(_PROTOS_TC)
+        for name, (res, args) in protos.items():
+            fn = getattr(self.cdll, name)          # AttributeError if the symbol is missing
+            fn.restype, fn.argtypes = res, args
+        if self.cdll.pev_abi_version() != 1:
+            raise RuntimeError(f"{path}: ABI version mismatch")
+
+    def call(self, name: str, *args):
+        rc = getattr(self.cdll, name)(*args)
+        if rc != 0:
+            msg = self.cdll.pev_last_error()
+            raise RuntimeError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def launch_count(self) -> int:
+        return int(self.cdll.pev_launch_count())
+
+
+_LIB: Lib | None = None
+_REQUIRE_CUDA = True      # flipped only by tests that run the host restatement
+
+
+def lib() -> Lib:
+    """The CUDA library; fails loudly when it has not been built (``python -m protein_ensemble_vae_b200.build``)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the sm_100a kernels first "
+                "(python -m protein_ensemble_vae_b200.build); there is no CPU fallback")
+        _LIB = Lib(LIB_PATH)
+    return _LIB
+
+
+def ptr(t: torch.Tensor | None, dtype=None):
+    """Device pointer of a contiguous tensor (``None`` -> NULL)."""
+    if t is None:
+        return None
+    if _REQUIRE_CUDA and not t.is_cuda:
+        raise RuntimeError("protein_ensemble_vae_b200 runs on CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("internal error: non-contiguous tensor passed to the C ABI")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"internal error: expected {dtype}, got {t.dtype}")
+    return c_void_p(t.data_ptr())
+
+
+def stream(t: torch.Tensor | None = None):
+    """``cudaStream_t`` of torch's current stream on the tensor's device."""
+    if t is not None and t.is_cuda:
+        return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return None
+
+
+def f32c(t: torch.Tensor | None) -> torch.Tensor | None:
+    """float32, contiguous view/copy (``None`` passes through)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
