@@ -100,30 +100,22 @@ int pev_scatter_coord_bwd(const float* gagg, const float* gxo, const float* w, c
 
 /* ---------------------------------------------------------------- K1 (bf16 tensor-core form)
  * Fused edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79) on tcgen05, H = 256.
- * Stage 1: a = silu(u) built on the fly from AB/x, v = a W2^T + b2 (bf16 x bf16 -> fp32 in TMEM),
- *          m = silu(v); writes v as bf16 [E,256] and accumulates agg[N,256] (+= into zeroed fp32).
- * Stage 2: s = m W5^T + b5, t = silu(s), w = t . w6 + b6; writes w[E] fp32 (and s as bf16 if
- *          s_out != NULL, for backward).
- * W2p / W5p are the weights repacked by pev_pack_weight_bf16.  AB is fp32 [N,512]. */
+ * Stage 1: a = silu(A_i + B_j + wd d2) built on the fly, v = a W2^T + b2 (bf16 x bf16 -> fp32 in
+ *          TMEM); writes v as bf16 [E,256] and agg[N,256] = segment_sum(silu(v)) (zeroed inside,
+ *          fp32 atomics per warp-segment).  AB is bf16 [N,512] = [h Wa^T + b1 | h Wb^T].
+ * Stage 2: m = silu(v), s = m W5^T + b5, t = silu(s), w = t . w6 + b6; writes w[E] fp32 (zeroed
+ *          inside) and, if s_out != NULL, s as bf16 [E,256] for the backward pass.
+ * W2p / W5p are 131072-byte images produced by pev_pack_weight_bf16 (bf16, K-major, 128-byte
+ * swizzle -- the resident B operand of tcgen05.mma). */
 int pev_pack_weight_bf16(const float* W /*[256,256] row-major (out,in)*/, int32_t transpose,
                          void* packed /*131072 bytes*/, void* stream);
-int pev_edge_mlp1_fwd_bf16(const float* AB, const float* x, const float* wd, const float* b1,
-                           const void* W2p, const float* b2, const int32_t* row, const int32_t* col,
+int pev_edge_mlp1_fwd_bf16(const void* AB, const float* x, const float* wd, const void* W2p,
+                           const float* b2, const int32_t* row, const int32_t* col,
                            int64_t num_nodes, int64_t num_edges, void* v_out /*bf16 [E,256]*/,
-                           float* agg /*[N,256], pre-zeroed*/, void* stream);
+                           float* agg /*[N,256]*/, void* stream);
 int pev_edge_mlp2_fwd_bf16(const void* v /*bf16 [E,256]*/, const void* W5p, const float* b5,
-                           const float* w6, const float* b6, int64_t num_edges,
+                           const float* w6, const float* b6 /*[1]*/, int64_t num_edges,
                            float* w_out /*[E]*/, void* s_out /*bf16 [E,256] or NULL*/, void* stream);
-/* Generic fused "rows -> GEMM with a resident 256x256 weight -> epilogue" used by the bf16
- * backward (kernels B1/B2). */
-int pev_edge_bwd1_bf16(const void* s /*bf16 [E,256]*/, const void* v /*bf16 [E,256]*/,
-                       const float* gw /*[E]*/, const float* w6, const void* W5tp,
-                       const float* gagg /*[N,256]*/, const int32_t* row, int64_t num_edges,
-                       void* gs_out /*bf16 [E,256]*/, void* gv_out /*bf16 [E,256]*/, void* stream);
-int pev_edge_bwd2_bf16(const void* gv /*bf16 [E,256]*/, const void* W2tp, const float* AB,
-                       const float* x, const float* wd, const float* b1, const int32_t* row,
-                       const int32_t* col, int64_t num_edges, float* gu_out /*fp32 [E,256]*/,
-                       void* stream);
 
 /* ---------------------------------------------------------------- K3: losses
  * Forward accumulators: acc_global[2*PEV_NUM_TERMS] doubles (numerator, denominator per term;

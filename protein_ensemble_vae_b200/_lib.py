@@ -54,7 +54,7 @@ _PROTOS = {
 # tensor-core entry points: present in libpev_b200.so only (no host restatement)
 _PROTOS_TC = {
     "pev_pack_weight_bf16": (c_int32, [_P, _I, _P, _P]),
-    "pev_edge_mlp1_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
+    "pev_edge_mlp1_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
     "pev_edge_mlp2_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
 }
 
@@ -69,7 +69,11 @@ class Lib:
         if require_tc:
             protos.update(_PROTOS_TC)
         for name, (res, args) in protos.items():
-            fn = getattr(self.cdll, name)          # AttributeError if the symbol is missing
+            try:
+                fn = getattr(self.cdll, name)
+            except AttributeError as e:
+                raise RuntimeError(f"{path} does not export {name}; rebuild it "
+                                   "(python -m protein_ensemble_vae_b200.build --force)") from e
             fn.restype, fn.argtypes = res, args
         if self.cdll.pev_abi_version() != 1:
             raise RuntimeError(f"{path}: ABI version mismatch")

@@ -1,0 +1,475 @@
+// K1, bf16 tensor-core form: the EGNN edge MLP (models/en_gnn_decoder.py:60-79) on tcgen05.
+//
+// One persistent, warp-specialised kernel template, instantiated twice:
+//   STAGE 1  a = silu(A_i + B_j + wd d2)  --GEMM W2-->  v = . + b2 ; v -> HBM (bf16), m = silu(v),
+//            agg[row] += m   (segmented butterfly reduction per warp, RED.ADD.F32 per segment)
+//   STAGE 2  m = silu(v)                  --GEMM W5-->  s = . + b5 ; t = silu(s), w[e] = t . w6 + b6
+// Tile = 128 consecutive edges (rows of the GEMM) x N = 256 x K = 256.
+//   * the 256x256 bf16 weight stays resident in shared memory for the whole kernel (128 KB,
+//     K-major, 128-byte swizzle), fetched once per CTA with cp.async.bulk (TMA, no tensor map);
+//   * producer warps build the A operand on the fly (gather + SiLU -> bf16) straight into a ring of
+//     [128 x 64] K-chunks in the UMMA canonical K-major SWIZZLE_128B layout;
+//   * one elected thread issues tcgen05.mma (M=128, N=256, K=16; fp32 accumulators in TMEM),
+//     two accumulator stages (2 x 256 TMEM columns) so the epilogue of tile t overlaps the MMAs of t+1;
+//   * epilogue warps read TMEM with tcgen05.ld (32x32b.x32), apply bias / SiLU and write results.
+// Synchronisation is mbarrier-only (full/empty per ring stage, full/empty per accumulator stage).
+#include <cuda_bf16.h>
+
+#include "../../include/pev_b200.h"
+#include "pev_common.cuh"
+
+namespace pev {
+namespace tc {
+
+constexpr int H = 256;                 // node_dim == hidden_dim of the reference decoder (F1)
+constexpr int TILE_M = 128;            // edges per tile
+constexpr int KCHUNK = 64;             // bf16 elements per 128-byte swizzle row
+constexpr int NUM_KCHUNKS = H / KCHUNK;
+constexpr int UMMA_K = 16;
+constexpr int NUM_STAGES = 5;          // A-operand ring (16 KB each)
+constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
+constexpr int W_BYTES = H * H * 2;
+constexpr int NUM_EPI_WARPS = 8;       // warps 0..7   (TMEM lane quarter = warp % 4, column half = warp / 4)
+constexpr int MMA_WARP = 8;            // warp 8       (TMEM alloc, weight load, MMA issue)
+constexpr int NUM_PROD_WARPS = 8;      // warps 9..16
+constexpr int NUM_THREADS = 32 * (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS);
+constexpr int NUM_PROD_THREADS = 32 * NUM_PROD_WARPS;
+constexpr int NUM_EPI_THREADS = 32 * NUM_EPI_WARPS;
+constexpr int TMEM_COLS = 512;
+
+struct __align__(16) SmemLayout {
+  // offsets into dynamic shared memory (base aligned to 1024)
+  static constexpr int W_OFF = 0;
+  static constexpr int A_OFF = W_BYTES;
+  static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 3 x 256 floats
+  static constexpr int META_OFF = VEC_OFF + 3 * H * 4;                  // 2 x 128 x (row,col,d2)
+  static constexpr int BAR_OFF = META_OFF + 2 * TILE_M * 12;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+constexpr int SMEM_BYTES = SmemLayout::TOTAL + 1024;   // slack for manual 1024-byte alignment
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), LBO = 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------ math
+// silu(z) = z sigmoid(z) = h + h tanh(h), h = z/2: one MUFU.TANH + 2 FMA-pipe ops
+__device__ __forceinline__ float silu_fast(float z) {
+  float h = 0.5f * z, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+// byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+struct Params {
+  // stage 1
+  const __nv_bfloat16* AB;   // [N, 512] bf16: A (+b1) | B
+  const float* x;            // [N, 3]
+  const float* wd;           // [256]
+  const int32_t* row;        // [E]
+  const int32_t* col;        // [E]
+  float* agg;                // [N, 256] (+=)
+  __nv_bfloat16* v_out;      // [E, 256]
+  // stage 2
+  const __nv_bfloat16* v_in; // [E, 256]
+  const float* w6;           // [256]
+  const float* b6;           // [1]
+  float* w_out;              // [E] (+=)
+  __nv_bfloat16* s_out;      // [E, 256] or null
+  // both
+  const void* Wp;            // packed weight image
+  const float* bias;         // [256] (b2 or b5)
+  int64_t E;
+  int num_tiles;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem + SmemLayout::W_OFF;
+  uint8_t* sA = smem + SmemLayout::A_OFF;
+  float* sBias = reinterpret_cast<float*>(smem + SmemLayout::VEC_OFF);
+  float* sVec1 = sBias + H;    // stage 1: wd      stage 2: w6
+  float* sMeta = reinterpret_cast<float*>(smem + SmemLayout::META_OFF);   // [2][128][3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::BAR_OFF);
+  uint64_t* full_bar = bars;                         // [NUM_STAGES]
+  uint64_t* empty_bar = bars + NUM_STAGES;           // [NUM_STAGES]
+  uint64_t* tfull_bar = bars + 2 * NUM_STAGES;       // [2]
+  uint64_t* tempty_bar = bars + 2 * NUM_STAGES + 2;  // [2]
+  uint64_t* w_bar = bars + 2 * NUM_STAGES + 4;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NUM_STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
+    sBias[k] = p.bias[k];
+    sVec1[k] = (STAGE == 1) ? p.wd[k] : p.w6[k];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(&full_bar[s], NUM_PROD_THREADS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], NUM_EPI_THREADS);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == MMA_WARP) {
+    // ===================================================================== weight load + MMA issue
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, W_BYTES);
+      for (int i = 0; i < W_BYTES / 16384; ++i)
+        bulk_g2s(sW + i * 16384, reinterpret_cast<const uint8_t*>(p.Wp) + i * 16384, 16384, w_bar);
+      mbar_wait(w_bar, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * H;
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * STAGE_BYTES);
+          const uint32_t b_base = smem_u32(sW + kc * (H * KCHUNK * 2));
+#pragma unroll
+          for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
+            umma_bf16(d_tmem, umma_desc(a_base + ks * UMMA_K * 2), umma_desc(b_base + ks * UMMA_K * 2),
+                      (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);          // frees the ring slot once these MMAs have read it
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp > MMA_WARP) {
+    // ===================================================================== producers
+    const int pt = threadIdx.x - 32 * (MMA_WARP + 1);       // 0..255
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int64_t e0 = (int64_t)tile * TILE_M;
+      float* meta = sMeta + (it & 1) * TILE_M * 3;
+      if (STAGE == 1) {
+        if (pt < TILE_M) {
+          const int64_t e = e0 + pt;
+          int r = -1, c = -1;
+          float d2 = 0.f;
+          if (e < p.E) {
+            r = p.row[e];
+            c = p.col[e];
+            const float dx = p.x[3 * (int64_t)r] - p.x[3 * (int64_t)c];
+            const float dy = p.x[3 * (int64_t)r + 1] - p.x[3 * (int64_t)c + 1];
+            const float dz = p.x[3 * (int64_t)r + 2] - p.x[3 * (int64_t)c + 2];
+            d2 = dx * dx + dy * dy + dz * dz;
+          }
+          meta[3 * pt] = __int_as_float(r);
+          meta[3 * pt + 1] = __int_as_float(c);
+          meta[3 * pt + 2] = d2;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      }
+      for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = sA + stage * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < (TILE_M * 8) / NUM_PROD_THREADS; ++i) {
+          const int cidx = pt + NUM_PROD_THREADS * i;
+          const int r = cidx >> 3, chunk = cidx & 7;
+          const int k0 = kc * KCHUNK + chunk * 8;             // first feature of this 16-byte chunk
+          uint4 out = make_uint4(0u, 0u, 0u, 0u);
+          if (STAGE == 1) {
+            const int nr = __float_as_int(meta[3 * r]);
+            if (nr >= 0) {
+              const int nc = __float_as_int(meta[3 * r + 1]);
+              const float d2 = meta[3 * r + 2];
+              const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.AB + (int64_t)nr * 2 * H + k0));
+              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.AB + (int64_t)nc * 2 * H + H + k0));
+              const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float u0 = bf16_lo(aw[j]) + bf16_lo(bw[j]) + sVec1[k0 + 2 * j] * d2;
+                const float u1 = bf16_hi(aw[j]) + bf16_hi(bw[j]) + sVec1[k0 + 2 * j + 1] * d2;
+                o[j] = pack_bf16(silu_fast(u0), silu_fast(u1));
+              }
+              out = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            const int64_t e = e0 + r;
+            if (e < p.E) {
+              const uint4 vv = __ldg(reinterpret_cast<const uint4*>(p.v_in + e * H + k0));
+              const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = pack_bf16(silu_fast(bf16_lo(vw[j])), silu_fast(bf16_hi(vw[j])));
+              out = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
+        }
+        fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(&full_bar[stage]);
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue
+    const int q = warp & 3, half = warp >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
+      const bool valid = e < p.E;
+      int dest = -1;
+      if (STAGE == 1 && valid) dest = p.row[e];
+      float dot = 0.f;
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        const int col0 = half * 128 + cb * 32;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + col0), raw);
+        float val[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[col0 + j];
+        if (STAGE == 1) {
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.v_out + e * H + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(val[8 * j], val[8 * j + 1]), pack_bf16(val[8 * j + 2], val[8 * j + 3]),
+                                  pack_bf16(val[8 * j + 4], val[8 * j + 5]), pack_bf16(val[8 * j + 6], val[8 * j + 7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = silu_fast(val[j]);
+          // segmented sum over the warp's 32 edges: one butterfly transpose-reduce per distinct destination
+          uint32_t todo = __ballot_sync(0xffffffffu, valid);
+          while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int d0 = __shfl_sync(0xffffffffu, dest, leader);
+            const bool mine = valid && dest == d0;
+            const uint32_t seg = __ballot_sync(0xffffffffu, mine);
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = mine ? val[j] : 0.f;
+#pragma unroll
+            for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+              const bool up = (lane & ofs) != 0;
+#pragma unroll
+              for (int j = 0; j < ofs; ++j) {
+                const float keep = up ? w[j + ofs] : w[j];
+                const float send = up ? w[j] : w[j + ofs];
+                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+              }
+            }
+            atomicAdd(p.agg + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
+            todo &= ~seg;
+          }
+        } else {
+          if (p.s_out && valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.s_out + e * H + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(val[8 * j], val[8 * j + 1]), pack_bf16(val[8 * j + 2], val[8 * j + 3]),
+                                  pack_bf16(val[8 * j + 4], val[8 * j + 5]), pack_bf16(val[8 * j + 6], val[8 * j + 7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dot = fmaf(silu_fast(val[j]), sVec1[col0 + j], dot);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);               // accumulator stage drained
+      if (STAGE == 2 && valid) atomicAdd(p.w_out + e, dot + (half == 0 ? __ldg(p.b6) : 0.f));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// fp32 [256,256] (out,in) -> bf16 image of the resident B operand: 4 K-blocks of [256 rows x 128 B],
+// 128-byte swizzle.  transpose != 0 packs W^T (for the dgrad GEMMs).
+__global__ void pack_weight_kernel(const float* __restrict__ W, int transpose, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * H) return;
+  const int n = idx / H, k = idx % H;
+  const float v = transpose ? W[k * H + n] : W[n * H + k];
+  const int kb = k / KCHUNK, kl = k % KCHUNK;
+  const uint32_t byte = kb * (H * KCHUNK * 2) + sw128_offset(n, kl >> 3) + (kl & 7) * 2;
+  out[byte >> 1] = __float2bfloat16(v);
+}
+
+static int launch_cfg(int64_t E, int* num_tiles, int* grid) {
+  *num_tiles = (int)((E + TILE_M - 1) / TILE_M);
+  const int sms = sm_count();
+  *grid = *num_tiles < sms ? *num_tiles : sms;
+  return 0;
+}
+
+template <int STAGE>
+static int launch(const Params& p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(edge_mlp_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(2, "edge_mlp_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  edge_mlp_kernel<STAGE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+  return after_launch(STAGE == 1 ? "edge_mlp_kernel<1>" : "edge_mlp_kernel<2>");
+}
+
+}  // namespace tc
+}  // namespace pev
+
+using namespace pev;
+
+extern "C" {
+
+int pev_pack_weight_bf16(const float* W, int32_t transpose, void* packed, void* stream) {
+  PEV_REQUIRE(W && packed, "null argument");
+  tc::pack_weight_kernel<<<(tc::H * tc::H + 255) / 256, 256, 0, as_stream(stream)>>>(
+      W, transpose, reinterpret_cast<__nv_bfloat16*>(packed));
+  return after_launch("pack_weight_kernel");
+}
+
+int pev_edge_mlp1_fwd_bf16(const void* AB, const float* x, const float* wd, const void* W2p, const float* b2,
+                           const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges,
+                           void* v_out, float* agg, void* stream) {
+  PEV_REQUIRE(AB && x && wd && W2p && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc::H * (size_t)num_nodes, st);
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(row && col && v_out, "edge arrays missing");
+  tc::Params p = {};
+  p.AB = reinterpret_cast<const __nv_bfloat16*>(AB);
+  p.x = x; p.wd = wd; p.row = row; p.col = col; p.agg = agg;
+  p.v_out = reinterpret_cast<__nv_bfloat16*>(v_out);
+  p.Wp = W2p; p.bias = b2; p.E = num_edges;
+  int grid;
+  tc::launch_cfg(num_edges, &p.num_tiles, &grid);
+  return tc::launch<1>(p, grid, st);
+}
+
+int pev_edge_mlp2_fwd_bf16(const void* v, const void* W5p, const float* b5, const float* w6, const float* b6,
+                           int64_t num_edges, float* w_out, void* s_out, void* stream) {
+  PEV_REQUIRE(W5p && b5 && w6 && b6 && num_edges >= 0, "bad argument");
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(v && w_out, "edge arrays missing");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
+  tc::Params p = {};
+  p.v_in = reinterpret_cast<const __nv_bfloat16*>(v);
+  p.w6 = w6; p.b6 = b6; p.w_out = w_out;
+  p.s_out = reinterpret_cast<__nv_bfloat16*>(s_out);
+  p.Wp = W5p; p.bias = b5; p.E = num_edges;
+  int grid;
+  tc::launch_cfg(num_edges, &p.num_tiles, &grid);
+  return tc::launch<2>(p, grid, st);
+}
+
+}  // extern "C"

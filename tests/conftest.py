@@ -30,8 +30,8 @@ def pytest_collection_modifyitems(config, items):
 def rel_err(a, b):
     """max|a-b| / max|b|  -- the tolerance metric used everywhere."""
     import numpy as np
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a = np.asarray(a.detach().cpu() if hasattr(a, "detach") else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if hasattr(b, "detach") else b, dtype=np.float64)
     den = max(float(np.abs(b).max()) if b.size else 0.0, 1e-30)
     return float(np.abs(a - b).max()) / den if b.size else 0.0
 
@@ -42,7 +42,7 @@ def assert_close_cond(mine, gold64, oracle32=None, tol=1e-5, slack=8.0, what="")
     float64 value (e.g. d sin/d cos = -c / sqrt(1 - c^2 + 1e-8) near |c| = 1) the bound grows to
     `slack` times that deviation."""
     import numpy as np
-    to_np = lambda a: np.asarray(a.detach() if hasattr(a, "detach") else a, dtype=np.float64)  # noqa: E731
+    to_np = lambda a: np.asarray(a.detach().cpu() if hasattr(a, "detach") else a, dtype=np.float64)  # noqa: E731
     mine, gold64 = to_np(mine), to_np(gold64)
     bound = tol * max(float(np.abs(gold64).max()) if gold64.size else 0.0, 1e-30) * np.ones_like(gold64)
     if oracle32 is not None:
@@ -66,3 +66,33 @@ def assert_named_close(mine, ref, tol=1e-5, max_outliers=2, outlier_tol=1e-2):
         allowed = max_outliers + int(0.002 * err.size)      # one flipped unit touches a whole weight row
         assert int((err > tol).sum()) <= allowed, (k, int((err > tol).sum()), float(err.max()))
         assert float(err.max()) if err.size else 0.0 <= outlier_tol, (k, float(err.max()))
+
+
+class Backend:
+    """'host': CPU tensors against tests/hostcheck (kernel bodies compiled with g++);
+    'cuda': CUDA tensors against libpev_b200.so -- the product path."""
+
+    def __init__(self, kind):
+        self.kind = kind
+        self.dev = "cpu" if kind == "host" else "cuda"
+
+    def ctx(self):
+        import contextlib
+        if self.kind == "host":
+            from hostlib import host_backend
+            return host_backend()
+        return contextlib.nullcontext()
+
+    def t32(self, a):
+        import numpy as np
+        import torch
+        return torch.tensor(np.asarray(a, dtype=np.float32), device=self.dev)
+
+    def ti(self, a):
+        import torch
+        return torch.as_tensor(a).to(self.dev)
+
+
+@pytest.fixture(params=["host", pytest.param("cuda", marks=pytest.mark.gpu)])
+def bk(request):
+    return Backend(request.param)

@@ -7,12 +7,11 @@ import torch
 import cases
 import synth
 from conftest import assert_close_cond, rel_err
-from hostlib import host_backend
 from oracle import losses_oracle
 
 import os
 G = os.path.join(os.path.dirname(__file__), "golden")
-T32 = lambda a: torch.tensor(np.asarray(a, dtype=np.float32))  # noqa: E731
+C32 = lambda a: torch.tensor(np.asarray(a, dtype=np.float32))  # noqa: E731  (CPU, oracle side)
 T64 = lambda a: torch.tensor(np.asarray(a, dtype=np.float64))  # noqa: E731
 
 
@@ -27,42 +26,44 @@ def assert_dihedrals_close(t, g):
     assert np.abs(t - g)[well].max() < 2e-5
 
 
-def run_total(mod, d, tdih, stride, make, requires_grad=True):
+def run_total(mod, d, tdih, stride, make, requires_grad=True, dev="cpu"):
     leaves = {k: make(d[k]).requires_grad_(requires_grad) for k in cases.GRAD_INPUTS}
     res = mod.compute_total_loss(
         leaves["pred_N"], leaves["pred_CA"], leaves["pred_C"], leaves["pred_seq"],
-        make(d["target_N"]), make(d["target_CA"]), make(d["target_C"]), torch.tensor(d["labels"]),
+        make(d["target_N"]), make(d["target_CA"]), make(d["target_C"]), torch.tensor(d["labels"]).to(dev),
         make(d["mask"]), leaves["mu_g"], leaves["lv_g"], leaves["mu_l"], leaves["lv_l"], tdih,
         pair_stride=stride, **cases.LOSS_WEIGHTS)
     return res, leaves
 
 
 @pytest.mark.parametrize("tag", list(cases.LOSS_CASES))
-def test_total_loss_and_grads_host(tag):
+def test_total_loss_and_grads_host(tag, bk):
+    T32 = bk.t32
     from protein_ensemble_vae_b200 import losses as pl
     gold = np.load(os.path.join(G, "losses.npz"))
     case = cases.LOSS_CASES[tag]
     d = cases.loss_inputs(case)
-    with host_backend():
+    with bk.ctx():
         tdih = pl.compute_dihedrals_from_coords(T32(d["target_N"]), T32(d["target_CA"]), T32(d["target_C"]),
                                                 T32(d["mask"]))
-        assert_dihedrals_close(tdih, gold[f"{tag}.target_dihedrals"])
+        assert_dihedrals_close(tdih.cpu(), gold[f"{tag}.target_dihedrals"])
         for stride in case[5]:
-            res, leaves = run_total(pl, d, tdih, stride, T32)
+            res, leaves = run_total(pl, d, tdih, stride, T32, dev=bk.dev)
             assert tuple(res) == losses_oracle.LOSS_KEYS
             for k, v in res.items():
                 ref = float(gold[f"{tag}.s{stride}.{k}"])
                 assert abs(float(v.detach()) - ref) <= 1e-5 * max(abs(ref), 1e-3), (k, float(v.detach()), ref)
             res["total"].backward()
             tdih32 = losses_oracle.compute_dihedrals_from_coords(
-                T32(d["target_N"]), T32(d["target_CA"]), T32(d["target_C"]), T32(d["mask"]))
-            r32, l32 = run_total(losses_oracle, d, tdih32, stride, T32)
+                C32(d["target_N"]), C32(d["target_CA"]), C32(d["target_C"]), C32(d["mask"]))
+            r32, l32 = run_total(losses_oracle, d, tdih32, stride, C32)
             r32["total"].backward()
             for k, v in leaves.items():
                 assert_close_cond(v.grad, gold[f"{tag}.s{stride}.grad.{k}"], l32[k].grad, what=k)
 
 
-def test_individual_losses_host():
+def test_individual_losses_host(bk):
+    T32 = bk.t32
     from protein_ensemble_vae_b200 import losses as pl
     d = cases.loss_inputs(cases.LOSS_CASES["walk"])
     m64, m32 = T64(d["mask"]), T32(d["mask"])
@@ -72,7 +73,7 @@ def test_individual_losses_host():
 
     def both(fn_name, args64, args32, **kw):
         o = getattr(losses_oracle, fn_name)(*args64, **kw)
-        with host_backend():
+        with bk.ctx():
             p = getattr(pl, fn_name)(*args32, **kw)
             g64 = torch.autograd.grad(o, [a for a in args64 if a.requires_grad], allow_unused=True)
             g32 = torch.autograd.grad(p, [a for a in args32 if a.requires_grad], allow_unused=True)
@@ -99,25 +100,25 @@ def test_individual_losses_host():
     both("kl_global", (mg64, lg64), (mg32, lg32))
     lo64, lo32 = T64(d["pred_seq"]).requires_grad_(), T32(d["pred_seq"]).requires_grad_()
     lab = torch.tensor(d["labels"])
-    both("sequence_classification_loss", (lo64, lab, m64), (lo32, lab, m32))
+    both("sequence_classification_loss", (lo64, lab, m64), (lo32, lab.to(bk.dev), m32))
     # dihedral-space functions on explicit tensors, and compute_dihedrals' own backward
     dih64 = losses_oracle.compute_dihedrals_from_coords(a64["pred_N"], a64["pred_CA"], a64["pred_C"], m64)
     tdh64 = losses_oracle.compute_dihedrals_from_coords(a64["target_N"], a64["target_CA"], a64["target_C"], m64).detach()
-    with host_backend():
+    with bk.ctx():
         dih32 = pl.compute_dihedrals_from_coords(a32["pred_N"], a32["pred_CA"], a32["pred_C"], m32)
-    assert_dihedrals_close(dih32, dih64)
+    assert_dihedrals_close(dih32.cpu(), dih64)
     coef = T64(np.random.default_rng(3).standard_normal(dih64.shape))
     g64 = torch.autograd.grad((dih64 * coef).sum(), [a64["pred_N"], a64["pred_CA"], a64["pred_C"]], retain_graph=True)
-    with host_backend():
-        g32 = torch.autograd.grad((dih32 * coef.float()).sum(), [a32["pred_N"], a32["pred_CA"], a32["pred_C"]])
-    o32 = {k: T32(d[k]).requires_grad_() for k in ("pred_N", "pred_CA", "pred_C")}
-    dih_o32 = losses_oracle.compute_dihedrals_from_coords(o32["pred_N"], o32["pred_CA"], o32["pred_C"], m32)
+    with bk.ctx():
+        g32 = torch.autograd.grad((dih32 * coef.float().to(bk.dev)).sum(), [a32["pred_N"], a32["pred_CA"], a32["pred_C"]])
+    o32 = {k: C32(d[k]).requires_grad_() for k in ("pred_N", "pred_CA", "pred_C")}
+    dih_o32 = losses_oracle.compute_dihedrals_from_coords(o32["pred_N"], o32["pred_CA"], o32["pred_C"], C32(d["mask"]))
     go32 = torch.autograd.grad((dih_o32 * coef.float()).sum(), list(o32.values()))
     for x, y, z in zip(g32, g64, go32):
         assert_close_cond(x, y, z, tol=2e-5)
     d64 = dih64.detach().clone().requires_grad_()
-    d32 = dih64.detach().float().requires_grad_()
-    both("dihedral_consistency_loss", (d64, tdh64, m64), (d32, tdh64.float(), m32))
+    d32 = dih64.detach().float().to(bk.dev).requires_grad_()
+    both("dihedral_consistency_loss", (d64, tdh64, m64), (d32, tdh64.float().to(bk.dev), m32))
     both("ramachandran_loss", (d64, m64), (d32, m32))
     both("omega_trans_loss", (d64, m64), (d32, m32))
 
