@@ -1,0 +1,320 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: EGNN decoder fwd+bwd + compute_total_loss fwd+bwd (train) and
+decoder fwd + Kabsch RMSD (decode), on synthetic backbone ensembles.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One JSON line on stdout (rank 0).  ``value`` = train conformers/s with the batch resident in HBM
+(BASELINE.json metric, configs[1]: L=256, 6 EGNN layers, 256 conformers per GPU, bf16 edge MLP);
+``e2e`` = the same step fed from pinned host buffers through the public module / loss API with the
+H2D copies and the loss read-back inside the timed region; ``decode`` = decoded conformers/s
+(configs[3] shape: L=100, 8 layers, + Kabsch RMSD against one reference structure).
+``--impl reference`` times the CPU restatement of the reference (``oracle/``) on the host cores for
+the same metric/config on a bounded sample (the reference itself is Python and cannot travel).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+LOSS_W = dict(klw_g=1.0, klw_l=0.5, w_pair=10.0, pair_stride=8, w_dihedral=20.0, w_rama=400.0, w_bond=500.0,
+              w_angle=500.0, w_rec=10.0, w_seq=50.0, w_clash=300.0)             # models/vae.py:39-50
+CFG = dict(L=256, layers=6, batch_per_gpu=256, z_g=512, z_l=256, hidden=256, max_neighbors=40, dropout=0.1)
+DECODE = dict(L=100, layers=8, chunk=2048, z_g=512, z_l=256)
+
+
+def synth_batch(B, L, z_g, z_l, seed, device="cpu", pin=False):
+    """Synthetic inputs of SURVEY.md 8(d): latents, random-walk targets, labels, posterior stats."""
+    g = torch.Generator().manual_seed(seed)
+    ca = torch.cumsum(torch.randn(B, L, 3, generator=g) * 2.2, 1)
+    ca = ca - ca.mean(1, keepdim=True)
+    d = dict(
+        z_g=torch.randn(B, z_g, generator=g), z_l=torch.randn(B, L, z_l, generator=g),
+        target_CA=ca, target_N=ca + 0.8 * torch.randn(B, L, 3, generator=g),
+        target_C=ca + 0.8 * torch.randn(B, L, 3, generator=g),
+        labels=torch.randint(0, 20, (B, L), generator=g), mask=torch.ones(B, L),
+        mu_g=torch.randn(B, z_g, generator=g), lv_g=0.1 * torch.randn(B, z_g, generator=g),
+        mu_l=torch.randn(B, L, z_l, generator=g), lv_l=0.1 * torch.randn(B, L, z_l, generator=g))
+    if pin:
+        d = {k: v.pin_memory() for k, v in d.items()}
+    if device != "cpu":
+        d = {k: v.to(device) for k, v in d.items()}
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(B, cfg):
+    """One train step of the CPU restatement (oracle port, fp32): decoder fwd + total loss + backward."""
+    import synth
+    from oracle import egnn_oracle, losses_oracle
+    params = synth.make_params(synth.decoder_param_shapes(cfg["z_g"], cfg["z_l"], cfg["hidden"], cfg["layers"]), 0)
+    sd = {k: torch.tensor(v).requires_grad_() for k, v in params.items()}
+    d = synth_batch(B, cfg["L"], cfg["z_g"], cfg["z_l"], seed=0)
+    tdih = losses_oracle.compute_dihedrals_from_coords(d["target_N"], d["target_CA"], d["target_C"], d["mask"])
+    cache = {}
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        n, ca, c, lg = egnn_oracle.egnn_decoder(sd, d["z_g"], d["z_l"], d["mask"], max_neighbors=cfg["max_neighbors"],
+                                                edge_cache=cache)
+        res = losses_oracle.compute_total_loss(n, ca, c, lg, d["target_N"], d["target_CA"], d["target_C"], d["labels"],
+                                               d["mask"], d["mu_g"], d["lv_g"], d["mu_l"], d["lv_l"], tdih, **LOSS_W)
+        res["total"].backward()
+        return float(res["total"])
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = 2
+    step = cpu_step_fn(B, CFG)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    sample = f"{B} conformers per step (of {CFG['batch_per_gpu']}), L={CFG['L']}, {CFG['layers']} layers, fp32, oracle port"
+    out = {"impl": "reference", "metric": "train_conformers_per_s", "value": val, "unit": "conformers/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": workload_config(args.gpus),
+           "cpu_baseline": {"value": val, "unit": "conformers/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": val, "unit": "conformers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: single protein L=256, 6 EGNN layers (hidden 256, W=40), 256 conformers per GPU, "
+                        "decoder fwd+bwd + compute_total_loss fwd+bwd + Adam step, bf16 edge MLP",
+            "L": CFG["L"], "layers": CFG["layers"], "batch_per_gpu": CFG["batch_per_gpu"],
+            "global_batch": CFG["batch_per_gpu"] * n_gpus, "parallelism": f"dp{n_gpus}",
+            "cache": "inputs_larger_than_l2 (603 MB of latents/posteriors + 5 GB of per-edge activations per layer)"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    from protein_ensemble_vae_b200 import EGNNDecoder, _lib, compute_total_loss, kabsch_rmsd_batch
+    from protein_ensemble_vae_b200 import losses as pl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    B, L = CFG["batch_per_gpu"], CFG["L"]
+
+    torch.manual_seed(0)
+    dec = EGNNDecoder(CFG["z_g"], CFG["z_l"], hidden_dim=CFG["hidden"], num_layers=CFG["layers"],
+                      max_neighbors=CFG["max_neighbors"], dropout=CFG["dropout"], precision="bf16").to(dev).train()
+    params = [p for p in dec.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    host = synth_batch(B, L, CFG["z_g"], CFG["z_l"], seed=rank, pin=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    tdih = pl.compute_dihedrals_from_coords(resident["target_N"], resident["target_CA"], resident["target_C"],
+                                            resident["mask"])
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(d):
+        outs = dec(d["z_g"], d["z_l"], d["mask"])
+        res = compute_total_loss(outs[0], outs[1], outs[2], outs[3], d["target_N"], d["target_CA"], d["target_C"],
+                                 d["labels"], d["mask"], d["mu_g"], d["lv_g"], d["mu_l"], d["lv_l"], tdih, **LOSS_W)
+        res["total"].backward()
+        if world > 1:       # data parallel over conformers: average the decoder gradients (17.8 MB) over NVLink
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return res["total"]
+
+    def timed(fn, steps):
+        """max over ranks of the CUDA-event time of `steps` calls, barrier + synchronize on both sides."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.PROFILE = {}
+    n0 = lib.launch_count()
+    ms = timed(lambda: step(resident), args.steps)
+    launches = lib.launch_count() - n0
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    sampler.stop_flag = True
+    value = B * world * args.steps / (ms / 1e3)
+
+    # end to end: pinned host buffers -> device every step, loss read back every step
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        float(step(d))
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+
+    # decode: decoder forward (no grad) + Kabsch RMSD of every sample against one reference CA trace
+    dd = DECODE
+    dec8 = EGNNDecoder(dd["z_g"], dd["z_l"], hidden_dim=256, num_layers=dd["layers"], max_neighbors=40, dropout=0.1,
+                       precision="bf16").to(dev).eval()
+    S = dd["chunk"]
+    zg = torch.randn(S, dd["z_g"], device=dev)
+    zl = torch.randn(S, dd["L"], dd["z_l"], device=dev)
+    mask1 = torch.ones(S, dd["L"], device=dev)
+    ref_ca = resident["target_CA"][0, :dd["L"]].contiguous()
+
+    def decode_step():
+        with torch.no_grad():
+            n, ca, c, lg = dec8(zg, zl, mask1)
+            return kabsch_rmsd_batch(ca, ref_ca)
+    for _ in range(2):
+        decode_step()
+    dsteps = max(3, args.steps // 2)
+    ms_dec = timed(decode_step, dsteps)
+    decode = S * world * dsteps / (ms_dec / 1e3)
+
+    if rank == 0:
+        hbm, tf, which = peaks()
+        E = lib_edges(L) * B
+        roof = {"bound": "tensor", "kernel": "edge_mlp_kernel<1> (tcgen05 GEMM W2 + gather/SiLU/segment-sum)",
+                "achieved": None, "peak": tf, "unit": "TFLOP/s", "frac": None, "traffic": None, "peak_source": which}
+        ev = prof.get("edge_mlp1", []) if prof else []
+        if ev:
+            tot = sum(s.elapsed_time(e) for s, e in ev)
+            per = tot / len(ev)
+            roof["achieved"] = 2.0 * E * 256 * 256 / (per * 1e-3) / 1e12
+            roof["frac"] = roof["achieved"] / tf
+            roof["ms_per_launch"] = per
+            roof["launches_timed"] = len(ev)
+            roof["share_of_step"] = tot / ms
+        cpu = None
+        if not args.no_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            Bc = 2
+            cstep = cpu_step_fn(Bc, CFG)
+            cstep()
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 12):
+                cstep()
+                reps += 1
+            dtc = time.perf_counter() - t0
+            cpu = {"value": Bc * reps / dtc, "unit": "conformers/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{reps} steps of {Bc} conformers (of {B}), L={L}, {CFG['layers']} layers, fp32 oracle port"}
+        out = {"metric": "train_conformers_per_s", "value": value, "unit": "conformers/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": workload_config(world), "clocks": sampler.summary(),
+               "e2e": {"value": e2e, "unit": "conformers/s", "h2d_bytes_per_step": h2d_bytes * world,
+                       "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+               "decode": {"metric": "decoded_conformers_per_s", "value": decode, "unit": "conformers/s",
+                          "config": {"workload": "configs[3] shape: L=100, 8 EGNN layers, decoder fwd + Kabsch RMSD vs one "
+                                                 "reference, latent samples sharded across GPUs", "chunk_per_gpu": S},
+                          "ms_per_chunk": ms_dec / dsteps}}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def lib_edges(L, W=40):
+    from protein_ensemble_vae_b200.graph import band_edge_count
+    return band_edge_count(L, W)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,3 +131,27 @@ def f32c(t: torch.Tensor | None) -> torch.Tensor | None:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+# Optional per-kernel CUDA-event timing (bench.py sets PROFILE = {} around its timed region).
+PROFILE: dict | None = None
+
+
+class profiled:
+    """``with profiled(tag): <launch>`` records a CUDA-event pair on the current stream when PROFILE is a dict."""
+
+    def __init__(self, tag: str):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.setdefault(self.tag, []).append((self.a, self.b))
+        return False

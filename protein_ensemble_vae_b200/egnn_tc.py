@@ -21,7 +21,6 @@ from ._lib import f32c, ptr, stream
 from .graph import PackedGraph
 
 H = 256
-_PACK_CACHE: dict = {}
 
 
 def supports(layer) -> bool:
@@ -29,19 +28,21 @@ def supports(layer) -> bool:
             and all(isinstance(layer.phi_e[i], nn.SiLU) for i in (1, 3)) and isinstance(layer.phi_x[1], nn.SiLU))
 
 
-def packed_weight(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
-    """bf16 swizzled image of a 256x256 weight (the resident tcgen05 B operand); cached per version."""
-    key = (W.data_ptr(), W._version, bool(transpose), str(W.device))
-    hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
+def packed_weight(W: torch.Tensor, transpose: bool = False, cache: dict | None = None) -> torch.Tensor:
+    """bf16 swizzled image of a 256x256 weight (the resident tcgen05 B operand).
+
+    ``cache`` (a dict owned by the module that owns ``W``) avoids repacking while the parameter is
+    unchanged; it is keyed on the parameter's in-place version counter and storage pointer.
+    """
+    key = ("T" if transpose else "N", W.data_ptr(), W._version)
+    if cache is not None and cache.get("key" + key[0]) == key:
+        return cache["img" + key[0]]
     Wc = f32c(W.detach())
     with torch.cuda.device_of(Wc):
         out = torch.empty(H * H, dtype=torch.bfloat16, device=W.device)
         _lib.lib().call("pev_pack_weight_bf16", ptr(Wc), int(transpose), ptr(out), stream(Wc))
-    if len(_PACK_CACHE) > 256:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = out
+    if cache is not None:
+        cache["key" + key[0]], cache["img" + key[0]] = key, out
     return out
 
 
@@ -54,7 +55,7 @@ class FusedEdgeBF16(torch.autograd.Function):
     """(AB, x, wd, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3])."""
 
     @staticmethod
-    def forward(ctx, AB, x, wd, W2, b2, W5, b5, w6, b6, dinv, g: PackedGraph, keep: bool):
+    def forward(ctx, AB, x, wd, W2, b2, W5, b5, w6, b6, dinv, g: PackedGraph, keep: bool, caches):
         L = _lib.lib()
         x, wd, b2, b5 = f32c(x), f32c(wd), f32c(b2), f32c(b5)
         w6v, b6v = f32c(w6).reshape(-1), f32c(b6).reshape(-1)
@@ -63,16 +64,18 @@ class FusedEdgeBF16(torch.autograd.Function):
         with torch.cuda.device_of(x):
             dev = x.device
             ABh = AB.detach().to(torch.bfloat16).contiguous()
-            W2p, W5p = packed_weight(W2), packed_weight(W5)
+            W2p, W5p = packed_weight(W2, cache=caches[0]), packed_weight(W5, cache=caches[1])
             v = torch.empty(E, H, dtype=torch.bfloat16, device=dev)
             s = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
             agg = torch.empty(N, H, dtype=torch.float32, device=dev)
             w = torch.empty(E, dtype=torch.float32, device=dev)
             x_out = torch.empty_like(x)
             st = stream(x)
-            L.call("pev_edge_mlp1_fwd_bf16", ptr(ABh), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row), ptr(g.col),
-                   N, E, ptr(v), ptr(agg), st)
-            L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(s), st)
+            with _lib.profiled("edge_mlp1"):
+                L.call("pev_edge_mlp1_fwd_bf16", ptr(ABh), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row),
+                       ptr(g.col), N, E, ptr(v), ptr(agg), st)
+            with _lib.profiled("edge_mlp2"):
+                L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(s), st)
             L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
                    None, ptr(x_out), st)
         ctx.g = g
@@ -132,7 +135,7 @@ class FusedEdgeBF16(torch.autograd.Function):
                 gx.index_add_(0, r, grel)
                 gx.index_add_(0, c, -grel)
             gb6 = gw.sum().reshape(1)
-        return (gAB, gx, gwd, gW2, gb2, gW5, gb5, gw6.reshape(1, H), gb6, None, None, None)
+        return (gAB, gx, gwd, gW2, gb2, gW5, gb5, gw6.reshape(1, H), gb6, None, None, None, None)
 
 
 def egn_layer_bf16(layer, h, x, g: PackedGraph, dinv):
@@ -141,10 +144,11 @@ def egn_layer_bf16(layer, h, x, g: PackedGraph, dinv):
     Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                      # [512, 256]
     bias = torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
     AB = torch.addmm(bias, h, Wcat.t())                                   # [N, 512]
+    caches = layer.__dict__.setdefault("_pev_packed", ({}, {}))
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
     agg, x_new = FusedEdgeBF16.apply(AB, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
                                      layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
-                                     layer.phi_x[2].bias, dinv, g, keep)
+                                     layer.phi_x[2].bias, dinv, g, keep, caches)
     h_new = layer.norm_h(h + layer.phi_h(torch.cat([h, agg], -1)))
     return h_new, x_new
