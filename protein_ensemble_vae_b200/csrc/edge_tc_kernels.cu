@@ -1,9 +1,13 @@
 // K1, bf16 tensor-core form: the EGNN edge MLP (models/en_gnn_decoder.py:60-79) on tcgen05.
 //
-// One persistent, warp-specialised kernel template, instantiated twice:
+// One persistent, warp-specialised kernel template, instantiated four times (SURVEY.md 8a math):
 //   STAGE 1  a = silu(A_i + B_j + wd d2)  --GEMM W2-->  v = . + b2 ; v -> HBM (bf16), m = silu(v),
 //            agg[row] += m   (segmented butterfly reduction per warp, RED.ADD.F32 per segment)
 //   STAGE 2  m = silu(v)                  --GEMM W5-->  s = . + b5 ; t = silu(s), w[e] = t . w6 + b6
+//   STAGE 3  gs = gw w6 silu'(s)          --GEMM W5^T-> gm = . + gagg[row] ; gv = gm silu'(v) -> HBM
+//            (column sums db5 = sum gs, dW6 = sum gw t accumulated in the producers' registers)
+//   STAGE 4  gv                           --GEMM W2^T-> ga ; gu = ga silu'(u) -> HBM, gd2[e] = gu . wd
+//            (column sum db2 = sum gv in the producers)
 // Tile = 128 consecutive edges (rows of the GEMM) x N = 256 x K = 256.
 //   * the 256x256 bf16 weight stays resident in shared memory for the whole kernel (128 KB,
 //     K-major, 128-byte swizzle), fetched once per CTA with cp.async.bulk (TMA, no tensor map);
@@ -149,26 +153,63 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
 }
 
 struct Params {
-  // stage 1
-  const __nv_bfloat16* AB;   // [N, 512] bf16: A (+b1) | B
-  const float* x;            // [N, 3]
-  const float* wd;           // [256]
-  const int32_t* row;        // [E]
-  const int32_t* col;        // [E]
-  float* agg;                // [N, 256] (+=)
-  __nv_bfloat16* v_out;      // [E, 256]
-  // stage 2
-  const __nv_bfloat16* v_in; // [E, 256]
-  const float* w6;           // [256]
-  const float* b6;           // [1]
-  float* w_out;              // [E] (+=)
-  __nv_bfloat16* s_out;      // [E, 256] or null
-  // both
-  const void* Wp;            // packed weight image
-  const float* bias;         // [256] (b2 or b5)
+  // graph / node inputs
+  const float* AB;           // [N, 512] fp32: A (+b1) | B            (stages 1, 4)
+  const float* x;            // [N, 3]                                (stages 1, 4)
+  const int32_t* row;        // [E]                                   (stages 1, 3, 4)
+  const int32_t* col;        // [E]                                   (stages 1, 4)
+  const float* vec1;         // [256]: wd (stages 1, 4), w6 (stages 2, 3)
+  const float* bias;         // [256]: b2 (stage 1), b5 (stage 2), unused otherwise
+  const void* Wp;            // packed weight image (W2, W5, W5^T, W2^T)
+  // per-edge streams
+  const __nv_bfloat16* in0;  // stage 2: v; stage 3: s; stage 4: gv
+  const __nv_bfloat16* in1;  // stage 3: v (epilogue)
+  const float* ein;          // stage 3: gw[E]
+  const float* nin;          // stage 3: gagg[N,256]
+  __nv_bfloat16* out0;       // stage 1: v; stage 2: s (or null); stage 3: gv; stage 4: gu
+  __nv_bfloat16* out1;       // stage 1: a (or null); stage 2: m (or null); stage 3: gs
+  float* eout;               // stage 2: w[E] (+=); stage 4: gd2[E] (+=)
+  float* nout;               // stage 1: agg[N,256] (+=)
+  float* csum0;              // [256] (+=): stage 3 db5; stage 4 db2
+  float* csum1;              // [256] (+=): stage 3 dW6
+  const float* b6;           // [1] stage 2
   int64_t E;
   int num_tiles;
 };
+
+// silu(z) and d silu / dz from one tanh: sg = sigmoid(z) = 0.5 + 0.5 tanh(z/2)
+__device__ __forceinline__ void silu_and_grad(float z, float& f, float& df) {
+  float h = 0.5f * z, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  const float sg = fmaf(0.5f, t, 0.5f);
+  f = z * sg;
+  df = fmaf(f, 1.0f - sg, sg);
+}
+__device__ __forceinline__ float silu_grad(float z) {
+  float f, df;
+  silu_and_grad(z, f, df);
+  return df;
+}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&val)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    d[j] = make_uint4(pack_bf16(val[8 * j], val[8 * j + 1]), pack_bf16(val[8 * j + 2], val[8 * j + 3]),
+                      pack_bf16(val[8 * j + 4], val[8 * j + 5]), pack_bf16(val[8 * j + 6], val[8 * j + 7]));
+}
+__device__ __forceinline__ void load_f32x8(const float* src, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float (&o)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+  o[0] = bf16_lo(v.x); o[1] = bf16_hi(v.x); o[2] = bf16_lo(v.y); o[3] = bf16_hi(v.y);
+  o[4] = bf16_lo(v.z); o[5] = bf16_hi(v.z); o[6] = bf16_lo(v.w); o[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+  return make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+}
 
 template <int STAGE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p) {
@@ -176,8 +217,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem + SmemLayout::W_OFF;
   uint8_t* sA = smem + SmemLayout::A_OFF;
-  float* sBias = reinterpret_cast<float*>(smem + SmemLayout::VEC_OFF);
-  float* sVec1 = sBias + H;    // stage 1: wd      stage 2: w6
+  float* sBias = reinterpret_cast<float*>(smem + SmemLayout::VEC_OFF);   // stage 3: column-sum scratch (db5)
+  float* sVec1 = sBias + H;
+  float* sRed = sBias + 2 * H;                                            // column-sum scratch
   float* sMeta = reinterpret_cast<float*>(smem + SmemLayout::META_OFF);   // [2][128][3]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::BAR_OFF);
   uint64_t* full_bar = bars;                         // [NUM_STAGES]
@@ -190,8 +232,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
-    sBias[k] = p.bias[k];
-    sVec1[k] = (STAGE == 1) ? p.wd[k] : p.w6[k];
+    sBias[k] = (STAGE <= 2) ? p.bias[k] : 0.f;
+    sVec1[k] = p.vec1[k];
+    sRed[k] = 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
@@ -244,65 +287,96 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   } else if (warp > MMA_WARP) {
     // ===================================================================== producers
     const int pt = threadIdx.x - 32 * (MMA_WARP + 1);       // 0..255
+    const int chunk = pt & 7;                               // fixed 16-byte column chunk of this thread
     int stage = 0, it = 0;
     uint32_t phase = 0;
+    float cs0[NUM_KCHUNKS][8], cs1[NUM_KCHUNKS][8];         // per-thread column sums (stages 3, 4)
+#pragma unroll
+    for (int a = 0; a < NUM_KCHUNKS; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs0[a][j] = cs1[a][j] = 0.f;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int64_t e0 = (int64_t)tile * TILE_M;
       float* meta = sMeta + (it & 1) * TILE_M * 3;
-      if (STAGE == 1) {
+      if (STAGE == 1 || STAGE == 3) {
         if (pt < TILE_M) {
           const int64_t e = e0 + pt;
-          int r = -1, c = -1;
-          float d2 = 0.f;
-          if (e < p.E) {
-            r = p.row[e];
-            c = p.col[e];
-            const float dx = p.x[3 * (int64_t)r] - p.x[3 * (int64_t)c];
-            const float dy = p.x[3 * (int64_t)r + 1] - p.x[3 * (int64_t)c + 1];
-            const float dz = p.x[3 * (int64_t)r + 2] - p.x[3 * (int64_t)c + 2];
-            d2 = dx * dx + dy * dy + dz * dz;
+          if (STAGE == 1) {
+            int r = -1, c = -1;
+            float d2 = 0.f;
+            if (e < p.E) {
+              r = p.row[e];
+              c = p.col[e];
+              const float dx = p.x[3 * (int64_t)r] - p.x[3 * (int64_t)c];
+              const float dy = p.x[3 * (int64_t)r + 1] - p.x[3 * (int64_t)c + 1];
+              const float dz = p.x[3 * (int64_t)r + 2] - p.x[3 * (int64_t)c + 2];
+              d2 = dx * dx + dy * dy + dz * dz;
+            }
+            meta[3 * pt] = __int_as_float(r);
+            meta[3 * pt + 1] = __int_as_float(c);
+            meta[3 * pt + 2] = d2;
+          } else {
+            meta[3 * pt] = e < p.E ? p.ein[e] : 0.f;
           }
-          meta[3 * pt] = __int_as_float(r);
-          meta[3 * pt + 1] = __int_as_float(c);
-          meta[3 * pt + 2] = d2;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       }
+#pragma unroll
       for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = sA + stage * STAGE_BYTES;
+        const int k0 = kc * KCHUNK + chunk * 8;               // first feature of this thread's chunk
 #pragma unroll
         for (int i = 0; i < (TILE_M * 8) / NUM_PROD_THREADS; ++i) {
-          const int cidx = pt + NUM_PROD_THREADS * i;
-          const int r = cidx >> 3, chunk = cidx & 7;
-          const int k0 = kc * KCHUNK + chunk * 8;             // first feature of this 16-byte chunk
+          const int r = (pt >> 3) + (NUM_PROD_THREADS / 8) * i;
+          const int64_t e = e0 + r;
           uint4 out = make_uint4(0u, 0u, 0u, 0u);
           if (STAGE == 1) {
             const int nr = __float_as_int(meta[3 * r]);
             if (nr >= 0) {
               const int nc = __float_as_int(meta[3 * r + 1]);
               const float d2 = meta[3 * r + 2];
-              const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.AB + (int64_t)nr * 2 * H + k0));
-              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.AB + (int64_t)nc * 2 * H + H + k0));
-              const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
-              uint32_t o[4];
+              float a8[8], b8[8];
+              load_f32x8(p.AB + (int64_t)nr * 2 * H + k0, a8);
+              load_f32x8(p.AB + (int64_t)nc * 2 * H + H + k0, b8);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float u0 = bf16_lo(aw[j]) + bf16_lo(bw[j]) + sVec1[k0 + 2 * j] * d2;
-                const float u1 = bf16_hi(aw[j]) + bf16_hi(bw[j]) + sVec1[k0 + 2 * j + 1] * d2;
-                o[j] = pack_bf16(silu_fast(u0), silu_fast(u1));
+              for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * d2);
+              out = pack8(a8);
+              if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+            }
+          } else if (STAGE == 2) {
+            if (e < p.E) {
+              float v8[8];
+              load_bf16x8(p.in0 + e * H + k0, v8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v8[j] = silu_fast(v8[j]);
+              out = pack8(v8);
+              if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+            }
+          } else if (STAGE == 3) {
+            if (e < p.E) {
+              const float gw = meta[3 * r];
+              float s8[8];
+              load_bf16x8(p.in0 + e * H + k0, s8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float t, dt;
+                silu_and_grad(s8[j], t, dt);
+                const float gs = gw * sVec1[k0 + j] * dt;
+                cs0[kc][j] += gs;
+                cs1[kc][j] = fmaf(gw, t, cs1[kc][j]);
+                s8[j] = gs;
               }
-              out = make_uint4(o[0], o[1], o[2], o[3]);
+              out = pack8(s8);
+              *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
             }
           } else {
-            const int64_t e = e0 + r;
             if (e < p.E) {
-              const uint4 vv = __ldg(reinterpret_cast<const uint4*>(p.v_in + e * H + k0));
-              const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
-              uint32_t o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = pack_bf16(silu_fast(bf16_lo(vw[j])), silu_fast(bf16_hi(vw[j])));
-              out = make_uint4(o[0], o[1], o[2], o[3]);
+              out = __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + k0));
+              cs0[kc][0] += bf16_lo(out.x); cs0[kc][1] += bf16_hi(out.x);
+              cs0[kc][2] += bf16_lo(out.y); cs0[kc][3] += bf16_hi(out.y);
+              cs0[kc][4] += bf16_lo(out.z); cs0[kc][5] += bf16_hi(out.z);
+              cs0[kc][6] += bf16_lo(out.w); cs0[kc][7] += bf16_hi(out.w);
             }
           }
           *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
@@ -312,6 +386,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (STAGE >= 3) {
+      // column sums: registers -> shared atomics (32 threads per column) -> one global atomic per column
+#pragma unroll
+      for (int kc = 0; kc < NUM_KCHUNKS; ++kc)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&sRed[kc * KCHUNK + chunk * 8 + j], cs0[kc][j]);
+          if (STAGE == 3) atomicAdd(&sBias[kc * KCHUNK + chunk * 8 + j], cs1[kc][j]);
+        }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      atomicAdd(p.csum0 + pt, sRed[pt]);
+      if (STAGE == 3) atomicAdd(p.csum1 + pt, sBias[pt]);
+    }
   } else {
     // ===================================================================== epilogue
     const int q = warp & 3, half = warp >> 2;
@@ -320,9 +407,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
       const int acc = it & 1;
       const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
       const bool valid = e < p.E;
-      int dest = -1;
-      if (STAGE == 1 && valid) dest = p.row[e];
-      float dot = 0.f;
+      int dest = -1, src = 0;
+      float d2 = 0.f, dot = 0.f;
+      if (STAGE != 2 && valid) dest = p.row[e];
+      if (STAGE == 4 && valid) {
+        src = p.col[e];
+        const float dx = p.x[3 * (int64_t)dest] - p.x[3 * (int64_t)src];
+        const float dy = p.x[3 * (int64_t)dest + 1] - p.x[3 * (int64_t)src + 1];
+        const float dz = p.x[3 * (int64_t)dest + 2] - p.x[3 * (int64_t)src + 2];
+        d2 = dx * dx + dy * dy + dz * dz;
+      }
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -334,13 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
 #pragma unroll
         for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[col0 + j];
         if (STAGE == 1) {
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.v_out + e * H + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(val[8 * j], val[8 * j + 1]), pack_bf16(val[8 * j + 2], val[8 * j + 3]),
-                                  pack_bf16(val[8 * j + 4], val[8 * j + 5]), pack_bf16(val[8 * j + 6], val[8 * j + 7]));
-          }
+          if (valid) store_bf16x32(p.out0 + e * H + col0, val);
 #pragma unroll
           for (int j = 0; j < 32; ++j) val[j] = silu_fast(val[j]);
           // segmented sum over the warp's 32 edges: one butterfly transpose-reduce per distinct destination
@@ -363,24 +451,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                 w[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
               }
             }
-            atomicAdd(p.agg + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
+            atomicAdd(p.nout + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
             todo &= ~seg;
           }
-        } else {
-          if (p.s_out && valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.s_out + e * H + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(val[8 * j], val[8 * j + 1]), pack_bf16(val[8 * j + 2], val[8 * j + 3]),
-                                  pack_bf16(val[8 * j + 4], val[8 * j + 5]), pack_bf16(val[8 * j + 6], val[8 * j + 7]));
-          }
+        } else if (STAGE == 2) {
+          if (p.out0 && valid) store_bf16x32(p.out0 + e * H + col0, val);
 #pragma unroll
           for (int j = 0; j < 32; ++j) dot = fmaf(silu_fast(val[j]), sVec1[col0 + j], dot);
+        } else if (STAGE == 3) {
+          if (valid) {
+            const float* ga = p.nin + (int64_t)dest * H + col0;
+            const __nv_bfloat16* vv = p.in1 + e * H + col0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              float g8[8], v8[8];
+              load_f32x8(ga + 8 * j8, g8);
+              load_bf16x8(vv + 8 * j8, v8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[8 * j8 + j] = (val[8 * j8 + j] + g8[j]) * silu_grad(v8[j]);
+            }
+            store_bf16x32(p.out0 + e * H + col0, val);
+          }
+        } else {
+          if (valid) {
+            const float* pa = p.AB + (int64_t)dest * 2 * H + col0;
+            const float* pb = p.AB + (int64_t)src * 2 * H + H + col0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              float a8[8], b8[8];
+              load_f32x8(pa + 8 * j8, a8);
+              load_f32x8(pb + 8 * j8, b8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float wdj = sVec1[col0 + 8 * j8 + j];
+                const float gu = val[8 * j8 + j] * silu_grad(a8[j] + b8[j] + wdj * d2);
+                val[8 * j8 + j] = gu;
+                dot = fmaf(gu, wdj, dot);
+              }
+            }
+            store_bf16x32(p.out0 + e * H + col0, val);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);               // accumulator stage drained
-      if (STAGE == 2 && valid) atomicAdd(p.w_out + e, dot + (half == 0 ? __ldg(p.b6) : 0.f));
+      if (STAGE == 2 && valid) atomicAdd(p.eout + e, dot + (half == 0 ? __ldg(p.b6) : 0.f));
+      if (STAGE == 4 && valid) atomicAdd(p.eout + e, dot);
     }
   }
 
@@ -404,72 +520,105 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int transpose, _
   out[byte >> 1] = __float2bfloat16(v);
 }
 
-static int launch_cfg(int64_t E, int* num_tiles, int* grid) {
-  *num_tiles = (int)((E + TILE_M - 1) / TILE_M);
-  const int sms = sm_count();
-  *grid = *num_tiles < sms ? *num_tiles : sms;
-  return 0;
-}
-
 template <int STAGE>
-static int launch(const Params& p, int grid, cudaStream_t st) {
+static int launch(Params& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(edge_mlp_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_error(2, "edge_mlp_kernel: %s", cudaGetErrorString(e));
     configured = true;
   }
+  p.num_tiles = (int)((p.E + TILE_M - 1) / TILE_M);
+  const int sms = sm_count();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   edge_mlp_kernel<STAGE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-  return after_launch(STAGE == 1 ? "edge_mlp_kernel<1>" : "edge_mlp_kernel<2>");
+  static const char* names[] = {"", "edge_mlp_kernel<1>", "edge_mlp_kernel<2>", "edge_mlp_kernel<3>", "edge_mlp_kernel<4>"};
+  return after_launch(names[STAGE]);
 }
 
 }  // namespace tc
 }  // namespace pev
 
 using namespace pev;
+typedef __nv_bfloat16 bf16_t;
 
 extern "C" {
 
 int pev_pack_weight_bf16(const float* W, int32_t transpose, void* packed, void* stream) {
   PEV_REQUIRE(W && packed, "null argument");
   tc::pack_weight_kernel<<<(tc::H * tc::H + 255) / 256, 256, 0, as_stream(stream)>>>(
-      W, transpose, reinterpret_cast<__nv_bfloat16*>(packed));
+      W, transpose, reinterpret_cast<bf16_t*>(packed));
   return after_launch("pack_weight_kernel");
 }
 
-int pev_edge_mlp1_fwd_bf16(const void* AB, const float* x, const float* wd, const void* W2p, const float* b2,
+int pev_edge_mlp1_fwd_bf16(const float* AB, const float* x, const float* wd, const void* W2p, const float* b2,
                            const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges,
-                           void* v_out, float* agg, void* stream) {
+                           void* v_out, void* a_out, float* agg, void* stream) {
   PEV_REQUIRE(AB && x && wd && W2p && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
   if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc::H * (size_t)num_nodes, st);
   if (num_edges == 0) return 0;
   PEV_REQUIRE(row && col && v_out, "edge arrays missing");
   tc::Params p = {};
-  p.AB = reinterpret_cast<const __nv_bfloat16*>(AB);
-  p.x = x; p.wd = wd; p.row = row; p.col = col; p.agg = agg;
-  p.v_out = reinterpret_cast<__nv_bfloat16*>(v_out);
+  p.AB = AB; p.x = x; p.vec1 = wd; p.row = row; p.col = col; p.nout = agg;
+  p.out0 = reinterpret_cast<bf16_t*>(v_out);
+  p.out1 = reinterpret_cast<bf16_t*>(a_out);
   p.Wp = W2p; p.bias = b2; p.E = num_edges;
-  int grid;
-  tc::launch_cfg(num_edges, &p.num_tiles, &grid);
-  return tc::launch<1>(p, grid, st);
+  return tc::launch<1>(p, st);
 }
 
 int pev_edge_mlp2_fwd_bf16(const void* v, const void* W5p, const float* b5, const float* w6, const float* b6,
-                           int64_t num_edges, float* w_out, void* s_out, void* stream) {
+                           int64_t num_edges, float* w_out, void* s_out, void* m_out, void* stream) {
   PEV_REQUIRE(W5p && b5 && w6 && b6 && num_edges >= 0, "bad argument");
   if (num_edges == 0) return 0;
   PEV_REQUIRE(v && w_out, "edge arrays missing");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   tc::Params p = {};
-  p.v_in = reinterpret_cast<const __nv_bfloat16*>(v);
-  p.w6 = w6; p.b6 = b6; p.w_out = w_out;
-  p.s_out = reinterpret_cast<__nv_bfloat16*>(s_out);
+  p.in0 = reinterpret_cast<const bf16_t*>(v);
+  p.vec1 = w6; p.b6 = b6; p.eout = w_out;
+  p.out0 = reinterpret_cast<bf16_t*>(s_out);
+  p.out1 = reinterpret_cast<bf16_t*>(m_out);
   p.Wp = W5p; p.bias = b5; p.E = num_edges;
-  int grid;
-  tc::launch_cfg(num_edges, &p.num_tiles, &grid);
-  return tc::launch<2>(p, grid, st);
+  return tc::launch<2>(p, st);
+}
+
+int pev_edge_mlp2_bwd_bf16(const void* s, const void* v, const float* gw, const float* w6, const void* W5tp,
+                           const float* gagg, const int32_t* row, int64_t num_edges, void* gs_out, void* gv_out,
+                           float* db5, float* dw6, void* stream) {
+  PEV_REQUIRE(w6 && W5tp && db5 && dw6 && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(db5, 0, sizeof(float) * tc::H, st);
+  cudaMemsetAsync(dw6, 0, sizeof(float) * tc::H, st);
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(s && v && gw && gagg && row && gs_out && gv_out, "edge arrays missing");
+  tc::Params p = {};
+  p.in0 = reinterpret_cast<const bf16_t*>(s);
+  p.in1 = reinterpret_cast<const bf16_t*>(v);
+  p.ein = gw; p.nin = gagg; p.row = row; p.vec1 = w6;
+  p.out0 = reinterpret_cast<bf16_t*>(gv_out);
+  p.out1 = reinterpret_cast<bf16_t*>(gs_out);
+  p.csum0 = db5; p.csum1 = dw6;
+  p.Wp = W5tp; p.E = num_edges;
+  return tc::launch<3>(p, st);
+}
+
+int pev_edge_mlp1_bwd_bf16(const void* gv, const void* W2tp, const float* AB, const float* x, const float* wd,
+                           const int32_t* row, const int32_t* col, int64_t num_edges, void* gu_out, float* gd2,
+                           float* db2, void* stream) {
+  PEV_REQUIRE(W2tp && AB && x && wd && db2 && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(db2, 0, sizeof(float) * tc::H, st);
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(gv && row && col && gu_out && gd2, "edge arrays missing");
+  cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
+  tc::Params p = {};
+  p.in0 = reinterpret_cast<const bf16_t*>(gv);
+  p.AB = AB; p.x = x; p.vec1 = wd; p.row = row; p.col = col;
+  p.out0 = reinterpret_cast<bf16_t*>(gu_out);
+  p.eout = gd2; p.csum0 = db2;
+  p.Wp = W2tp; p.E = num_edges;
+  return tc::launch<4>(p, st);
 }
 
 }  // extern "C"

@@ -8,8 +8,8 @@ Forward per layer over the packed batch::
     x'   = pev_scatter_coord_fwd(w, x, dinv)    exact-order coordinate update (K2)
     h'   = LayerNorm(h + phi_h([h, agg]))       node-level fp32 (cuBLAS + torch)
 
-The per-edge pre-activations ``v`` and ``s`` are kept in HBM as bf16 ``[E,256]`` for the backward
-pass (2.47 GB each per layer at L=256, B=256 -- sized for the 180 GB of a B200).
+For training the per-edge tensors ``a, v, m, s`` are kept in HBM as bf16 ``[E,256]`` for the backward
+pass (2.47 GB each per layer at L=256, B=256: 59 GB for 6 layers -- sized for the 180 GB of a B200).
 """
 from __future__ import annotations
 
@@ -46,94 +46,92 @@ def packed_weight(W: torch.Tensor, transpose: bool = False, cache: dict | None =
     return out
 
 
-def _silu_and_grad(z):
-    sg = torch.sigmoid(z)
-    return z * sg, sg * (1.0 + z * (1.0 - sg))
+def _wgrad(g_bf16: torch.Tensor, act_bf16: torch.Tensor) -> torch.Tensor:
+    """``g^T @ act`` over the edge dimension ([256,E] x [E,256]); plain library GEMM (cuBLAS bf16, fp32 out)."""
+    try:
+        return torch.mm(g_bf16.t(), act_bf16, out_dtype=torch.float32)
+    except TypeError:                                    # torch without mm(out_dtype=)
+        return torch.mm(g_bf16.t(), act_bf16).float()
 
 
 class FusedEdgeBF16(torch.autograd.Function):
-    """(AB, x, wd, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3])."""
+    """(AB, x, wd, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3]).
+
+    Forward: stage-1 and stage-2 tcgen05 kernels + the exact-order coordinate update.  When a backward
+    pass will follow, the per-edge tensors a, v, m, s are kept in HBM as bf16 [E,256].
+    Backward: K2 coordinate backward -> stage-3 kernel (gs, gv) -> stage-4 kernel (gu, gd2)
+    -> segmented row/column sums; the two weight gradients dW5 = gs^T m, dW2 = gv^T a are library GEMMs.
+    """
 
     @staticmethod
     def forward(ctx, AB, x, wd, W2, b2, W5, b5, w6, b6, dinv, g: PackedGraph, keep: bool, caches):
         L = _lib.lib()
-        x, wd, b2, b5 = f32c(x), f32c(wd), f32c(b2), f32c(b5)
+        AB, x, wd, b2, b5 = f32c(AB.detach()), f32c(x), f32c(wd), f32c(b2), f32c(b5)
         w6v, b6v = f32c(w6).reshape(-1), f32c(b6).reshape(-1)
         dinv = f32c(dinv)
         N, E = g.num_nodes, g.num_edges
+        bf = torch.bfloat16
         with torch.cuda.device_of(x):
             dev = x.device
-            ABh = AB.detach().to(torch.bfloat16).contiguous()
             W2p, W5p = packed_weight(W2, cache=caches[0]), packed_weight(W5, cache=caches[1])
-            v = torch.empty(E, H, dtype=torch.bfloat16, device=dev)
-            s = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
+            v = torch.empty(E, H, dtype=bf, device=dev)
+            a, m, s = (torch.empty(E, H, dtype=bf, device=dev) if keep else None for _ in range(3))
             agg = torch.empty(N, H, dtype=torch.float32, device=dev)
             w = torch.empty(E, dtype=torch.float32, device=dev)
             x_out = torch.empty_like(x)
             st = stream(x)
             with _lib.profiled("edge_mlp1"):
-                L.call("pev_edge_mlp1_fwd_bf16", ptr(ABh), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row),
-                       ptr(g.col), N, E, ptr(v), ptr(agg), st)
+                L.call("pev_edge_mlp1_fwd_bf16", ptr(AB), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row),
+                       ptr(g.col), N, E, ptr(v), ptr(a), ptr(agg), st)
             with _lib.profiled("edge_mlp2"):
-                L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(s), st)
+                L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(s),
+                       ptr(m), st)
             L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
                    None, ptr(x_out), st)
-        ctx.g = g
-        ctx.save_for_backward(ABh, x, wd, W2, W5, w6v, dinv, v, s, w)
+        ctx.g, ctx.caches = g, caches
+        ctx.save_for_backward(AB, x, wd, W2, W5, w6v, dinv, a, v, m, s, w)
         return agg, x_out
 
     @staticmethod
     def backward(ctx, gagg, gxo):
-        ABh, x, wd, W2, W5, w6v, dinv, v, s, w = ctx.saved_tensors
+        AB, x, wd, W2, W5, w6v, dinv, a, v, m, s, w = ctx.saved_tensors
         if s is None:
-            raise RuntimeError("FusedEdgeBF16 was run without keep=True; backward is unavailable")
+            raise RuntimeError("FusedEdgeBF16 ran with keep=False (no_grad); backward is unavailable")
         g = ctx.g
         N, E = g.num_nodes, g.num_edges
         gagg, gxo = f32c(gagg), f32c(gxo)
-        bf = torch.bfloat16
+        bf, f32 = torch.bfloat16, torch.float32
+        L = _lib.lib()
         with torch.cuda.device_of(x):
-            dev = x.device
-            gw = torch.empty(E, dtype=torch.float32, device=dev)
-            gx = torch.empty(N, 3, dtype=torch.float32, device=dev)
-            _lib.lib().call("pev_scatter_coord_bwd", None, ptr(gxo), ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr),
-                            ptr(g.row), ptr(g.col), ptr(g.col_ptr), ptr(g.csc_perm), N, E, H, None, ptr(gw),
-                            ptr(gx), stream(x))
-            # Interim dense backward (torch elementwise + cuBLAS bf16 GEMMs), chunked over edges.
-            W2b, W5b = W2.detach().to(bf), W5.detach().to(bf)
-            gAB = torch.zeros(N, 2 * H, dtype=torch.float32, device=dev)
-            gW2 = torch.zeros(H, H, dtype=torch.float32, device=dev)
-            gW5 = torch.zeros(H, H, dtype=torch.float32, device=dev)
-            gb2 = torch.zeros(H, dtype=torch.float32, device=dev)
-            gb5 = torch.zeros(H, dtype=torch.float32, device=dev)
-            gw6 = torch.zeros(H, dtype=torch.float32, device=dev)
-            gwd = torch.zeros(H, dtype=torch.float32, device=dev)
-            row, col = g.row.long(), g.col.long()
-            chunk = 1 << 19
-            for e0 in range(0, E, chunk):
-                e1 = min(E, e0 + chunk)
-                r, c = row[e0:e1], col[e0:e1]
-                t, dt = _silu_and_grad(s[e0:e1].float())
-                gs = gw[e0:e1, None] * w6v[None, :] * dt
-                gw6 += gw[e0:e1] @ t
-                gb5 += gs.sum(0)
-                m, dm = _silu_and_grad(v[e0:e1].float())
-                gsb = gs.to(bf)
-                gW5 += (gsb.t() @ m.to(bf)).float()
-                gv = ((gsb @ W5b).float() + gagg[r]) * dm
-                gb2 += gv.sum(0)
-                rel = x[r] - x[c]
-                d2 = (rel * rel).sum(-1, keepdim=True)
-                u = ABh[r, :H].float() + ABh[c, H:].float() + wd[None, :] * d2
-                a, da = _silu_and_grad(u)
-                gvb = gv.to(bf)
-                gW2 += (gvb.t() @ a.to(bf)).float()
-                gu = (gvb @ W2b).float() * da
-                gAB[:, :H].index_add_(0, r, gu)
-                gAB[:, H:].index_add_(0, c, gu)
-                gwd += (gu * d2).sum(0)
-                grel = (2.0 * (gu @ wd))[:, None] * rel
-                gx.index_add_(0, r, grel)
-                gx.index_add_(0, c, -grel)
+            dev, st = x.device, stream(x)
+            W5tp = packed_weight(W5, transpose=True, cache=ctx.caches[1])
+            W2tp = packed_weight(W2, transpose=True, cache=ctx.caches[0])
+            gw = torch.empty(E, dtype=f32, device=dev)
+            gx = torch.empty(N, 3, dtype=f32, device=dev)
+            L.call("pev_scatter_coord_bwd", None, ptr(gxo), ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.row),
+                   ptr(g.col), ptr(g.col_ptr), ptr(g.csc_perm), N, E, H, None, ptr(gw), ptr(gx), st)
+            gs = torch.empty(E, H, dtype=bf, device=dev)
+            gv = torch.empty(E, H, dtype=bf, device=dev)
+            gb5, gw6 = torch.empty(H, dtype=f32, device=dev), torch.empty(H, dtype=f32, device=dev)
+            with _lib.profiled("edge_mlp2_bwd"):
+                L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(v), ptr(gw), ptr(w6v), ptr(W5tp), ptr(gagg), ptr(g.row),
+                       E, ptr(gs), ptr(gv), ptr(gb5), ptr(gw6), st)
+            gW5 = _wgrad(gs, m)
+            del gs
+            gu = torch.empty(E, H, dtype=bf, device=dev)
+            gd2 = torch.empty(max(E, 1), dtype=f32, device=dev)
+            gb2 = torch.empty(H, dtype=f32, device=dev)
+            with _lib.profiled("edge_mlp1_bwd"):
+                L.call("pev_edge_mlp1_bwd_bf16", ptr(gv), ptr(W2tp), ptr(AB), ptr(x), ptr(wd), ptr(g.row), ptr(g.col),
+                       E, ptr(gu), ptr(gd2), ptr(gb2), st)
+            gW2 = _wgrad(gv, a)
+            del gv
+            gAB = torch.empty(N, 2 * H, dtype=f32, device=dev)
+            part = torch.empty(N, H, dtype=f32, device=dev)
+            with _lib.profiled("edge_prologue_bwd"):
+                L.call("pev_edge_prologue_bwd_bf16", ptr(gu), ptr(gd2), ptr(x), ptr(g.row_ptr), ptr(g.row), ptr(g.col),
+                       ptr(g.col_ptr), ptr(g.csc_perm), N, E, ptr(gAB), ptr(gx), ptr(part), st)
+            gwd = part.sum(0)
             gb6 = gw.sum().reshape(1)
         return (gAB, gx, gwd, gW2, gb2, gW5, gb5, gw6.reshape(1, H), gb6, None, None, None, None)
 

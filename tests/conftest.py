@@ -68,6 +68,21 @@ def assert_named_close(mine, ref, tol=1e-5, max_outliers=2, outlier_tol=1e-2):
         assert float(err.max()) if err.size else 0.0 <= outlier_tol, (k, float(err.max()))
 
 
+def assert_named_close_l2(mine, ref, tol):
+    """Per-tensor relative L2 error -- the meaningful metric for the bf16 path, where single ReLU / rounding
+    flips move individual elements by O(1) of their value but not the gradient as a whole."""
+    import numpy as np
+    assert set(mine) == set(ref), set(mine) ^ set(ref)
+    worst = ("", 0.0)
+    for k in sorted(ref):
+        a = np.asarray(mine[k].detach().cpu() if hasattr(mine[k], "detach") else mine[k], dtype=np.float64)
+        b = np.asarray(ref[k].detach().cpu() if hasattr(ref[k], "detach") else ref[k], dtype=np.float64)
+        err = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < tol, worst
+
+
 class Backend:
     """'host': CPU tensors against tests/hostcheck (kernel bodies compiled with g++);
     'cuda': CUDA tensors against libpev_b200.so -- the product path."""
