@@ -45,8 +45,8 @@ struct __align__(16) SmemLayout {
   // offsets into dynamic shared memory (base aligned to 1024)
   static constexpr int W_OFF = 0;
   static constexpr int A_OFF = W_BYTES;
-  static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 3 x 256 floats
-  static constexpr int META_OFF = VEC_OFF + 3 * H * 4;                  // 2 x 128 x (row,col,d2)
+  static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 4 x 256 floats
+  static constexpr int META_OFF = VEC_OFF + 4 * H * 4;                  // 2 x 128 x (row,col,d2)
   static constexpr int BAR_OFF = META_OFF + 2 * TILE_M * 12;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
@@ -217,9 +217,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem + SmemLayout::W_OFF;
   uint8_t* sA = smem + SmemLayout::A_OFF;
-  float* sBias = reinterpret_cast<float*>(smem + SmemLayout::VEC_OFF);   // stage 3: column-sum scratch (db5)
-  float* sVec1 = sBias + H;
-  float* sRed = sBias + 2 * H;                                            // column-sum scratch
+  float* sBias = reinterpret_cast<float*>(smem + SmemLayout::VEC_OFF);   // b2 / b5 (stages 1, 2)
+  float* sVec1 = sBias + H;                                               // wd / w6
+  float* sRed = sBias + 2 * H;                                            // column-sum scratch (stages 3, 4)
+  float* sRed2 = sBias + 3 * H;                                           // second column sum (stage 3)
   float* sMeta = reinterpret_cast<float*>(smem + SmemLayout::META_OFF);   // [2][128][3]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::BAR_OFF);
   uint64_t* full_bar = bars;                         // [NUM_STAGES]
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
     sBias[k] = (STAGE <= 2) ? p.bias[k] : 0.f;
     sVec1[k] = p.vec1[k];
     sRed[k] = 0.f;
+    sRed2[k] = 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
@@ -393,11 +395,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           atomicAdd(&sRed[kc * KCHUNK + chunk * 8 + j], cs0[kc][j]);
-          if (STAGE == 3) atomicAdd(&sBias[kc * KCHUNK + chunk * 8 + j], cs1[kc][j]);
+          if (STAGE == 3) atomicAdd(&sRed2[kc * KCHUNK + chunk * 8 + j], cs1[kc][j]);
         }
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       atomicAdd(p.csum0 + pt, sRed[pt]);
-      if (STAGE == 3) atomicAdd(p.csum1 + pt, sBias[pt]);
+      if (STAGE == 3) atomicAdd(p.csum1 + pt, sRed2[pt]);
     }
   } else {
     // ===================================================================== epilogue
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + col0), raw);
         float val[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[col0 + j];
+        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + (STAGE <= 2 ? sBias[col0 + j] : 0.f);
         if (STAGE == 1) {
           if (valid) store_bf16x32(p.out0 + e * H + col0, val);
 #pragma unroll
