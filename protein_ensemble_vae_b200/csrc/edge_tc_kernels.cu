@@ -288,15 +288,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
     __syncwarp();
   } else if (warp > MMA_WARP) {
     // ===================================================================== producers
+    // Thread pt owns the 16-byte column chunk (pt & 7) of rows (pt >> 3) + 32 i, i < 4, of every K-chunk.
+    // Global loads are issued one K-chunk ahead of their use (register double buffer) so that the
+    // L2 latency of the gather overlaps the SiLU / pack / st.shared work of the current chunk.
     const int pt = threadIdx.x - 32 * (MMA_WARP + 1);       // 0..255
-    const int chunk = pt & 7;                               // fixed 16-byte column chunk of this thread
+    const int chunk = pt & 7;
+    constexpr int RPT = (TILE_M * 8) / NUM_PROD_THREADS;    // rows per thread per K-chunk (4)
+    constexpr int RSTEP = NUM_PROD_THREADS / 8;             // 32
     int stage = 0, it = 0;
     uint32_t phase = 0;
-    float cs0[NUM_KCHUNKS][8], cs1[NUM_KCHUNKS][8];         // per-thread column sums (stages 3, 4)
-#pragma unroll
-    for (int a = 0; a < NUM_KCHUNKS; ++a)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cs0[a][j] = cs1[a][j] = 0.f;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int64_t e0 = (int64_t)tile * TILE_M;
       float* meta = sMeta + (it & 1) * TILE_M * 3;
@@ -323,62 +323,98 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       }
+      // per-row metadata of this thread's rows, held in registers for the whole tile
+      int nr[RPT], nc[RPT];
+      float rw[RPT];                                        // stage 1: d2; stage 3: gw
+      bool ok[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = (pt >> 3) + RSTEP * i;
+        ok[i] = (e0 + r) < p.E;
+        nr[i] = nc[i] = 0;
+        rw[i] = 0.f;
+        if (STAGE == 1) {
+          nr[i] = __float_as_int(meta[3 * r]);
+          nc[i] = __float_as_int(meta[3 * r + 1]);
+          rw[i] = meta[3 * r + 2];
+          ok[i] = nr[i] >= 0;
+        } else if (STAGE == 3) {
+          rw[i] = meta[3 * r];
+        }
+      }
+      // prefetch buffers: stage 1 -> fp32 B rows (2 x uint4 per row); others -> one bf16 uint4 per row
+      uint4 pf[2][RPT][STAGE == 1 ? 2 : 1];
+      auto issue_loads = [&](int kc, int buf) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int k0 = kc * KCHUNK + chunk * 8;
+          if (STAGE == 1) {
+            pf[buf][i][0] = pf[buf][i][STAGE == 1 ? 1 : 0] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[i]) {
+              const uint4* src = reinterpret_cast<const uint4*>(p.AB + (int64_t)nc[i] * 2 * H + H + k0);
+              pf[buf][i][0] = __ldg(src);
+              pf[buf][i][STAGE == 1 ? 1 : 0] = __ldg(src + 1);
+            }
+          } else {
+            const int r = (pt >> 3) + RSTEP * i;
+            pf[buf][i][0] = ok[i] ? __ldg(reinterpret_cast<const uint4*>(p.in0 + (e0 + r) * H + k0))
+                                  : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      };
+      issue_loads(0, 0);
 #pragma unroll
       for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+        if (kc + 1 < NUM_KCHUNKS) issue_loads(kc + 1, (kc + 1) & 1);
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = sA + stage * STAGE_BYTES;
         const int k0 = kc * KCHUNK + chunk * 8;               // first feature of this thread's chunk
+        float ls0[8], ls1[8];                                 // column sums over this thread's rows (stages 3, 4)
 #pragma unroll
-        for (int i = 0; i < (TILE_M * 8) / NUM_PROD_THREADS; ++i) {
-          const int r = (pt >> 3) + (NUM_PROD_THREADS / 8) * i;
+        for (int j = 0; j < 8; ++j) ls0[j] = ls1[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = (pt >> 3) + RSTEP * i;
           const int64_t e = e0 + r;
           uint4 out = make_uint4(0u, 0u, 0u, 0u);
-          if (STAGE == 1) {
-            const int nr = __float_as_int(meta[3 * r]);
-            if (nr >= 0) {
-              const int nc = __float_as_int(meta[3 * r + 1]);
-              const float d2 = meta[3 * r + 2];
-              float a8[8], b8[8];
-              load_f32x8(p.AB + (int64_t)nr * 2 * H + k0, a8);
-              load_f32x8(p.AB + (int64_t)nc * 2 * H + H + k0, b8);
+          if (ok[i]) {
+            if (STAGE == 1) {
+              float a8[8];
+              load_f32x8(p.AB + (int64_t)nr[i] * 2 * H + k0, a8);     // shared by the row's edges: L1 hit
+              const uint4 b0 = pf[kc & 1][i][0], b1 = pf[kc & 1][i][STAGE == 1 ? 1 : 0];
+              const float b8[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z),
+                                   __uint_as_float(b0.w), __uint_as_float(b1.x), __uint_as_float(b1.y),
+                                   __uint_as_float(b1.z), __uint_as_float(b1.w)};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * d2);
+              for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * rw[i]);
               out = pack8(a8);
               if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
-            }
-          } else if (STAGE == 2) {
-            if (e < p.E) {
-              float v8[8];
-              load_bf16x8(p.in0 + e * H + k0, v8);
+            } else {
+              const uint4 in = pf[kc & 1][i][0];
+              float v8[8] = {bf16_lo(in.x), bf16_hi(in.x), bf16_lo(in.y), bf16_hi(in.y),
+                             bf16_lo(in.z), bf16_hi(in.z), bf16_lo(in.w), bf16_hi(in.w)};
+              if (STAGE == 2) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v8[j] = silu_fast(v8[j]);
-              out = pack8(v8);
-              if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
-            }
-          } else if (STAGE == 3) {
-            if (e < p.E) {
-              const float gw = meta[3 * r];
-              float s8[8];
-              load_bf16x8(p.in0 + e * H + k0, s8);
+                for (int j = 0; j < 8; ++j) v8[j] = silu_fast(v8[j]);
+                out = pack8(v8);
+                if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+              } else if (STAGE == 3) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float t, dt;
-                silu_and_grad(s8[j], t, dt);
-                const float gs = gw * sVec1[k0 + j] * dt;
-                cs0[kc][j] += gs;
-                cs1[kc][j] = fmaf(gw, t, cs1[kc][j]);
-                s8[j] = gs;
+                for (int j = 0; j < 8; ++j) {
+                  float t, dt;
+                  silu_and_grad(v8[j], t, dt);
+                  const float gs = rw[i] * sVec1[k0 + j] * dt;
+                  ls0[j] += gs;
+                  ls1[j] = fmaf(rw[i], t, ls1[j]);
+                  v8[j] = gs;
+                }
+                out = pack8(v8);
+                *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+              } else {
+                out = in;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ls0[j] += v8[j];
               }
-              out = pack8(s8);
-              *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
-            }
-          } else {
-            if (e < p.E) {
-              out = __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + k0));
-              cs0[kc][0] += bf16_lo(out.x); cs0[kc][1] += bf16_hi(out.x);
-              cs0[kc][2] += bf16_lo(out.y); cs0[kc][3] += bf16_hi(out.y);
-              cs0[kc][4] += bf16_lo(out.z); cs0[kc][5] += bf16_hi(out.z);
-              cs0[kc][6] += bf16_lo(out.w); cs0[kc][7] += bf16_hi(out.w);
             }
           }
           *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
@@ -386,17 +422,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
         mbar_arrive(&full_bar[stage]);
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        if (STAGE >= 3) {
+          // lanes l, l^8, l^16, l^24 hold the same columns: fold them, then 8 lanes per warp add to shared
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 8);
+            ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 16);
+            if (STAGE == 3) {
+              ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 8);
+              ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 16);
+            }
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              atomicAdd(&sRed[k0 + j], ls0[j]);
+              if (STAGE == 3) atomicAdd(&sRed2[k0 + j], ls1[j]);
+            }
+          }
+        }
       }
     }
     if (STAGE >= 3) {
-      // column sums: registers -> shared atomics (32 threads per column) -> one global atomic per column
-#pragma unroll
-      for (int kc = 0; kc < NUM_KCHUNKS; ++kc)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&sRed[kc * KCHUNK + chunk * 8 + j], cs0[kc][j]);
-          if (STAGE == 3) atomicAdd(&sRed2[kc * KCHUNK + chunk * 8 + j], cs1[kc][j]);
-        }
+      // column sums: shared -> one global atomic per column per CTA
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       atomicAdd(p.csum0 + pt, sRed[pt]);
       if (STAGE == 3) atomicAdd(p.csum1 + pt, sRed2[pt]);

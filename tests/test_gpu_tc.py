@@ -162,7 +162,11 @@ def test_decoder_bf16_vs_oracle(tag):
     ref.update({k: v.grad for k, v in sd.items() if v.grad is not None})
     grads = {"z_g": zg_t.grad, "z_l": zl_t.grad}
     grads.update({k: p.grad for k, p in dec.named_parameters() if p.grad is not None})
-    assert_named_close_l2(grads, ref, tol=3e-2)
+    # 1e-1: at random init the gradients are ~10x more sensitive than the outputs -- sequence_head.0.weight,
+    # whose backward is plain fp32 torch in both paths, already differs by 4.5% (relative L2) when its input h
+    # carries the bf16 path's 0.5% forward error (tools/grad_diag.py).  The backward kernels themselves are
+    # held to 6e-3 against a same-rounding emulation in test_edge_mlp_kernels_match_bf16_emulation.
+    assert_named_close_l2(grads, ref, tol=1e-1)
 
 
 def test_no_grad_decode_keeps_nothing():
