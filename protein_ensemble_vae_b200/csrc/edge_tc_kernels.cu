@@ -30,7 +30,8 @@ constexpr int TILE_M = 128;            // edges per tile
 constexpr int KCHUNK = 64;             // bf16 elements per 128-byte swizzle row
 constexpr int NUM_KCHUNKS = H / KCHUNK;
 constexpr int UMMA_K = 16;
-constexpr int NUM_STAGES = 5;          // A-operand ring (16 KB each)
+constexpr int NUM_STAGES = 4;          // A-operand ring (16 KB each): one full tile in flight
+constexpr int NA = 8;                  // destination rows of a tile staged in shared memory (stage 1)
 constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
 constexpr int W_BYTES = H * H * 2;
 constexpr int NUM_EPI_WARPS = 8;       // warps 0..7   (TMEM lane quarter = warp % 4, column half = warp / 4)
@@ -46,8 +47,9 @@ struct __align__(16) SmemLayout {
   static constexpr int W_OFF = 0;
   static constexpr int A_OFF = W_BYTES;
   static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 4 x 256 floats
-  static constexpr int META_OFF = VEC_OFF + 4 * H * 4;                  // 2 x 128 x (row,col,d2)
-  static constexpr int BAR_OFF = META_OFF + 2 * TILE_M * 12;
+  static constexpr int META_OFF = VEC_OFF + 4 * H * 4;                  // 2 x 128 floats (d2 per tile row)
+  static constexpr int AROW_OFF = META_OFF + 2 * TILE_M * 4;            // 2 x NA x 256 floats (A rows of the tile)
+  static constexpr int BAR_OFF = AROW_OFF + 2 * NA * H * 4;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 constexpr int SMEM_BYTES = SmemLayout::TOTAL + 1024;   // slack for manual 1024-byte alignment
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   float* sVec1 = sBias + H;                                               // wd / w6
   float* sRed = sBias + 2 * H;                                            // column-sum scratch (stages 3, 4)
   float* sRed2 = sBias + 3 * H;                                           // second column sum (stage 3)
-  float* sMeta = reinterpret_cast<float*>(smem + SmemLayout::META_OFF);   // [2][128][3]
+  float* sMeta = reinterpret_cast<float*>(smem + SmemLayout::META_OFF);   // [2][128]
+  float* sArow = reinterpret_cast<float*>(smem + SmemLayout::AROW_OFF);   // [2][NA][256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::BAR_OFF);
   uint64_t* full_bar = bars;                         // [NUM_STAGES]
   uint64_t* empty_bar = bars + NUM_STAGES;           // [NUM_STAGES]
@@ -289,108 +292,164 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   } else if (warp > MMA_WARP) {
     // ===================================================================== producers
     // Thread pt owns the 16-byte column chunk (pt & 7) of rows (pt >> 3) + 32 i, i < 4, of every K-chunk.
-    // Global loads are issued one K-chunk ahead of their use (register double buffer) so that the
-    // L2 latency of the gather overlaps the SiLU / pack / st.shared work of the current chunk.
+    // All global loads are software-pipelined: edge indices one tile ahead, the tile's gathers (x, A rows,
+    // first B chunk) issued together at the top of the tile, later chunks one K-chunk ahead of their use.
     const int pt = threadIdx.x - 32 * (MMA_WARP + 1);       // 0..255
     const int chunk = pt & 7;
     constexpr int RPT = (TILE_M * 8) / NUM_PROD_THREADS;    // rows per thread per K-chunk (4)
     constexpr int RSTEP = NUM_PROD_THREADS / 8;             // 32
     int stage = 0, it = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int64_t e0 = (int64_t)tile * TILE_M;
-      float* meta = sMeta + (it & 1) * TILE_M * 3;
-      if (STAGE == 1 || STAGE == 3) {
-        if (pt < TILE_M) {
-          const int64_t e = e0 + pt;
-          if (STAGE == 1) {
-            int r = -1, c = -1;
-            float d2 = 0.f;
-            if (e < p.E) {
-              r = p.row[e];
-              c = p.col[e];
-              const float dx = p.x[3 * (int64_t)r] - p.x[3 * (int64_t)c];
-              const float dy = p.x[3 * (int64_t)r + 1] - p.x[3 * (int64_t)c + 1];
-              const float dz = p.x[3 * (int64_t)r + 2] - p.x[3 * (int64_t)c + 2];
-              d2 = dx * dx + dy * dy + dz * dz;
-            }
-            meta[3 * pt] = __int_as_float(r);
-            meta[3 * pt + 1] = __int_as_float(c);
-            meta[3 * pt + 2] = d2;
-          } else {
-            meta[3 * pt] = e < p.E ? p.ein[e] : 0.f;
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      }
-      // per-row metadata of this thread's rows, held in registers for the whole tile
-      int nr[RPT], nc[RPT];
-      float rw[RPT];                                        // stage 1: d2; stage 3: gw
-      bool ok[RPT];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int r = (pt >> 3) + RSTEP * i;
-        ok[i] = (e0 + r) < p.E;
-        nr[i] = nc[i] = 0;
-        rw[i] = 0.f;
-        if (STAGE == 1) {
-          nr[i] = __float_as_int(meta[3 * r]);
-          nc[i] = __float_as_int(meta[3 * r + 1]);
-          rw[i] = meta[3 * r + 2];
-          ok[i] = nr[i] >= 0;
-        } else if (STAGE == 3) {
-          rw[i] = meta[3 * r];
-        }
-      }
-      // prefetch buffers: stage 1 -> fp32 B rows (2 x uint4 per row); others -> one bf16 uint4 per row
-      uint4 pf[2][RPT][STAGE == 1 ? 2 : 1];
-      auto issue_loads = [&](int kc, int buf) {
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int k0 = kc * KCHUNK + chunk * 8;
-          if (STAGE == 1) {
-            pf[buf][i][0] = pf[buf][i][STAGE == 1 ? 1 : 0] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok[i]) {
-              const uint4* src = reinterpret_cast<const uint4*>(p.AB + (int64_t)nc[i] * 2 * H + H + k0);
-              pf[buf][i][0] = __ldg(src);
-              pf[buf][i][STAGE == 1 ? 1 : 0] = __ldg(src + 1);
-            }
-          } else {
-            const int r = (pt >> 3) + RSTEP * i;
-            pf[buf][i][0] = ok[i] ? __ldg(reinterpret_cast<const uint4*>(p.in0 + (e0 + r) * H + k0))
-                                  : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-      };
-      issue_loads(0, 0);
-#pragma unroll
-      for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
-        if (kc + 1 < NUM_KCHUNKS) issue_loads(kc + 1, (kc + 1) & 1);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = sA + stage * STAGE_BYTES;
-        const int k0 = kc * KCHUNK + chunk * 8;               // first feature of this thread's chunk
-        float ls0[8], ls1[8];                                 // column sums over this thread's rows (stages 3, 4)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ls0[j] = ls1[j] = 0.f;
+    if constexpr (STAGE == 1) {
+      struct TileIdx { int mr, mc, rf, rl, nr[RPT], nc[RPT]; };
+      auto load_idx = [&](int tile, TileIdx& t) {
+        const int64_t e0 = (int64_t)tile * TILE_M;
+        const int64_t rem = p.E - e0;
+        const int nvalid = rem < TILE_M ? (int)rem : TILE_M;
+        t.mr = t.mc = -1;
+        if (pt < nvalid) { t.mr = __ldg(p.row + e0 + pt); t.mc = __ldg(p.col + e0 + pt); }
+        t.rf = __ldg(p.row + e0);
+        t.rl = __ldg(p.row + e0 + nvalid - 1);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const int r = (pt >> 3) + RSTEP * i;
-          const int64_t e = e0 + r;
-          uint4 out = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[i]) {
-            if (STAGE == 1) {
+          t.nr[i] = t.nc[i] = -1;
+          if (r < nvalid) { t.nr[i] = __ldg(p.row + e0 + r); t.nc[i] = __ldg(p.col + e0 + r); }
+        }
+      };
+      TileIdx nxt;
+      load_idx(blockIdx.x, nxt);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const TileIdx cur = nxt;
+        if (tile + (int)gridDim.x < p.num_tiles) load_idx(tile + gridDim.x, nxt);
+        const int64_t e0 = (int64_t)tile * TILE_M;
+        float* meta = sMeta + (it & 1) * TILE_M;
+        float* arow = sArow + (it & 1) * NA * H;
+        const int span = cur.rl - cur.rf + 1;
+        const bool staged = span <= NA;
+        // ---- issue every gather of the tile prologue at once
+        float xr[3] = {0.f, 0.f, 0.f}, xc[3] = {0.f, 0.f, 0.f};
+        if (cur.mr >= 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            xr[k] = __ldg(p.x + 3 * (int64_t)cur.mr + k);
+            xc[k] = __ldg(p.x + 3 * (int64_t)cur.mc + k);
+          }
+        }
+        float4 ar[(NA * H / 4) / NUM_PROD_THREADS];
+#pragma unroll
+        for (int j = 0; j < (NA * H / 4) / NUM_PROD_THREADS; ++j) {
+          const int idx = pt + NUM_PROD_THREADS * j;
+          ar[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (staged && idx < span * (H / 4))
+            ar[j] = __ldg(reinterpret_cast<const float4*>(p.AB + (int64_t)(cur.rf + idx / (H / 4)) * 2 * H) + idx % (H / 4));
+        }
+        uint4 pf[2][RPT][2];
+        auto issue_b = [&](int kc, int buf) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            pf[buf][i][0] = pf[buf][i][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (cur.nc[i] >= 0) {
+              const uint4* src = reinterpret_cast<const uint4*>(p.AB + (int64_t)cur.nc[i] * 2 * H + H + kc * KCHUNK + chunk * 8);
+              pf[buf][i][0] = __ldg(src);
+              pf[buf][i][1] = __ldg(src + 1);
+            }
+          }
+        };
+        issue_b(0, 0);
+        // ---- publish d2 and the staged A rows
+        if (pt < TILE_M) {
+          const float dx = xr[0] - xc[0], dy = xr[1] - xc[1], dz = xr[2] - xc[2];
+          meta[pt] = dx * dx + dy * dy + dz * dz;
+        }
+#pragma unroll
+        for (int j = 0; j < (NA * H / 4) / NUM_PROD_THREADS; ++j)
+          reinterpret_cast<float4*>(arow)[pt + NUM_PROD_THREADS * j] = ar[j];
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+        float d2[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) d2[i] = meta[(pt >> 3) + RSTEP * i];
+#pragma unroll
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          if (kc + 1 < NUM_KCHUNKS) issue_b(kc + 1, (kc + 1) & 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = sA + stage * STAGE_BYTES;
+          const int k0 = kc * KCHUNK + chunk * 8;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = (pt >> 3) + RSTEP * i;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);
+            if (cur.nr[i] >= 0) {
               float a8[8];
-              load_f32x8(p.AB + (int64_t)nr[i] * 2 * H + k0, a8);     // shared by the row's edges: L1 hit
-              const uint4 b0 = pf[kc & 1][i][0], b1 = pf[kc & 1][i][STAGE == 1 ? 1 : 0];
+              if (staged) {
+                const float4* src = reinterpret_cast<const float4*>(arow + (cur.nr[i] - cur.rf) * H + k0);
+                const float4 a0 = src[0], a1 = src[1];
+                a8[0] = a0.x; a8[1] = a0.y; a8[2] = a0.z; a8[3] = a0.w;
+                a8[4] = a1.x; a8[5] = a1.y; a8[6] = a1.z; a8[7] = a1.w;
+              } else {
+                load_f32x8(p.AB + (int64_t)cur.nr[i] * 2 * H + k0, a8);
+              }
+              const uint4 b0 = pf[kc & 1][i][0], b1 = pf[kc & 1][i][1];
               const float b8[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z),
                                    __uint_as_float(b0.w), __uint_as_float(b1.x), __uint_as_float(b1.y),
                                    __uint_as_float(b1.z), __uint_as_float(b1.w)};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * rw[i]);
+              for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * d2[i]);
               out = pack8(a8);
-              if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
-            } else {
-              const uint4 in = pf[kc & 1][i][0];
+              if (p.out1) *reinterpret_cast<uint4*>(p.out1 + (e0 + r) * H + k0) = out;
+            }
+            *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
+          }
+          fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+      // streams (stages 2-4): one bf16 [E,256] input, no shared metadata, no producer barrier
+      uint4 pf[2][RPT];
+      float rw[2][RPT];                                     // stage 3: gw of this thread's rows
+      auto issue = [&](int tile, int kc, int buf) {
+        const int64_t e0 = (int64_t)tile * TILE_M;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int64_t e = e0 + (pt >> 3) + RSTEP * i;
+          pf[buf][i] = (e < p.E) ? __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + kc * KCHUNK + chunk * 8))
+                                 : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      auto issue_rw = [&](int tile, int buf) {
+        const int64_t e0 = (int64_t)tile * TILE_M;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int64_t e = e0 + (pt >> 3) + RSTEP * i;
+          rw[buf][i] = (STAGE == 3 && e < p.E) ? __ldg(p.ein + e) : 0.f;
+        }
+      };
+      issue_rw(blockIdx.x, 0);
+      issue(blockIdx.x, 0, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int64_t e0 = (int64_t)tile * TILE_M;
+        const int next_tile = tile + gridDim.x;
+        if (next_tile < p.num_tiles) issue_rw(next_tile, (it + 1) & 1);
+#pragma unroll
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          // NUM_KCHUNKS is even, so the prefetch buffer of chunk kc is always kc & 1
+          if (kc + 1 < NUM_KCHUNKS) issue(tile, kc + 1, (kc + 1) & 1);
+          else if (next_tile < p.num_tiles) issue(next_tile, 0, 0);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = sA + stage * STAGE_BYTES;
+          const int k0 = kc * KCHUNK + chunk * 8;
+          float ls0[8], ls1[8];                               // column sums over this thread's rows (stages 3, 4)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ls0[j] = ls1[j] = 0.f;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = (pt >> 3) + RSTEP * i;
+            const int64_t e = e0 + r;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);
+            if (e < p.E) {
+              const uint4 in = pf[kc & 1][i];
               float v8[8] = {bf16_lo(in.x), bf16_hi(in.x), bf16_lo(in.y), bf16_hi(in.y),
                              bf16_lo(in.z), bf16_hi(in.z), bf16_lo(in.w), bf16_hi(in.w)};
               if (STAGE == 2) {
@@ -399,13 +458,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                 out = pack8(v8);
                 if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
               } else if (STAGE == 3) {
+                const float gw = rw[it & 1][i];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   float t, dt;
                   silu_and_grad(v8[j], t, dt);
-                  const float gs = rw[i] * sVec1[k0 + j] * dt;
+                  const float gs = gw * sVec1[k0 + j] * dt;
                   ls0[j] += gs;
-                  ls1[j] = fmaf(rw[i], t, ls1[j]);
+                  ls1[j] = fmaf(gw, t, ls1[j]);
                   v8[j] = gs;
                 }
                 out = pack8(v8);
@@ -416,38 +476,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                 for (int j = 0; j < 8; ++j) ls0[j] += v8[j];
               }
             }
+            *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
           }
-          *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
-        }
-        fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
-        mbar_arrive(&full_bar[stage]);
-        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-        if (STAGE >= 3) {
-          // lanes l, l^8, l^16, l^24 hold the same columns: fold them, then 8 lanes per warp add to shared
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 8);
-            ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 16);
-            if (STAGE == 3) {
-              ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 8);
-              ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 16);
-            }
-          }
-          if (lane < 8) {
+          fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+          if (STAGE >= 3) {
+            // lanes l, l^8, l^16, l^24 hold the same columns: fold them, then 8 lanes per warp add to shared
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              atomicAdd(&sRed[k0 + j], ls0[j]);
-              if (STAGE == 3) atomicAdd(&sRed2[k0 + j], ls1[j]);
+              ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 8);
+              ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 16);
+              if (STAGE == 3) {
+                ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 8);
+                ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 16);
+              }
+            }
+            if (lane < 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                atomicAdd(&sRed[k0 + j], ls0[j]);
+                if (STAGE == 3) atomicAdd(&sRed2[k0 + j], ls1[j]);
+              }
             }
           }
         }
       }
-    }
-    if (STAGE >= 3) {
-      // column sums: shared -> one global atomic per column per CTA
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      atomicAdd(p.csum0 + pt, sRed[pt]);
-      if (STAGE == 3) atomicAdd(p.csum1 + pt, sRed2[pt]);
+      if (STAGE >= 3) {
+        // column sums: shared -> one global atomic per column per CTA
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+        atomicAdd(p.csum0 + pt, sRed[pt]);
+        if (STAGE == 3) atomicAdd(p.csum1 + pt, sRed2[pt]);
+      }
     }
   } else {
     // ===================================================================== epilogue
