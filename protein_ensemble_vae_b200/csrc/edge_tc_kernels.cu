@@ -34,10 +34,14 @@ constexpr int NUM_STAGES = 4;          // A-operand ring (16 KB each): one full 
 constexpr int NA = 8;                  // destination rows of a tile staged in shared memory (stage 1)
 constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
 constexpr int W_BYTES = H * H * 2;
+// Roles are aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
 constexpr int NUM_EPI_WARPS = 8;       // warps 0..7   (TMEM lane quarter = warp % 4, column half = warp / 4)
-constexpr int MMA_WARP = 8;            // warp 8       (TMEM alloc, weight load, MMA issue)
-constexpr int NUM_PROD_WARPS = 8;      // warps 9..16
-constexpr int NUM_THREADS = 32 * (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS);
+constexpr int MMA_WARP = 8;            // warp 8       (TMEM alloc, weight load, MMA issue); warps 9..11 idle
+constexpr int PROD_WARP0 = 12;         // warps 12..19 producers
+constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (PROD_WARP0 + NUM_PROD_WARPS);   // 640 -> 96 registers per thread at launch
+constexpr int REGS_MMA_WG = 32;        // setmaxnreg.dec in the MMA warpgroup frees 128 x 64 registers ...
+constexpr int REGS_PROD = 128;         // ... which the 256 producer threads take (96 -> 128)
 constexpr int NUM_PROD_THREADS = 32 * NUM_PROD_WARPS;
 constexpr int NUM_EPI_THREADS = 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
@@ -259,9 +263,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == MMA_WARP) {
+  if (warp >= MMA_WARP && warp < PROD_WARP0) {
     // ===================================================================== weight load + MMA issue
-    if (lane == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA_WG));
+    if (warp == MMA_WARP && lane == 0) {
       mbar_arrive_expect_tx(w_bar, W_BYTES);
       for (int i = 0; i < W_BYTES / 16384; ++i)
         bulk_g2s(sW + i * 16384, reinterpret_cast<const uint8_t*>(p.Wp) + i * 16384, 16384, w_bar);
@@ -289,12 +294,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
       }
     }
     __syncwarp();
-  } else if (warp > MMA_WARP) {
+  } else if (warp >= PROD_WARP0) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     // ===================================================================== producers
     // Thread pt owns the 16-byte column chunk (pt & 7) of rows (pt >> 3) + 32 i, i < 4, of every K-chunk.
     // All global loads are software-pipelined: edge indices one tile ahead, the tile's gathers (x, A rows,
     // first B chunk) issued together at the top of the tile, later chunks one K-chunk ahead of their use.
-    const int pt = threadIdx.x - 32 * (MMA_WARP + 1);       // 0..255
+    const int pt = threadIdx.x - 32 * PROD_WARP0;           // 0..255
     const int chunk = pt & 7;
     constexpr int RPT = (TILE_M * 8) / NUM_PROD_THREADS;    // rows per thread per K-chunk (4)
     constexpr int RSTEP = NUM_PROD_THREADS / 8;             // 32
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         if (STAGE == 3) atomicAdd(p.csum1 + pt, sRed2[pt]);
       }
     }
-  } else {
+  } else if (warp < NUM_EPI_WARPS) {
     // ===================================================================== epilogue
     const int q = warp & 3, half = warp >> 2;
     int it = 0;
