@@ -113,7 +113,7 @@ def cpu_step_fn(B, cfg):
         res = losses_oracle.compute_total_loss(n, ca, c, lg, d["target_N"], d["target_CA"], d["target_C"], d["labels"],
                                                d["mask"], d["mu_g"], d["lv_g"], d["mu_l"], d["lv_l"], tdih, **LOSS_W)
         res["total"].backward()
-        return float(res["total"])
+        return float(res["total"].detach())
     return step
 
 
@@ -154,6 +154,7 @@ def workload_config(n_gpus):
 def run_gpu(args):
     import torch.distributed as dist
     from protein_ensemble_vae_b200 import EGNNDecoder, _lib, compute_total_loss, kabsch_rmsd_batch
+    from protein_ensemble_vae_b200 import distributed as pdist
     from protein_ensemble_vae_b200 import losses as pl
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,15 +184,10 @@ def run_gpu(args):
                                  d["labels"], d["mask"], d["mu_g"], d["lv_g"], d["mu_l"], d["lv_l"], tdih, **LOSS_W)
         res["total"].backward()
         if world > 1:       # data parallel over conformers: average the decoder gradients (17.8 MB) over NVLink
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+            pdist.allreduce_gradients(params)
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return res["total"]
+        return res["total"].detach()
 
     def timed(fn, steps):
         """max over ranks of the CUDA-event time of `steps` calls, barrier + synchronize on both sides."""
@@ -256,8 +252,11 @@ def run_gpu(args):
     if rank == 0:
         hbm, tf, which = peaks()
         E = lib_edges(L) * B
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of edge_mlp_kernel<1> from the ncu --set full
+        # capture in profiles/ (1074.9 B per edge at B=32, training mode: it writes v and a as bf16), per launch
         roof = {"bound": "tensor", "kernel": "edge_mlp_kernel<1> (tcgen05 GEMM W2 + gather/SiLU/segment-sum)",
-                "achieved": None, "peak": tf, "unit": "TFLOP/s", "frac": None, "traffic": None, "peak_source": which}
+                "achieved": None, "peak": tf, "unit": "TFLOP/s", "frac": None, "traffic": 1074.9 * E,
+                "traffic_source": "profiles/r01_edge_kernels_ncu.md", "peak_source": which}
         ev = prof.get("edge_mlp1", []) if prof else []
         if ev:
             tot = sum(s.elapsed_time(e) for s, e in ev)
