@@ -113,24 +113,24 @@ int pev_edge_mlp1_fwd_bf16(const float* AB /*fp32 [N,512]*/, const float* x, con
                            const void* W2p, const float* b2, const int32_t* row, const int32_t* col,
                            int64_t num_nodes, int64_t num_edges, void* v_out /*bf16 [E,256]*/,
                            void* a_out /*bf16 [E,256] or NULL: a = silu(u), kept for dW2*/,
+                           void* da_out /*bf16 [E,256] or NULL (with a_out): silu'(u)*/,
                            float* agg /*[N,256]*/, void* stream);
 int pev_edge_mlp2_fwd_bf16(const void* v /*bf16 [E,256]*/, const void* W5p, const float* b5,
                            const float* w6, const float* b6 /*[1]*/, int64_t num_edges,
                            float* w_out /*[E]*/, void* s_out /*bf16 [E,256] or NULL*/,
                            void* m_out /*bf16 [E,256] or NULL: m = silu(v), kept for dW5*/,
-                           void* stream);
+                           void* dm_out /*bf16 [E,256] or NULL (with m_out): silu'(v)*/, void* stream);
 /* Backward of stage 2 (phi_x and the aggregation): gs = gw w6 silu'(s),
- * gm = gs W5 + gagg[row], gv = gm silu'(v).  W5tp = pev_pack_weight_bf16(W5, transpose=1).
- * Writes gs, gv (bf16 [E,256]) and the column sums db5[256] = sum_e gs, dw6[256] = sum_e gw silu(s)
- * (zeroed inside). */
-int pev_edge_mlp2_bwd_bf16(const void* s, const void* v, const float* gw /*[E]*/, const float* w6,
+ * gm = gs W5 + gagg[row], gv = gm dm with dm = silu'(v) as stored by the forward pass.
+ * W5tp = pev_pack_weight_bf16(W5, transpose=1).  Writes gs, gv (bf16 [E,256]) and the column sums
+ * db5[256] = sum_e gs, dw6[256] = sum_e gw silu(s) (zeroed inside). */
+int pev_edge_mlp2_bwd_bf16(const void* s, const void* dm, const float* gw /*[E]*/, const float* w6,
                            const void* W5tp, const float* gagg /*[N,256]*/, const int32_t* row,
                            int64_t num_edges, void* gs_out, void* gv_out, float* db5, float* dw6,
                            void* stream);
-/* Backward of stage 1: ga = gv W2, gu = ga silu'(u) with u rebuilt from AB/x; writes gu (bf16
- * [E,256]), gd2[e] = gu . wd and db2[256] = sum_e gv (both zeroed inside). */
-int pev_edge_mlp1_bwd_bf16(const void* gv, const void* W2tp, const float* AB, const float* x,
-                           const float* wd, const int32_t* row, const int32_t* col,
+/* Backward of stage 1: ga = gv W2, gu = ga da with da = silu'(u) as stored by the forward pass; writes
+ * gu (bf16 [E,256]), gd2[e] = gu . wd and db2[256] = sum_e gv (both zeroed inside). */
+int pev_edge_mlp1_bwd_bf16(const void* gv, const void* da, const void* W2tp, const float* wd,
                            int64_t num_edges, void* gu_out, float* gd2 /*[E]*/, float* db2,
                            void* stream);
 /* Segmented sums of the bf16 per-edge gradient gu over CSR rows and CSC columns (the bf16 twin of

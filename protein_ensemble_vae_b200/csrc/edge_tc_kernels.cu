@@ -138,6 +138,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------ math
 // silu(z) = z sigmoid(z) = h + h tanh(h), h = z/2: one MUFU.TANH + 2 FMA-pipe ops
 __device__ __forceinline__ float silu_fast(float z) {
@@ -169,11 +180,12 @@ struct Params {
   const void* Wp;            // packed weight image (W2, W5, W5^T, W2^T)
   // per-edge streams
   const __nv_bfloat16* in0;  // stage 2: v; stage 3: s; stage 4: gv
-  const __nv_bfloat16* in1;  // stage 3: v (epilogue)
+  const __nv_bfloat16* in1;  // epilogue stream: stage 3: dm = silu'(v); stage 4: da = silu'(u)
   const float* ein;          // stage 3: gw[E]
   const float* nin;          // stage 3: gagg[N,256]
   __nv_bfloat16* out0;       // stage 1: v; stage 2: s (or null); stage 3: gv; stage 4: gu
   __nv_bfloat16* out1;       // stage 1: a (or null); stage 2: m (or null); stage 3: gs
+  __nv_bfloat16* out2;       // stage 1: da = silu'(u) (or null); stage 2: dm = silu'(v) (or null)
   float* eout;               // stage 2: w[E] (+=); stage 4: gd2[E] (+=)
   float* nout;               // stage 1: agg[N,256] (+=)
   float* csum0;              // [256] (+=): stage 3 db5; stage 4 db2
@@ -399,10 +411,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
               const float b8[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z),
                                    __uint_as_float(b0.w), __uint_as_float(b1.x), __uint_as_float(b1.y),
                                    __uint_as_float(b1.z), __uint_as_float(b1.w)};
+              if (p.out2) {                          // training: keep a and silu'(u) for the backward pass
+                float g8[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * d2[i]);
-              out = pack8(a8);
-              if (p.out1) *reinterpret_cast<uint4*>(p.out1 + (e0 + r) * H + k0) = out;
+                for (int j = 0; j < 8; ++j) silu_and_grad(a8[j] + b8[j] + sVec1[k0 + j] * d2[i], a8[j], g8[j]);
+                out = pack8(a8);
+                *reinterpret_cast<uint4*>(p.out1 + (e0 + r) * H + k0) = out;
+                *reinterpret_cast<uint4*>(p.out2 + (e0 + r) * H + k0) = pack8(g8);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[j] = silu_fast(a8[j] + b8[j] + sVec1[k0 + j] * d2[i]);
+                out = pack8(a8);
+              }
             }
             *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
           }
@@ -459,10 +479,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
               float v8[8] = {bf16_lo(in.x), bf16_hi(in.x), bf16_lo(in.y), bf16_hi(in.y),
                              bf16_lo(in.z), bf16_hi(in.z), bf16_lo(in.w), bf16_hi(in.w)};
               if (STAGE == 2) {
+                if (p.out2) {
+                  float g8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v8[j] = silu_fast(v8[j]);
-                out = pack8(v8);
-                if (p.out1) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+                  for (int j = 0; j < 8; ++j) silu_and_grad(v8[j], v8[j], g8[j]);
+                  out = pack8(v8);
+                  *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+                  *reinterpret_cast<uint4*>(p.out2 + e * H + k0) = pack8(g8);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v8[j] = silu_fast(v8[j]);
+                  out = pack8(v8);
+                }
               } else if (STAGE == 3) {
                 const float gw = rw[it & 1][i];
 #pragma unroll
@@ -518,94 +546,109 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   } else if (warp < NUM_EPI_WARPS) {
     // ===================================================================== epilogue
     const int q = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
       const bool valid = e < p.E;
-      int dest = -1, src = 0;
-      float d2 = 0.f, dot = 0.f;
-      if (STAGE != 2 && valid) dest = p.row[e];
-      if (STAGE == 4 && valid) {
-        src = p.col[e];
-        const float dx = p.x[3 * (int64_t)dest] - p.x[3 * (int64_t)src];
-        const float dy = p.x[3 * (int64_t)dest + 1] - p.x[3 * (int64_t)src + 1];
-        const float dz = p.x[3 * (int64_t)dest + 2] - p.x[3 * (int64_t)src + 2];
-        d2 = dx * dx + dy * dy + dz * dz;
-      }
-      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-      tc_fence_after();
+      float dot = 0.f;
+      if constexpr (STAGE <= 2) {
+        int dest = -1;
+        if (STAGE == 1 && valid) dest = __ldg(p.row + e);
+        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        const int col0 = half * 128 + cb * 32;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + col0), raw);
-        float val[32];
+        for (int cb = 0; cb < 4; ++cb) {
+          const int col0 = half * 128 + cb * 32;
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * H + col0), raw);
+          float val[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + (STAGE <= 2 ? sBias[col0 + j] : 0.f);
-        if (STAGE == 1) {
-          if (valid) store_bf16x32(p.out0 + e * H + col0, val);
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[col0 + j];
+          if (STAGE == 1) {
+            if (valid) store_bf16x32(p.out0 + e * H + col0, val);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = silu_fast(val[j]);
-          // segmented sum over the warp's 32 edges: one butterfly transpose-reduce per distinct destination
-          uint32_t todo = __ballot_sync(0xffffffffu, valid);
-          while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const int d0 = __shfl_sync(0xffffffffu, dest, leader);
-            const bool mine = valid && dest == d0;
-            const uint32_t seg = __ballot_sync(0xffffffffu, mine);
-            float w[32];
+            for (int j = 0; j < 32; ++j) val[j] = silu_fast(val[j]);
+            // segmented sum over the warp's 32 edges: one butterfly transpose-reduce per distinct destination
+            uint32_t todo = __ballot_sync(0xffffffffu, valid);
+            while (todo) {
+              const int leader = __ffs(todo) - 1;
+              const int d0 = __shfl_sync(0xffffffffu, dest, leader);
+              const bool mine = valid && dest == d0;
+              const uint32_t seg = __ballot_sync(0xffffffffu, mine);
+              float w[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) w[j] = mine ? val[j] : 0.f;
+              for (int j = 0; j < 32; ++j) w[j] = mine ? val[j] : 0.f;
 #pragma unroll
-            for (int ofs = 16; ofs >= 1; ofs >>= 1) {
-              const bool up = (lane & ofs) != 0;
+              for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+                const bool up = (lane & ofs) != 0;
 #pragma unroll
-              for (int j = 0; j < ofs; ++j) {
-                const float keep = up ? w[j + ofs] : w[j];
-                const float send = up ? w[j] : w[j + ofs];
-                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+                for (int j = 0; j < ofs; ++j) {
+                  const float keep = up ? w[j + ofs] : w[j];
+                  const float send = up ? w[j] : w[j + ofs];
+                  w[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+                }
               }
+              atomicAdd(p.nout + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
+              todo &= ~seg;
             }
-            atomicAdd(p.nout + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
-            todo &= ~seg;
+          } else {
+            if (p.out0 && valid) store_bf16x32(p.out0 + e * H + col0, val);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(silu_fast(val[j]), sVec1[col0 + j], dot);
           }
-        } else if (STAGE == 2) {
-          if (p.out0 && valid) store_bf16x32(p.out0 + e * H + col0, val);
+        }
+      } else {
+        // backward epilogues: 8 batches of 16 columns; the per-edge operand stream (dm / da) and, for
+        // stage 3, the destination row of gagg are fetched one batch ahead of the TMEM read they meet
+        const __nv_bfloat16* dsrc = p.in1 + (valid ? e : 0) * H + half * 128;
+        const float* gsrc = nullptr;
+        if (STAGE == 3) gsrc = p.nin + (int64_t)(valid ? __ldg(p.row + e) : 0) * H + half * 128;
+        uint4 dq[2][2];
+        float4 gq[2][STAGE == 3 ? 4 : 1];
+        auto fetch = [&](int cb, int buf) {
+          dq[buf][0] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16));
+          dq[buf][1] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16) + 1);
+          if (STAGE == 3) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dot = fmaf(silu_fast(val[j]), sVec1[col0 + j], dot);
-        } else if (STAGE == 3) {
-          if (valid) {
-            const float* ga = p.nin + (int64_t)dest * H + col0;
-            const __nv_bfloat16* vv = p.in1 + e * H + col0;
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              float g8[8], v8[8];
-              load_f32x8(ga + 8 * j8, g8);
-              load_bf16x8(vv + 8 * j8, v8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) val[8 * j8 + j] = (val[8 * j8 + j] + g8[j]) * silu_grad(v8[j]);
-            }
-            store_bf16x32(p.out0 + e * H + col0, val);
+            for (int k = 0; k < 4; ++k) gq[buf][STAGE == 3 ? k : 0] = __ldg(reinterpret_cast<const float4*>(gsrc + cb * 16) + k);
           }
-        } else {
-          if (valid) {
-            const float* pa = p.AB + (int64_t)dest * 2 * H + col0;
-            const float* pb = p.AB + (int64_t)src * 2 * H + H + col0;
+        };
+        fetch(0, 0);
+        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              float a8[8], b8[8];
-              load_f32x8(pa + 8 * j8, a8);
-              load_f32x8(pb + 8 * j8, b8);
+        for (int cb = 0; cb < 8; ++cb) {
+          if (cb + 1 < 8) fetch(cb + 1, (cb + 1) & 1);
+          const int col0 = half * 128 + cb * 16;
+          uint32_t raw[16];
+          tmem_ld16(tmem_base + lane_base + (uint32_t)(acc * H + col0), raw);
+          const uint4 d0 = dq[cb & 1][0], d1 = dq[cb & 1][1];
+          const float dd[16] = {bf16_lo(d0.x), bf16_hi(d0.x), bf16_lo(d0.y), bf16_hi(d0.y), bf16_lo(d0.z), bf16_hi(d0.z),
+                                bf16_lo(d0.w), bf16_hi(d0.w), bf16_lo(d1.x), bf16_hi(d1.x), bf16_lo(d1.y), bf16_hi(d1.y),
+                                bf16_lo(d1.z), bf16_hi(d1.z), bf16_lo(d1.w), bf16_hi(d1.w)};
+          float val[16];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float wdj = sVec1[col0 + 8 * j8 + j];
-                const float gu = val[8 * j8 + j] * silu_grad(a8[j] + b8[j] + wdj * d2);
-                val[8 * j8 + j] = gu;
-                dot = fmaf(gu, wdj, dot);
-              }
+          for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(raw[j]);
+          if (STAGE == 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 g = gq[cb & 1][STAGE == 3 ? k : 0];
+              val[4 * k] += g.x; val[4 * k + 1] += g.y; val[4 * k + 2] += g.z; val[4 * k + 3] += g.w;
             }
-            store_bf16x32(p.out0 + e * H + col0, val);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            val[j] *= dd[j];
+            if (STAGE == 4) dot = fmaf(val[j], sVec1[col0 + j], dot);
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out0 + e * H + col0);
+            dst[0] = make_uint4(pack_bf16(val[0], val[1]), pack_bf16(val[2], val[3]), pack_bf16(val[4], val[5]),
+                                pack_bf16(val[6], val[7]));
+            dst[1] = make_uint4(pack_bf16(val[8], val[9]), pack_bf16(val[10], val[11]), pack_bf16(val[12], val[13]),
+                                pack_bf16(val[14], val[15]));
           }
         }
       }
@@ -669,25 +712,28 @@ int pev_pack_weight_bf16(const float* W, int32_t transpose, void* packed, void* 
 
 int pev_edge_mlp1_fwd_bf16(const float* AB, const float* x, const float* wd, const void* W2p, const float* b2,
                            const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges,
-                           void* v_out, void* a_out, float* agg, void* stream) {
+                           void* v_out, void* a_out, void* da_out, float* agg, void* stream) {
   PEV_REQUIRE(AB && x && wd && W2p && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
   if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc::H * (size_t)num_nodes, st);
   if (num_edges == 0) return 0;
   PEV_REQUIRE(row && col && v_out, "edge arrays missing");
+  PEV_REQUIRE((a_out == nullptr) == (da_out == nullptr), "a_out and da_out go together");
   tc::Params p = {};
   p.AB = AB; p.x = x; p.vec1 = wd; p.row = row; p.col = col; p.nout = agg;
   p.out0 = reinterpret_cast<bf16_t*>(v_out);
   p.out1 = reinterpret_cast<bf16_t*>(a_out);
+  p.out2 = reinterpret_cast<bf16_t*>(da_out);
   p.Wp = W2p; p.bias = b2; p.E = num_edges;
   return tc::launch<1>(p, st);
 }
 
 int pev_edge_mlp2_fwd_bf16(const void* v, const void* W5p, const float* b5, const float* w6, const float* b6,
-                           int64_t num_edges, float* w_out, void* s_out, void* m_out, void* stream) {
+                           int64_t num_edges, float* w_out, void* s_out, void* m_out, void* dm_out, void* stream) {
   PEV_REQUIRE(W5p && b5 && w6 && b6 && num_edges >= 0, "bad argument");
   if (num_edges == 0) return 0;
   PEV_REQUIRE(v && w_out, "edge arrays missing");
+  PEV_REQUIRE((m_out == nullptr) == (dm_out == nullptr), "m_out and dm_out go together");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   tc::Params p = {};
@@ -695,11 +741,12 @@ int pev_edge_mlp2_fwd_bf16(const void* v, const void* W5p, const float* b5, cons
   p.vec1 = w6; p.b6 = b6; p.eout = w_out;
   p.out0 = reinterpret_cast<bf16_t*>(s_out);
   p.out1 = reinterpret_cast<bf16_t*>(m_out);
+  p.out2 = reinterpret_cast<bf16_t*>(dm_out);
   p.Wp = W5p; p.bias = b5; p.E = num_edges;
   return tc::launch<2>(p, st);
 }
 
-int pev_edge_mlp2_bwd_bf16(const void* s, const void* v, const float* gw, const float* w6, const void* W5tp,
+int pev_edge_mlp2_bwd_bf16(const void* s, const void* dm, const float* gw, const float* w6, const void* W5tp,
                            const float* gagg, const int32_t* row, int64_t num_edges, void* gs_out, void* gv_out,
                            float* db5, float* dw6, void* stream) {
   PEV_REQUIRE(w6 && W5tp && db5 && dw6 && num_edges >= 0, "bad argument");
@@ -707,10 +754,10 @@ int pev_edge_mlp2_bwd_bf16(const void* s, const void* v, const float* gw, const 
   cudaMemsetAsync(db5, 0, sizeof(float) * tc::H, st);
   cudaMemsetAsync(dw6, 0, sizeof(float) * tc::H, st);
   if (num_edges == 0) return 0;
-  PEV_REQUIRE(s && v && gw && gagg && row && gs_out && gv_out, "edge arrays missing");
+  PEV_REQUIRE(s && dm && gw && gagg && row && gs_out && gv_out, "edge arrays missing");
   tc::Params p = {};
   p.in0 = reinterpret_cast<const bf16_t*>(s);
-  p.in1 = reinterpret_cast<const bf16_t*>(v);
+  p.in1 = reinterpret_cast<const bf16_t*>(dm);
   p.ein = gw; p.nin = gagg; p.row = row; p.vec1 = w6;
   p.out0 = reinterpret_cast<bf16_t*>(gv_out);
   p.out1 = reinterpret_cast<bf16_t*>(gs_out);
@@ -719,18 +766,18 @@ int pev_edge_mlp2_bwd_bf16(const void* s, const void* v, const float* gw, const 
   return tc::launch<3>(p, st);
 }
 
-int pev_edge_mlp1_bwd_bf16(const void* gv, const void* W2tp, const float* AB, const float* x, const float* wd,
-                           const int32_t* row, const int32_t* col, int64_t num_edges, void* gu_out, float* gd2,
-                           float* db2, void* stream) {
-  PEV_REQUIRE(W2tp && AB && x && wd && db2 && num_edges >= 0, "bad argument");
+int pev_edge_mlp1_bwd_bf16(const void* gv, const void* da, const void* W2tp, const float* wd, int64_t num_edges,
+                           void* gu_out, float* gd2, float* db2, void* stream) {
+  PEV_REQUIRE(W2tp && wd && db2 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(db2, 0, sizeof(float) * tc::H, st);
   if (num_edges == 0) return 0;
-  PEV_REQUIRE(gv && row && col && gu_out && gd2, "edge arrays missing");
+  PEV_REQUIRE(gv && da && gu_out && gd2, "edge arrays missing");
   cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
   tc::Params p = {};
   p.in0 = reinterpret_cast<const bf16_t*>(gv);
-  p.AB = AB; p.x = x; p.vec1 = wd; p.row = row; p.col = col;
+  p.in1 = reinterpret_cast<const bf16_t*>(da);
+  p.vec1 = wd;
   p.out0 = reinterpret_cast<bf16_t*>(gu_out);
   p.eout = gd2; p.csum0 = db2;
   p.Wp = W2tp; p.E = num_edges;

@@ -8,8 +8,9 @@ Forward per layer over the packed batch::
     x'   = pev_scatter_coord_fwd(w, x, dinv)    exact-order coordinate update (K2)
     h'   = LayerNorm(h + phi_h([h, agg]))       node-level fp32 (cuBLAS + torch)
 
-For training the per-edge tensors ``a, v, m, s`` are kept in HBM as bf16 ``[E,256]`` for the backward
-pass (2.47 GB each per layer at L=256, B=256: 59 GB for 6 layers -- sized for the 180 GB of a B200).
+For training the per-edge tensors ``a, silu'(u), m, silu'(v), s`` are kept in HBM as bf16 ``[E,256]`` for
+the backward pass (2.47 GB each per layer at L=256, B=256: 74 GB for 6 layers -- sized for the 180 GB of a
+B200); storing the SiLU derivatives keeps every transcendental out of the backward epilogues.
 """
 from __future__ import annotations
 
@@ -75,26 +76,26 @@ class FusedEdgeBF16(torch.autograd.Function):
             dev = x.device
             W2p, W5p = packed_weight(W2, cache=caches[0]), packed_weight(W5, cache=caches[1])
             v = torch.empty(E, H, dtype=bf, device=dev)
-            a, m, s = (torch.empty(E, H, dtype=bf, device=dev) if keep else None for _ in range(3))
+            a, da, m, dm, s = (torch.empty(E, H, dtype=bf, device=dev) if keep else None for _ in range(5))
             agg = torch.empty(N, H, dtype=torch.float32, device=dev)
             w = torch.empty(E, dtype=torch.float32, device=dev)
             x_out = torch.empty_like(x)
             st = stream(x)
             with _lib.profiled("edge_mlp1"):
                 L.call("pev_edge_mlp1_fwd_bf16", ptr(AB), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row),
-                       ptr(g.col), N, E, ptr(v), ptr(a), ptr(agg), st)
+                       ptr(g.col), N, E, ptr(v), ptr(a), ptr(da), ptr(agg), st)
             with _lib.profiled("edge_mlp2"):
                 L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(s),
-                       ptr(m), st)
+                       ptr(m), ptr(dm), st)
             L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
                    None, ptr(x_out), st)
         ctx.g, ctx.caches = g, caches
-        ctx.save_for_backward(AB, x, wd, W2, W5, w6v, dinv, a, v, m, s, w)
+        ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, a, da, m, dm, s, w)
         return agg, x_out
 
     @staticmethod
     def backward(ctx, gagg, gxo):
-        AB, x, wd, W2, W5, w6v, dinv, a, v, m, s, w = ctx.saved_tensors
+        x, wd, W2, W5, w6v, dinv, a, da, m, dm, s, w = ctx.saved_tensors
         if s is None:
             raise RuntimeError("FusedEdgeBF16 ran with keep=False (no_grad); backward is unavailable")
         g = ctx.g
@@ -114,7 +115,7 @@ class FusedEdgeBF16(torch.autograd.Function):
             gv = torch.empty(E, H, dtype=bf, device=dev)
             gb5, gw6 = torch.empty(H, dtype=f32, device=dev), torch.empty(H, dtype=f32, device=dev)
             with _lib.profiled("edge_mlp2_bwd"):
-                L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(v), ptr(gw), ptr(w6v), ptr(W5tp), ptr(gagg), ptr(g.row),
+                L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(dm), ptr(gw), ptr(w6v), ptr(W5tp), ptr(gagg), ptr(g.row),
                        E, ptr(gs), ptr(gv), ptr(gb5), ptr(gw6), st)
             gW5 = _wgrad(gs, m)
             del gs
@@ -122,8 +123,7 @@ class FusedEdgeBF16(torch.autograd.Function):
             gd2 = torch.empty(max(E, 1), dtype=f32, device=dev)
             gb2 = torch.empty(H, dtype=f32, device=dev)
             with _lib.profiled("edge_mlp1_bwd"):
-                L.call("pev_edge_mlp1_bwd_bf16", ptr(gv), ptr(W2tp), ptr(AB), ptr(x), ptr(wd), ptr(g.row), ptr(g.col),
-                       E, ptr(gu), ptr(gd2), ptr(gb2), st)
+                L.call("pev_edge_mlp1_bwd_bf16", ptr(gv), ptr(da), ptr(W2tp), ptr(wd), E, ptr(gu), ptr(gd2), ptr(gb2), st)
             gW2 = _wgrad(gv, a)
             del gv
             gAB = torch.empty(N, 2 * H, dtype=f32, device=dev)

@@ -51,13 +51,15 @@ def test_edge_mlp_kernels_match_bf16_emulation(lengths, W):
     s = torch.empty(E, H, dtype=bf, device="cuda")
     a_k = torch.empty(E, H, dtype=bf, device="cuda")
     m_k = torch.empty(E, H, dtype=bf, device="cuda")
+    da_k = torch.empty(E, H, dtype=bf, device="cuda")
+    dm_k = torch.empty(E, H, dtype=bf, device="cuda")
     agg = torch.full((N, H), 7.0, device="cuda")        # must be zeroed inside
     w = torch.full((E,), 7.0, device="cuda")
     L = _lib.lib()
     L.call("pev_edge_mlp1_fwd_bf16", ptr(AB), ptr(x), ptr(wd), ptr(packed_weight(W2)), ptr(b2), ptr(g.row), ptr(g.col),
-           N, E, ptr(v), ptr(a_k), ptr(agg), stream(x))
+           N, E, ptr(v), ptr(a_k), ptr(da_k), ptr(agg), stream(x))
     L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(packed_weight(W5)), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(s),
-           ptr(m_k), stream(x))
+           ptr(m_k), ptr(dm_k), stream(x))
     torch.cuda.synchronize()
     # emulation with the kernel's rounding points (bf16 operands, fp32 accumulation)
     row, col = g.row.long(), g.col.long()
@@ -87,10 +89,10 @@ def test_edge_mlp_kernels_match_bf16_emulation(lengths, W):
     gu_k = torch.empty(E, H, dtype=bf, device="cuda")
     db5, dw6, db2 = (torch.full((H,), 3.0, device="cuda") for _ in range(3))
     gd2 = torch.full((E,), 3.0, device="cuda")
-    L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(v), ptr(gw), ptr(w6), ptr(packed_weight(W5, transpose=True)), ptr(gagg),
+    L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(dm_k), ptr(gw), ptr(w6), ptr(packed_weight(W5, transpose=True)), ptr(gagg),
            ptr(g.row), E, ptr(gs_k), ptr(gv_k), ptr(db5), ptr(dw6), stream(x))
-    L.call("pev_edge_mlp1_bwd_bf16", ptr(gv_k), ptr(packed_weight(W2, transpose=True)), ptr(AB), ptr(x), ptr(wd),
-           ptr(g.row), ptr(g.col), E, ptr(gu_k), ptr(gd2), ptr(db2), stream(x))
+    L.call("pev_edge_mlp1_bwd_bf16", ptr(gv_k), ptr(da_k), ptr(packed_weight(W2, transpose=True)), ptr(wd), E,
+           ptr(gu_k), ptr(gd2), ptr(db2), stream(x))
     gAB = torch.empty(N, 2 * H, device="cuda")
     part = torch.empty(N, H, device="cuda")
     gx = torch.zeros(N, 3, device="cuda")
@@ -102,14 +104,15 @@ def test_edge_mlp_kernels_match_bf16_emulation(lengths, W):
         sg = torch.sigmoid(z)
         return sg * (1 + z * (1 - sg))
     sf, vf = s.float(), v.float()
+    assert rel_err(da_k.float(), dsilu(u)) < 6e-3 and rel_err(dm_k.float(), dsilu(vf)) < 6e-3
     gs_ref = gw[:, None] * w6[None] * dsilu(sf)
     assert rel_err(gs_k.float(), gs_ref) < 6e-3
     assert rel_err(db5, gs_ref.sum(0)) < 6e-3
     assert rel_err(dw6, gw @ _silu(sf)) < 6e-3
-    gv_ref = (gs_k.float() @ W5.to(bf).float() + gagg[row]) * dsilu(vf)
+    gv_ref = (gs_k.float() @ W5.to(bf).float() + gagg[row]) * dm_k.float()
     assert rel_err(gv_k.float(), gv_ref) < 6e-3
     assert rel_err(db2, gv_k.float().sum(0)) < 6e-3
-    gu_ref = (gv_k.float() @ W2.to(bf).float()) * dsilu(u)
+    gu_ref = (gv_k.float() @ W2.to(bf).float()) * da_k.float()
     assert rel_err(gu_k.float(), gu_ref) < 6e-3
     assert rel_err(gd2, gu_ref @ wd) < 1e-2
     guf = gu_k.float()

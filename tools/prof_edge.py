@@ -21,7 +21,7 @@ W2, W5 = torch.randn(H, H, device="cuda") / 16, torch.randn(H, H, device="cuda")
 b2, b5, w6 = (torch.randn(H, device="cuda") * 0.1 for _ in range(3))
 b6 = torch.zeros(1, device="cuda")
 bf = torch.bfloat16
-v, a, m, s, gs, gv, gu = (torch.empty(E, H, dtype=bf, device="cuda") for _ in range(7))
+v, a, da, m, dm, s, gs, gv, gu = (torch.empty(E, H, dtype=bf, device="cuda") for _ in range(9))
 agg = torch.empty(N, H, device="cuda")
 w = torch.empty(E, device="cuda")
 gw = torch.randn(E, device="cuda")
@@ -34,13 +34,13 @@ W2p, W5p, W2t, W5t = packed_weight(W2), packed_weight(W5), packed_weight(W2, Tru
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 for rep in range(reps + 1):
     ev[0].record()
-    L.call("pev_edge_mlp1_fwd_bf16", ptr(AB), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row), ptr(g.col), N, E, ptr(v), ptr(a), ptr(agg), st)
+    L.call("pev_edge_mlp1_fwd_bf16", ptr(AB), ptr(x), ptr(wd), ptr(W2p), ptr(b2), ptr(g.row), ptr(g.col), N, E, ptr(v), ptr(a), ptr(da), ptr(agg), st)
     ev[1].record()
-    L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(s), ptr(m), st)
+    L.call("pev_edge_mlp2_fwd_bf16", ptr(v), ptr(W5p), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(s), ptr(m), ptr(dm), st)
     ev[2].record()
-    L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(v), ptr(gw), ptr(w6), ptr(W5t), ptr(gagg), ptr(g.row), E, ptr(gs), ptr(gv), ptr(db5), ptr(dw6), st)
+    L.call("pev_edge_mlp2_bwd_bf16", ptr(s), ptr(dm), ptr(gw), ptr(w6), ptr(W5t), ptr(gagg), ptr(g.row), E, ptr(gs), ptr(gv), ptr(db5), ptr(dw6), st)
     ev[3].record()
-    L.call("pev_edge_mlp1_bwd_bf16", ptr(gv), ptr(W2t), ptr(AB), ptr(x), ptr(wd), ptr(g.row), ptr(g.col), E, ptr(gu), ptr(gd2), ptr(db2), st)
+    L.call("pev_edge_mlp1_bwd_bf16", ptr(gv), ptr(da), ptr(W2t), ptr(wd), E, ptr(gu), ptr(gd2), ptr(db2), st)
     ev[4].record()
     torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
