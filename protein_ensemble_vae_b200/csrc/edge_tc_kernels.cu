@@ -435,6 +435,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
       // streams (stages 2-4): one bf16 [E,256] input, no shared metadata, no producer barrier
       uint4 pf[2][RPT];
       float rw[2][RPT];                                     // stage 3: gw of this thread's rows
+      // column sums (stage 3: db5, dW6; stage 4: db2) live in registers for the whole persistent loop
+      float cs0[STAGE >= 3 ? NUM_KCHUNKS : 1][8], cs1[STAGE == 3 ? NUM_KCHUNKS : 1][8];
+#pragma unroll
+      for (int a = 0; a < (STAGE >= 3 ? NUM_KCHUNKS : 1); ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs0[a][j] = 0.f;
+#pragma unroll
+      for (int a = 0; a < (STAGE == 3 ? NUM_KCHUNKS : 1); ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs1[a][j] = 0.f;
       auto issue = [&](int tile, int kc, int buf) {
         const int64_t e0 = (int64_t)tile * TILE_M;
 #pragma unroll
@@ -466,9 +476,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = sA + stage * STAGE_BYTES;
           const int k0 = kc * KCHUNK + chunk * 8;
-          float ls0[8], ls1[8];                               // column sums over this thread's rows (stages 3, 4)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ls0[j] = ls1[j] = 0.f;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const int r = (pt >> 3) + RSTEP * i;
@@ -498,8 +505,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                   float t, dt;
                   silu_and_grad(v8[j], t, dt);
                   const float gs = gw * sVec1[k0 + j] * dt;
-                  ls0[j] += gs;
-                  ls1[j] = fmaf(gw, t, ls1[j]);
+                  cs0[STAGE >= 3 ? kc : 0][j] += gs;
+                  cs1[STAGE == 3 ? kc : 0][j] = fmaf(gw, t, cs1[STAGE == 3 ? kc : 0][j]);
                   v8[j] = gs;
                 }
                 out = pack8(v8);
@@ -507,7 +514,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
               } else {
                 out = in;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ls0[j] += v8[j];
+                for (int j = 0; j < 8; ++j) cs0[STAGE >= 3 ? kc : 0][j] += v8[j];
               }
             }
             *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
@@ -515,29 +522,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
           fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
           mbar_arrive(&full_bar[stage]);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-          if (STAGE >= 3) {
-            // lanes l, l^8, l^16, l^24 hold the same columns: fold them, then 8 lanes per warp add to shared
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 8);
-              ls0[j] += __shfl_xor_sync(0xffffffffu, ls0[j], 16);
-              if (STAGE == 3) {
-                ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 8);
-                ls1[j] += __shfl_xor_sync(0xffffffffu, ls1[j], 16);
-              }
-            }
-            if (lane < 8) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                atomicAdd(&sRed[k0 + j], ls0[j]);
-                if (STAGE == 3) atomicAdd(&sRed2[k0 + j], ls1[j]);
-              }
-            }
-          }
         }
       }
       if (STAGE >= 3) {
-        // column sums: shared -> one global atomic per column per CTA
+        // column sums: registers -> (lanes l, l^8, l^16, l^24 share columns) -> shared -> one global atomic
+        // per column per CTA
+#pragma unroll
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a0 = cs0[STAGE >= 3 ? kc : 0][j];
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+            if (lane < 8) atomicAdd(&sRed[kc * KCHUNK + chunk * 8 + j], a0);
+            if (STAGE == 3) {
+              float a1 = cs1[STAGE == 3 ? kc : 0][j];
+              a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+              if (lane < 8) atomicAdd(&sRed2[kc * KCHUNK + chunk * 8 + j], a1);
+            }
+          }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
         atomicAdd(p.csum0 + pt, sRed[pt]);
         if (STAGE == 3) atomicAdd(p.csum1 + pt, sRed2[pt]);
