@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import _lib, nodeops
+from . import _lib
 from ._lib import f32c, ptr, stream
 from .graph import PackedGraph
 
@@ -141,13 +141,12 @@ def egn_layer_bf16(layer, h, x, g: PackedGraph, dinv):
     W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
     Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                      # [512, 256]
     bias = torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
-    AB = nodeops.linear(h, Wcat, bias, fast=True)                         # [N, 512]
+    AB = torch.addmm(bias, h, Wcat.t())                                   # [N, 512]
     caches = layer.__dict__.setdefault("_pev_packed", ({}, {}))
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
     agg, x_new = FusedEdgeBF16.apply(AB, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
                                      layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
                                      layer.phi_x[2].bias, dinv, g, keep, caches)
-    q = layer.phi_h[1](nodeops.linear(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias, fast=True))
-    h_new = layer.norm_h(h + nodeops.linear(q, layer.phi_h[2].weight, layer.phi_h[2].bias, fast=True))
+    h_new = layer.norm_h(h + layer.phi_h(torch.cat([h, agg], -1)))
     return h_new, x_new

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import egnn_ops, nodeops
+from . import egnn_ops
 from .graph import PackedGraph, band_graph, graph_from_edge_index
 
 N_CA_LENGTH = 1.46      # models/en_gnn_decoder.py:274
@@ -166,10 +166,8 @@ class EGNNDecoder(nn.Module):
         conf_of = torch.repeat_interleave(torch.arange(B, device=device),
                                           torch.tensor(lengths, device=device), output_size=N)
         z = torch.cat([z_g.index_select(0, conf_of), zl_p], -1)
-        fast = self.precision == "bf16"                         # split-bf16 tensor-core GEMMs, fp32-grade
-        l2c = self.latent_to_coords
-        x = l2c[1:](nodeops.linear(z, l2c[0].weight, l2c[0].bias, fast))                    # :237
-        h = nodeops.linear(z, self.input_embedding.weight, self.input_embedding.bias, fast)  # :240
+        x = self.latent_to_coords(z)                            # :237
+        h = self.input_embedding(z)                             # :240
         g, dinv = self._graph(lengths, device)
         for layer in self.layers:                               # :248-250
             h, x = _layer_forward(layer, h, x, g, dinv, self.precision)

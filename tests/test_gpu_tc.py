@@ -181,20 +181,3 @@ def test_no_grad_decode_keeps_nothing():
     # N-CA and CA-C bonds are fixed-length offsets (models/en_gnn_decoder.py:289-293); C is never pulled
     assert torch.allclose((c - ca).norm(dim=-1), torch.full((5, 70), 1.52, device="cuda"), atol=1e-4)
 
-
-def test_split_bf16_linear_is_fp32_grade():
-    from protein_ensemble_vae_b200 import nodeops
-    if not nodeops.supported("cuda"):
-        pytest.skip("torch.mm(out_dtype=) not available")
-    g = torch.Generator(device="cuda").manual_seed(0)
-    x = torch.randn(4096, 512, device="cuda", generator=g, requires_grad=True)
-    W = (torch.randn(256, 512, device="cuda", generator=g) / 22).requires_grad_()
-    b = torch.randn(256, device="cuda", generator=g, requires_grad=True)
-    c = torch.randn(4096, 256, device="cuda", generator=g)
-    y = nodeops.linear(x, W, b, fast=True)
-    (y * c).sum().backward()
-    x64, W64, b64 = (t.detach().double().requires_grad_() for t in (x, W, b))
-    y64 = x64 @ W64.t() + b64
-    (y64 * c.double()).sum().backward()
-    assert rel_err(y, y64) < 2e-6
-    assert rel_err(x.grad, x64.grad) < 2e-6 and rel_err(W.grad, W64.grad) < 2e-6 and rel_err(b.grad, b64.grad) < 2e-6
