@@ -1,0 +1,164 @@
+"""BASELINE.json's configurations on a real B200, checked through size-independent properties where the
+oracle would take too long: E(3) equivariance, padding invariance, shard invariance,
+Kabsch invariances, loss consistency between the fused path and the per-function API."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_err
+from oracle import kabsch_oracle, losses_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rot(seed):
+    q, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] *= -1
+    return torch.tensor(q, dtype=torch.float32, device=DEV)
+
+
+def _decoder(layers, precision, seed=0, W=40):
+    from protein_ensemble_vae_b200 import EGNNDecoder
+    torch.manual_seed(seed)
+    return EGNNDecoder(64, 32, hidden_dim=256, num_layers=layers, max_neighbors=W, dropout=0.0,
+                       precision=precision).to(DEV).eval()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_layer_equivariance_config2_shape(precision, tol):
+    """EGNLayer(h, xQ+t) == (h', x'Q+t) at L=256, W=40."""
+    from protein_ensemble_vae_b200 import EGNLayer
+    from protein_ensemble_vae_b200.graph import band_graph
+    torch.manual_seed(1)
+    layer = EGNLayer(256, 256, precision=precision).to(DEV)
+    g = band_graph((256,) * 4, 40, DEV)
+    h = torch.randn(g.num_nodes, 256, device=DEV)
+    x = torch.randn(g.num_nodes, 3, device=DEV) * 3
+    Q, t = _rot(2), torch.tensor([1.0, -2.0, 0.5], device=DEV)
+    with torch.no_grad():
+        h1, x1 = layer(h, x, g, g.dinv)
+        h2, x2 = layer(h, x @ Q + t, g, g.dinv)
+    assert rel_err(h2, h1) < tol and rel_err(x2, x1 @ Q + t) < tol
+
+
+def test_mixed_lengths_config3_padding_and_batch_invariance():
+    """config 3: ragged lengths 64..512 with interior gaps; a conformer's output must not depend on its batch
+    mates or on where the padding sits, and padded rows are exact zeros."""
+    dec = _decoder(3, "fp32")
+    rng = np.random.default_rng(3)
+    B, L = 6, 512
+    lengths = [512, 64, 300, 129, 257, 400]
+    mask = torch.zeros(B, L, device=DEV)
+    for b, n in enumerate(lengths):
+        mask[b, :n] = 1
+    mask[2, 100:105] = 0
+    mask[4, 7:9] = 0
+    zg = torch.randn(B, 64, device=DEV)
+    zl = torch.randn(B, L, 32, device=DEV)
+    with torch.no_grad():
+        full = dec(zg, zl, mask)
+        for b in (1, 2, 5):
+            solo = dec(zg[b:b + 1], zl[b:b + 1], mask[b:b + 1])
+            for o_full, o_solo in zip(full, solo):
+                assert rel_err(o_full[b], o_solo[0]) < 1e-5
+        # compacting the valid residues to the front gives the same per-residue outputs
+        b = 2
+        idx = torch.nonzero(mask[b]).squeeze(-1)
+        zl_c = torch.zeros(1, L, 32, device=DEV)
+        zl_c[0, :idx.numel()] = zl[b, idx]
+        m_c = torch.zeros(1, L, device=DEV)
+        m_c[0, :idx.numel()] = 1
+        comp = dec(zg[b:b + 1], zl_c, m_c)
+        for o_full, o_c in zip(full, comp):
+            assert rel_err(o_full[b, idx], o_c[0, :idx.numel()]) < 1e-5
+    for o in full:
+        assert float(o[mask == 0].abs().max()) == 0.0
+
+
+def test_decoder_bf16_tracks_fp32_at_config2_depth():
+    """6 layers, L=256: the bf16 tensor-core path stays within 1e-2 of the fp32 exact-order path."""
+    d32, d16 = _decoder(6, "fp32", seed=5), _decoder(6, "bf16", seed=5)
+    d16.load_state_dict(d32.state_dict())
+    zg, zl = torch.randn(4, 64, device=DEV), torch.randn(4, 256, 32, device=DEV)
+    with torch.no_grad():
+        a, b = d32(zg, zl), d16(zg, zl)
+    for x, y in zip(a, b):
+        assert rel_err(y, x) < 1e-2
+
+
+def test_stress_config5_l1024_band_and_dense():
+    """config 5: L=1024 with the W=40 band (E=80 280) and the dense graph W=1023 (E=1 047 552) through the
+    generic CSR path; full pairwise losses with pair_stride=1 and the 4.7 M-pair clash tile."""
+    from protein_ensemble_vae_b200 import EGNNDecoder, compute_total_loss
+    from protein_ensemble_vae_b200 import losses as pl
+    from protein_ensemble_vae_b200.graph import band_edge_count, band_graph
+    assert band_edge_count(1024, 40) == 80280 and band_edge_count(1024, 1023) == 1047552
+    g = band_graph((1024,), 1023, DEV)
+    assert g.num_edges == 1047552 and int(g.row_ptr[-1]) == 1047552
+    B, L = 2, 1024
+    for W, prec in ((40, "bf16"), (1023, "bf16"), (1023, "fp32")):
+        torch.manual_seed(0)
+        dec = EGNNDecoder(64, 32, hidden_dim=256, num_layers=2, max_neighbors=W, dropout=0.0, precision=prec).to(DEV)
+        zg = torch.randn(B, 64, device=DEV)
+        zl = torch.randn(B, L, 32, device=DEV, requires_grad=True)
+        mask = torch.ones(B, L, device=DEV)
+        n, ca, c, lg = dec(zg, zl, mask)
+        d = cases.loss_inputs((B, L, "full", 9, 1.0, (1,)))
+        t = lambda a: torch.tensor(a, device=DEV)  # noqa: E731
+        tn, tca, tc = t(d["target_N"]), t(d["target_CA"]), t(d["target_C"])
+        tdih = pl.compute_dihedrals_from_coords(tn, tca, tc, mask)
+        res = compute_total_loss(n, ca, c, lg, tn, tca, tc, t(d["labels"]), mask, t(d["mu_g"]), t(d["lv_g"]),
+                                 t(d["mu_l"]), t(d["lv_l"]), tdih, pair_stride=1, **cases.LOSS_WEIGHTS)
+        res["total"].backward()
+        assert all(torch.isfinite(v) for v in res.values()) and torch.isfinite(zl.grad).all()
+        if W == 40:      # loss values of the fused kernels vs the float64 oracle on the same predictions
+            T64 = lambda a: a.detach().cpu().double()  # noqa: E731
+            chk = losses_oracle.compute_total_loss(
+                T64(n), T64(ca), T64(c), T64(lg), T64(tn), T64(tca), T64(tc), torch.tensor(d["labels"]), T64(mask),
+                T64(t(d["mu_g"])), T64(t(d["lv_g"])), T64(t(d["mu_l"])), T64(t(d["lv_l"])), T64(tdih), pair_stride=1,
+                **cases.LOSS_WEIGHTS)
+            for k in chk:
+                assert abs(float(res[k]) - float(chk[k])) <= 2e-5 * max(abs(float(chk[k])), 1e-3), k
+
+
+def test_generation_config4_sharded_decode_and_kabsch():
+    """config 4 shape (L=100, 8 layers): chunked decode == one-shot decode; Kabsch RMSD is invariant to rigid
+    motion of either structure and matches the numpy oracle."""
+    from protein_ensemble_vae_b200 import ResidueDecoder, kabsch_rmsd_batch
+    from protein_ensemble_vae_b200 import distributed as pd
+    torch.manual_seed(0)
+    dec = ResidueDecoder(64, 32, dropout=0.1, precision="bf16").to(DEV).eval()
+    S, L = 300, 100
+    zg, zl = torch.randn(S, 64, device=DEV), torch.randn(S, L, 32, device=DEV)
+    mask = torch.ones(L, device=DEV)
+    ref = torch.cumsum(torch.randn(L, 3, device=DEV) * 2.2, 0)
+    with torch.no_grad():
+        one = dec(zg, zl, mask.expand(S, L))[1]
+    r1, coords = pd.decode_ensemble(dec, zg, zl, mask, ref, chunk=77, return_coords=True)
+    assert rel_err(coords, one) < 5e-3          # fp32 atomics in the aggregation are order-dependent across batches
+    r2 = kabsch_rmsd_batch(one, ref, mask)
+    assert rel_err(r1, r2) < 5e-3
+    Q, t = _rot(4), torch.tensor([3.0, 1.0, -2.0], device=DEV)
+    assert rel_err(kabsch_rmsd_batch(one @ Q + t, ref, mask), r2) < 1e-5
+    assert rel_err(kabsch_rmsd_batch(one, ref @ Q + t, mask), r2) < 1e-5
+    for s in (0, 17, 299):
+        want = kabsch_oracle.kabsch_rmsd(one[s].cpu().double().numpy(), ref.cpu().double().numpy(), np.ones(L))
+        assert abs(float(r2[s]) - want) < 1e-5 * max(want, 1.0)
+    assert float(kabsch_rmsd_batch(ref[None] @ Q + t, ref, mask)[0]) < 1e-4        # rigid copy -> ~0
+
+
+def test_single_residue_and_empty_conformers():
+    """Lb == 1 crashes the reference; here it decodes (no edges) and empty rows give zeros."""
+    dec = _decoder(2, "bf16")
+    mask = torch.zeros(3, 9, device=DEV)
+    mask[0, 4] = 1
+    mask[2, :5] = 1
+    with torch.no_grad():
+        n, ca, c, lg = dec(torch.randn(3, 64, device=DEV), torch.randn(3, 9, 32, device=DEV), mask)
+    assert torch.isfinite(ca).all() and float(ca[1].abs().max()) == 0.0 and float(lg[1].abs().max()) == 0.0
+    assert float(ca[0, 4].abs().max()) > 0 and float(ca[0, :4].abs().max()) == 0.0
