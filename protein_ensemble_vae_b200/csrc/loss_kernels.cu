@@ -258,7 +258,7 @@ static int grid_for(int64_t n, int threads, int per_sm = 8) {
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes, const char* what) {
   if (bytes > (size_t)kMaxDynSmem) return set_error(1, "%s: conformer too long for the shared-memory tile", what);
-  if (bytes > 48 * 1024) {
+  if (bytes > 40 * 1024) {      // static shared memory counts against the 48 KB default as well
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return set_error(2, "%s: %s", what, cudaGetErrorString(e));
   }
