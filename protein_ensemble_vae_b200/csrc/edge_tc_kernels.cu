@@ -432,9 +432,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         }
       }
     } else {
-      // streams (stages 2-4): one bf16 [E,256] input, no shared metadata, no producer barrier
-      uint4 pf[2][RPT];
-      float rw[2][RPT];                                     // stage 3: gw of this thread's rows
+      // streams (stages 2-4): one bf16 [E,256] input, no shared metadata, no producer barrier.
+      // Loads run PD K-chunks ahead of their use (one register buffer per K-chunk, refilled across tile
+      // boundaries) so that ~48-64 KB per SM are in flight -- what HBM latency x bandwidth asks for.
+      constexpr int PD = (STAGE == 3) ? 1 : 3;             // stage 3 also carries 64 column-sum registers
+      uint4 pf[NUM_KCHUNKS][RPT];
+      float rw_cur[RPT], rw_nxt[RPT];                       // stage 3: gw of this thread's rows
       // column sums (stage 3: db5, dW6; stage 4: db2) live in registers for the whole persistent loop
       float cs0[STAGE >= 3 ? NUM_KCHUNKS : 1][8], cs1[STAGE == 3 ? NUM_KCHUNKS : 1][8];
 #pragma unroll
@@ -445,34 +448,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
       for (int a = 0; a < (STAGE == 3 ? NUM_KCHUNKS : 1); ++a)
 #pragma unroll
         for (int j = 0; j < 8; ++j) cs1[a][j] = 0.f;
-      auto issue = [&](int tile, int kc, int buf) {
+      auto issue = [&](int tile, int kc) {
         const int64_t e0 = (int64_t)tile * TILE_M;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const int64_t e = e0 + (pt >> 3) + RSTEP * i;
-          pf[buf][i] = (e < p.E) ? __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + kc * KCHUNK + chunk * 8))
-                                 : make_uint4(0u, 0u, 0u, 0u);
+          pf[kc][i] = (e < p.E) ? __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + kc * KCHUNK + chunk * 8))
+                                : make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      auto issue_rw = [&](int tile, int buf) {
+      auto issue_rw = [&](int tile) {
         const int64_t e0 = (int64_t)tile * TILE_M;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const int64_t e = e0 + (pt >> 3) + RSTEP * i;
-          rw[buf][i] = (STAGE == 3 && e < p.E) ? __ldg(p.ein + e) : 0.f;
+          rw_nxt[i] = (STAGE == 3 && e < p.E) ? __ldg(p.ein + e) : 0.f;
         }
       };
-      issue_rw(blockIdx.x, 0);
-      issue(blockIdx.x, 0, 0);
+      issue_rw(blockIdx.x);
+#pragma unroll
+      for (int kc = 0; kc < PD; ++kc) issue(blockIdx.x, kc);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int64_t e0 = (int64_t)tile * TILE_M;
         const int next_tile = tile + gridDim.x;
-        if (next_tile < p.num_tiles) issue_rw(next_tile, (it + 1) & 1);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) rw_cur[i] = rw_nxt[i];
+        if (next_tile < p.num_tiles) issue_rw(next_tile);
 #pragma unroll
         for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
-          // NUM_KCHUNKS is even, so the prefetch buffer of chunk kc is always kc & 1
-          if (kc + 1 < NUM_KCHUNKS) issue(tile, kc + 1, (kc + 1) & 1);
-          else if (next_tile < p.num_tiles) issue(next_tile, 0, 0);
+          if (kc + PD < NUM_KCHUNKS) issue(tile, kc + PD);
+          else if (next_tile < p.num_tiles) issue(next_tile, kc + PD - NUM_KCHUNKS);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = sA + stage * STAGE_BYTES;
           const int k0 = kc * KCHUNK + chunk * 8;
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
             const int64_t e = e0 + r;
             uint4 out = make_uint4(0u, 0u, 0u, 0u);
             if (e < p.E) {
-              const uint4 in = pf[kc & 1][i];
+              const uint4 in = pf[kc][i];
               float v8[8] = {bf16_lo(in.x), bf16_hi(in.x), bf16_lo(in.y), bf16_hi(in.y),
                              bf16_lo(in.z), bf16_hi(in.z), bf16_lo(in.w), bf16_hi(in.w)};
               if (STAGE == 2) {
@@ -499,7 +504,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                   out = pack8(v8);
                 }
               } else if (STAGE == 3) {
-                const float gw = rw[it & 1][i];
+                const float gw = rw_cur[i];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   float t, dt;
@@ -552,6 +557,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     int it = 0;
+    // backward epilogues (stages 3, 4): operand prefetch state carried across tiles
+    const __nv_bfloat16* bw_dsrc = nullptr;
+    const float* bw_gsrc = nullptr;
+    constexpr int EPD = (STAGE == 3) ? 1 : 2;              // batches ahead (stage 3 also streams gagg: 16 more registers per buffer)
+    constexpr int ENB = EPD + 1;
+    uint4 dq[ENB][2];
+    float4 gq[ENB][STAGE == 3 ? 4 : 1];
+    auto bw_fetch = [&](const __nv_bfloat16* dsrc, const float* gsrc, int cb, int buf) {
+      dq[buf][0] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16));
+      dq[buf][1] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16) + 1);
+      if (STAGE == 3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gq[buf][STAGE == 3 ? k : 0] = __ldg(reinterpret_cast<const float4*>(gsrc + cb * 16) + k);
+      }
+    };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
@@ -605,30 +625,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
         }
       } else {
         // backward epilogues: 8 batches of 16 columns; the per-edge operand stream (dm / da) and, for
-        // stage 3, the destination row of gagg are fetched one batch ahead of the TMEM read they meet
-        const __nv_bfloat16* dsrc = p.in1 + (valid ? e : 0) * H + half * 128;
-        const float* gsrc = nullptr;
-        if (STAGE == 3) gsrc = p.nin + (int64_t)(valid ? __ldg(p.row + e) : 0) * H + half * 128;
-        uint4 dq[2][2];
-        float4 gq[2][STAGE == 3 ? 4 : 1];
-        auto fetch = [&](int cb, int buf) {
-          dq[buf][0] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16));
-          dq[buf][1] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16) + 1);
-          if (STAGE == 3) {
+        // stage 3, the destination row of gagg are fetched two batches ahead of the TMEM read they meet,
+        // across tile boundaries (three register buffers, indices static after unrolling)
+        if (it == 0) {
+          bw_dsrc = p.in1 + (valid ? e : 0) * H + half * 128;
+          if (STAGE == 3) bw_gsrc = p.nin + (int64_t)(valid ? __ldg(p.row + e) : 0) * H + half * 128;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gq[buf][STAGE == 3 ? k : 0] = __ldg(reinterpret_cast<const float4*>(gsrc + cb * 16) + k);
-          }
-        };
-        fetch(0, 0);
+          for (int j = 0; j < EPD; ++j) bw_fetch(bw_dsrc, bw_gsrc, j, j);
+        }
+        // operand pointers of this thread's row in the next tile (its row index load overlaps this tile)
+        const int next_tile = tile + gridDim.x;
+        const int64_t en = (int64_t)next_tile * TILE_M + q * 32 + lane;
+        const bool nvalid = next_tile < p.num_tiles && en < p.E;
+        const __nv_bfloat16* n_dsrc = p.in1 + (nvalid ? en : 0) * H + half * 128;
+        int n_dest = 0;
+        if (STAGE == 3 && nvalid) n_dest = __ldg(p.row + en);
         mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int cb = 0; cb < 8; ++cb) {
-          if (cb + 1 < 8) fetch(cb + 1, (cb + 1) & 1);
+          // buffer of batch cb is (cb + 2 * it_par) % 3 -- kept static by rotating the buffers per tile below
+          if (cb + EPD < 8) bw_fetch(bw_dsrc, bw_gsrc, cb + EPD, (cb + EPD) % ENB);
+          else if (next_tile < p.num_tiles) {
+            const float* n_gsrc = (STAGE == 3) ? p.nin + (int64_t)n_dest * H + half * 128 : nullptr;
+            bw_fetch(n_dsrc, n_gsrc, cb + EPD - 8, (cb + EPD) % ENB);
+          }
           const int col0 = half * 128 + cb * 16;
           uint32_t raw[16];
           tmem_ld16(tmem_base + lane_base + (uint32_t)(acc * H + col0), raw);
-          const uint4 d0 = dq[cb & 1][0], d1 = dq[cb & 1][1];
+          const uint4 d0 = dq[cb % ENB][0], d1 = dq[cb % ENB][1];
           const float dd[16] = {bf16_lo(d0.x), bf16_hi(d0.x), bf16_lo(d0.y), bf16_hi(d0.y), bf16_lo(d0.z), bf16_hi(d0.z),
                                 bf16_lo(d0.w), bf16_hi(d0.w), bf16_lo(d1.x), bf16_hi(d1.x), bf16_lo(d1.y), bf16_hi(d1.y),
                                 bf16_lo(d1.z), bf16_hi(d1.z), bf16_lo(d1.w), bf16_hi(d1.w)};
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
           if (STAGE == 3) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float4 g = gq[cb & 1][STAGE == 3 ? k : 0];
+              const float4 g = gq[cb % ENB][STAGE == 3 ? k : 0];
               val[4 * k] += g.x; val[4 * k + 1] += g.y; val[4 * k + 2] += g.z; val[4 * k + 3] += g.w;
             }
           }
@@ -655,6 +680,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                                 pack_bf16(val[14], val[15]));
           }
         }
+        // next tile's first EPD batches sit in buffers (8 + j) % ENB; move them to j so that batch cb is always
+        // in buffer cb % ENB (ENB == 2: 8 % 2 == 0, nothing to do; ENB == 3: (2, 0) -> (0, 1))
+        if constexpr (ENB == 3) {
+          dq[1][0] = dq[0][0]; dq[1][1] = dq[0][1];
+          dq[0][0] = dq[2][0]; dq[0][1] = dq[2][1];
+        }
+        bw_dsrc = n_dsrc;
+        if (STAGE == 3) bw_gsrc = p.nin + (int64_t)n_dest * H + half * 128;
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);               // accumulator stage drained
