@@ -231,8 +231,10 @@ __device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
 
 template <int STAGE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B.  Plain pointer arithmetic on the __shared__ array (no integer round
+  // trip) so the compiler keeps the shared address space and emits LDS/STS instead of generic LD/ST.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem + SmemLayout::W_OFF;
   uint8_t* sA = smem + SmemLayout::A_OFF;
   float* sBias = reinterpret_cast<float*>(smem + SmemLayout::VEC_OFF);   // b2 / b5 (stages 1, 2)
