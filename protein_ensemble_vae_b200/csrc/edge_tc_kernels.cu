@@ -19,6 +19,8 @@
 // Synchronisation is mbarrier-only (full/empty per ring stage, full/empty per accumulator stage).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "../../include/pev_b200.h"
 #include "pev_common.cuh"
 
@@ -31,7 +33,9 @@ constexpr int KCHUNK = 64;             // bf16 elements per 128-byte swizzle row
 constexpr int NUM_KCHUNKS = H / KCHUNK;
 constexpr int UMMA_K = 16;
 constexpr int NUM_STAGES = 4;          // A-operand ring (16 KB each): one full tile in flight
-constexpr int NA = 8;                  // destination rows of a tile staged in shared memory (stage 1)
+constexpr int NA = 4;                  // destination rows of a tile staged in shared memory (stage 1)
+constexpr int EPI_ROW = 80;            // bytes per row of an epilogue warp's transposition scratch (64 + 16 pad)
+constexpr int EPI_SCRATCH = 32 * EPI_ROW;
 constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
 constexpr int W_BYTES = H * H * 2;
 // Roles are aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
@@ -53,7 +57,8 @@ struct __align__(16) SmemLayout {
   static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 4 x 256 floats
   static constexpr int META_OFF = VEC_OFF + 4 * H * 4;                  // 2 x 128 floats (d2 per tile row)
   static constexpr int AROW_OFF = META_OFF + 2 * TILE_M * 4;            // 2 x NA x 256 floats (A rows of the tile)
-  static constexpr int BAR_OFF = AROW_OFF + 2 * NA * H * 4;
+  static constexpr int EPI_OFF = AROW_OFF + 2 * NA * H * 4;             // 8 warps x [32 rows x 80 B]
+  static constexpr int BAR_OFF = EPI_OFF + NUM_EPI_WARPS * EPI_SCRATCH;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 constexpr int SMEM_BYTES = SmemLayout::TOTAL + 1024;   // slack for manual 1024-byte alignment
@@ -193,6 +198,7 @@ struct Params {
   const float* b6;           // [1] stage 2
   int64_t E;
   int num_tiles;
+  int dbg;                   // PEV_TC_DEBUG bit mask (profiling experiments only; 0 in production)
 };
 
 // silu(z) and d silu / dz from one tanh: sg = sigmoid(z) = 0.5 + 0.5 tanh(z/2)
@@ -229,6 +235,47 @@ __device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
   return make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
 }
 
+// ---- epilogue transposition through a per-warp scratch ([32 rows][80 B], conflict-free both ways).
+// In the TMEM layout a lane owns a ROW of the tile, so a direct global access touches 32 rows x 16 B per
+// instruction (32 L2 transactions).  Going through the scratch, 4 lanes cover 64 contiguous bytes of a row:
+// 8 rows x 64 B per instruction -- 4x fewer, full-sector transactions.
+__device__ __forceinline__ void warp_store_rows(uint8_t* sc, int lane, const uint4 (&mine)[4], __nv_bfloat16* gbase,
+                                                int nrows) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sc + lane * EPI_ROW + k * 16) = mine[k];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = (lane >> 2) + 8 * j;
+    const uint4 v = *reinterpret_cast<const uint4*>(sc + row * EPI_ROW + (lane & 3) * 16);
+    if (row < nrows) *reinterpret_cast<uint4*>(gbase + (int64_t)row * H + (lane & 3) * 8) = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_issue_rows(const __nv_bfloat16* gbase, int lane, int nrows, uint4 (&buf)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = (lane >> 2) + 8 * j;
+    buf[j] = (row < nrows) ? __ldg(reinterpret_cast<const uint4*>(gbase + (int64_t)row * H + (lane & 3) * 8))
+                           : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void warp_deposit_rows(uint8_t* sc, int lane, const uint4 (&buf)[4], uint4 (&mine)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(sc + ((lane >> 2) + 8 * j) * EPI_ROW + (lane & 3) * 16) = buf[j];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mine[k] = *reinterpret_cast<const uint4*>(sc + lane * EPI_ROW + k * 16);
+  __syncwarp();
+}
+__device__ __forceinline__ void pack32(const float (&val)[32], uint4 (&o)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    o[k] = make_uint4(pack_bf16(val[8 * k], val[8 * k + 1]), pack_bf16(val[8 * k + 2], val[8 * k + 3]),
+                      pack_bf16(val[8 * k + 4], val[8 * k + 5]), pack_bf16(val[8 * k + 6], val[8 * k + 7]));
+}
+
 template <int STAGE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -243,6 +290,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
   float* sRed2 = sBias + 3 * H;                                           // second column sum (stage 3)
   float* sMeta = reinterpret_cast<float*>(smem + SmemLayout::META_OFF);   // [2][128]
   float* sArow = reinterpret_cast<float*>(smem + SmemLayout::AROW_OFF);   // [2][NA][256]
+  uint8_t* sEpi = smem + SmemLayout::EPI_OFF;                             // [8][32][80]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::BAR_OFF);
   uint64_t* full_bar = bars;                         // [NUM_STAGES]
   uint64_t* empty_bar = bars + NUM_STAGES;           // [NUM_STAGES]
@@ -297,6 +345,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * STAGE_BYTES);
           const uint32_t b_base = smem_u32(sW + kc * (H * KCHUNK * 2));
+          if (!(p.dbg & 32))
 #pragma unroll
           for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
             umma_bf16(d_tmem, umma_desc(a_base + ks * UMMA_K * 2), umma_desc(b_base + ks * UMMA_K * 2),
@@ -369,7 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             pf[buf][i][0] = pf[buf][i][1] = make_uint4(0u, 0u, 0u, 0u);
-            if (cur.nc[i] >= 0) {
+            if (cur.nc[i] >= 0 && !(p.dbg & 1)) {
               const uint4* src = reinterpret_cast<const uint4*>(p.AB + (int64_t)cur.nc[i] * 2 * H + H + kc * KCHUNK + chunk * 8);
               pf[buf][i][0] = __ldg(src);
               pf[buf][i][1] = __ldg(src + 1);
@@ -413,7 +462,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
               const float b8[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z),
                                    __uint_as_float(b0.w), __uint_as_float(b1.x), __uint_as_float(b1.y),
                                    __uint_as_float(b1.z), __uint_as_float(b1.w)};
-              if (p.out2) {                          // training: keep a and silu'(u) for the backward pass
+              if (p.out2 && !(p.dbg & 2)) {          // training: keep a and silu'(u) for the backward pass
                 float g8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) silu_and_grad(a8[j] + b8[j] + sVec1[k0 + j] * d2[i], a8[j], g8[j]);
@@ -455,7 +504,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const int64_t e = e0 + (pt >> 3) + RSTEP * i;
-          pf[kc][i] = (e < p.E) ? __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + kc * KCHUNK + chunk * 8))
+          pf[kc][i] = (e < p.E && !(p.dbg & 1)) ? __ldg(reinterpret_cast<const uint4*>(p.in0 + e * H + kc * KCHUNK + chunk * 8))
                                 : make_uint4(0u, 0u, 0u, 0u);
         }
       };
@@ -493,7 +542,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
               float v8[8] = {bf16_lo(in.x), bf16_hi(in.x), bf16_lo(in.y), bf16_hi(in.y),
                              bf16_lo(in.z), bf16_hi(in.z), bf16_lo(in.w), bf16_hi(in.w)};
               if (STAGE == 2) {
-                if (p.out2) {
+                if (p.out2 && !(p.dbg & 2)) {
                   float g8[8];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) silu_and_grad(v8[j], v8[j], g8[j]);
@@ -517,7 +566,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
                   v8[j] = gs;
                 }
                 out = pack8(v8);
-                *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
+                if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(p.out1 + e * H + k0) = out;
               } else {
                 out = in;
 #pragma unroll
@@ -556,140 +605,113 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
     }
   } else if (warp < NUM_EPI_WARPS) {
     // ===================================================================== epilogue
+    // warp (q, half): TMEM lanes 32q..32q+31 (= tile rows), columns half*128 .. +127, in 4 batches of 32.
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* sc = sEpi + warp * EPI_SCRATCH;
     int it = 0;
-    // backward epilogues (stages 3, 4): operand prefetch state carried across tiles
-    const __nv_bfloat16* bw_dsrc = nullptr;
-    const float* bw_gsrc = nullptr;
-    constexpr int EPD = (STAGE == 3) ? 1 : 2;              // batches ahead (stage 3 also streams gagg: 16 more registers per buffer)
-    constexpr int ENB = EPD + 1;
-    uint4 dq[ENB][2];
-    float4 gq[ENB][STAGE == 3 ? 4 : 1];
-    auto bw_fetch = [&](const __nv_bfloat16* dsrc, const float* gsrc, int cb, int buf) {
-      dq[buf][0] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16));
-      dq[buf][1] = __ldg(reinterpret_cast<const uint4*>(dsrc + cb * 16) + 1);
-      if (STAGE == 3) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gq[buf][STAGE == 3 ? k : 0] = __ldg(reinterpret_cast<const float4*>(gsrc + cb * 16) + k);
-      }
+    // operand stream of the backward epilogues (dm / da), fetched one batch ahead, across tile boundaries
+    uint4 nb[4];
+    auto rows_of = [&](int tile) {                 // valid rows of this warp's 32-row slice in `tile`
+      const int64_t r0 = (int64_t)tile * TILE_M + q * 32;
+      const int64_t left = p.E - r0;
+      return left >= 32 ? 32 : (left > 0 ? (int)left : 0);
     };
+    if (STAGE >= 3) {
+      if (p.dbg & 4) { nb[0] = nb[1] = nb[2] = nb[3] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u); }
+      else warp_issue_rows(p.in1 + ((int64_t)blockIdx.x * TILE_M + q * 32) * H + half * 128, lane, rows_of(blockIdx.x), nb);
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
-      const bool valid = e < p.E;
+      const int64_t e0w = (int64_t)tile * TILE_M + q * 32;      // first row of this warp's slice
+      const int64_t e = e0w + lane;
+      const int nrows = rows_of(tile);
+      const bool valid = lane < nrows;
+      const int next_tile = tile + gridDim.x;
       float dot = 0.f;
-      if constexpr (STAGE <= 2) {
-        int dest = -1;
-        if (STAGE == 1 && valid) dest = __ldg(p.row + e);
-        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          const int col0 = half * 128 + cb * 32;
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * H + col0), raw);
-          float val[32];
+      int dest = -1;
+      if ((STAGE == 1 || STAGE == 3) && valid) dest = __ldg(p.row + e);
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[col0 + j];
-          if (STAGE == 1) {
-            if (valid) store_bf16x32(p.out0 + e * H + col0, val);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = silu_fast(val[j]);
-            // segmented sum over the warp's 32 edges: one butterfly transpose-reduce per distinct destination
-            uint32_t todo = __ballot_sync(0xffffffffu, valid);
-            while (todo) {
-              const int leader = __ffs(todo) - 1;
-              const int d0 = __shfl_sync(0xffffffffu, dest, leader);
-              const bool mine = valid && dest == d0;
-              const uint32_t seg = __ballot_sync(0xffffffffu, mine);
-              float w[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) w[j] = mine ? val[j] : 0.f;
-#pragma unroll
-              for (int ofs = 16; ofs >= 1; ofs >>= 1) {
-                const bool up = (lane & ofs) != 0;
-#pragma unroll
-                for (int j = 0; j < ofs; ++j) {
-                  const float keep = up ? w[j + ofs] : w[j];
-                  const float send = up ? w[j] : w[j + ofs];
-                  w[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
-                }
-              }
-              atomicAdd(p.nout + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
-              todo &= ~seg;
-            }
-          } else {
-            if (p.out0 && valid) store_bf16x32(p.out0 + e * H + col0, val);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dot = fmaf(silu_fast(val[j]), sVec1[col0 + j], dot);
+      for (int cb = 0; cb < 4; ++cb) {
+        const int col0 = half * 128 + cb * 32;
+        uint4 dmine[4];
+        if (STAGE >= 3) {
+          warp_deposit_rows(sc, lane, nb, dmine);
+          if (!(p.dbg & 4)) {                      // next batch of the operand stream (next tile after batch 3)
+            if (cb + 1 < 4) warp_issue_rows(p.in1 + e0w * H + col0 + 32, lane, nrows, nb);
+            else if (next_tile < p.num_tiles)
+              warp_issue_rows(p.in1 + ((int64_t)next_tile * TILE_M + q * 32) * H + half * 128, lane, rows_of(next_tile), nb);
           }
         }
-      } else {
-        // backward epilogues: 8 batches of 16 columns; the per-edge operand stream (dm / da) and, for
-        // stage 3, the destination row of gagg are fetched two batches ahead of the TMEM read they meet,
-        // across tile boundaries (three register buffers, indices static after unrolling)
-        if (it == 0) {
-          bw_dsrc = p.in1 + (valid ? e : 0) * H + half * 128;
-          if (STAGE == 3) bw_gsrc = p.nin + (int64_t)(valid ? __ldg(p.row + e) : 0) * H + half * 128;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * H + col0), raw);
+        float val[32];
 #pragma unroll
-          for (int j = 0; j < EPD; ++j) bw_fetch(bw_dsrc, bw_gsrc, j, j);
-        }
-        // operand pointers of this thread's row in the next tile (its row index load overlaps this tile)
-        const int next_tile = tile + gridDim.x;
-        const int64_t en = (int64_t)next_tile * TILE_M + q * 32 + lane;
-        const bool nvalid = next_tile < p.num_tiles && en < p.E;
-        const __nv_bfloat16* n_dsrc = p.in1 + (nvalid ? en : 0) * H + half * 128;
-        int n_dest = 0;
-        if (STAGE == 3 && nvalid) n_dest = __ldg(p.row + en);
-        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-        tc_fence_after();
+        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + (STAGE <= 2 ? sBias[col0 + j] : 0.f);
+        if (STAGE == 3 && !(p.dbg & 4)) {          // + gagg[dest, col0..col0+31]: mostly one row per warp (broadcast)
+          const float4* gsrc = reinterpret_cast<const float4*>(p.nin + (int64_t)(valid ? dest : 0) * H + col0);
 #pragma unroll
-        for (int cb = 0; cb < 8; ++cb) {
-          // buffer of batch cb is (cb + 2 * it_par) % 3 -- kept static by rotating the buffers per tile below
-          if (cb + EPD < 8) bw_fetch(bw_dsrc, bw_gsrc, cb + EPD, (cb + EPD) % ENB);
-          else if (next_tile < p.num_tiles) {
-            const float* n_gsrc = (STAGE == 3) ? p.nin + (int64_t)n_dest * H + half * 128 : nullptr;
-            bw_fetch(n_dsrc, n_gsrc, cb + EPD - 8, (cb + EPD) % ENB);
-          }
-          const int col0 = half * 128 + cb * 16;
-          uint32_t raw[16];
-          tmem_ld16(tmem_base + lane_base + (uint32_t)(acc * H + col0), raw);
-          const uint4 d0 = dq[cb % ENB][0], d1 = dq[cb % ENB][1];
-          const float dd[16] = {bf16_lo(d0.x), bf16_hi(d0.x), bf16_lo(d0.y), bf16_hi(d0.y), bf16_lo(d0.z), bf16_hi(d0.z),
-                                bf16_lo(d0.w), bf16_hi(d0.w), bf16_lo(d1.x), bf16_hi(d1.x), bf16_lo(d1.y), bf16_hi(d1.y),
-                                bf16_lo(d1.z), bf16_hi(d1.z), bf16_lo(d1.w), bf16_hi(d1.w)};
-          float val[16];
+          for (int hh = 0; hh < 2; ++hh) {
+            float4 g4[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(raw[j]);
-          if (STAGE == 3) {
+            for (int k = 0; k < 4; ++k) g4[k] = __ldg(gsrc + 4 * hh + k);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float4 g = gq[cb % ENB][STAGE == 3 ? k : 0];
-              val[4 * k] += g.x; val[4 * k + 1] += g.y; val[4 * k + 2] += g.z; val[4 * k + 3] += g.w;
+              val[16 * hh + 4 * k] += g4[k].x; val[16 * hh + 4 * k + 1] += g4[k].y;
+              val[16 * hh + 4 * k + 2] += g4[k].z; val[16 * hh + 4 * k + 3] += g4[k].w;
             }
           }
+        }
+        if (STAGE >= 3) {
+          const uint32_t dw[16] = {dmine[0].x, dmine[0].y, dmine[0].z, dmine[0].w, dmine[1].x, dmine[1].y, dmine[1].z, dmine[1].w,
+                                   dmine[2].x, dmine[2].y, dmine[2].z, dmine[2].w, dmine[3].x, dmine[3].y, dmine[3].z, dmine[3].w};
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            val[j] *= dd[j];
-            if (STAGE == 4) dot = fmaf(val[j], sVec1[col0 + j], dot);
+            val[2 * j] *= bf16_lo(dw[j]);
+            val[2 * j + 1] *= bf16_hi(dw[j]);
           }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out0 + e * H + col0);
-            dst[0] = make_uint4(pack_bf16(val[0], val[1]), pack_bf16(val[2], val[3]), pack_bf16(val[4], val[5]),
-                                pack_bf16(val[6], val[7]));
-            dst[1] = make_uint4(pack_bf16(val[8], val[9]), pack_bf16(val[10], val[11]), pack_bf16(val[12], val[13]),
-                                pack_bf16(val[14], val[15]));
+          if (STAGE == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(val[j], sVec1[col0 + j], dot);
           }
         }
-        // next tile's first EPD batches sit in buffers (8 + j) % ENB; move them to j so that batch cb is always
-        // in buffer cb % ENB (ENB == 2: 8 % 2 == 0, nothing to do; ENB == 3: (2, 0) -> (0, 1))
-        if constexpr (ENB == 3) {
-          dq[1][0] = dq[0][0]; dq[1][1] = dq[0][1];
-          dq[0][0] = dq[2][0]; dq[0][1] = dq[2][1];
+        if ((STAGE != 2 || p.out0) && !(p.dbg & 8)) {       // v (stage 1), s (stage 2), gv (stage 3), gu (stage 4)
+          uint4 packed[4];
+          pack32(val, packed);
+          warp_store_rows(sc, lane, packed, p.out0 + e0w * H + col0, nrows);
         }
-        bw_dsrc = n_dsrc;
-        if (STAGE == 3) bw_gsrc = p.nin + (int64_t)n_dest * H + half * 128;
+        if (STAGE == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = silu_fast(val[j]);
+          // segmented sum over the warp's 32 edges: one butterfly transpose-reduce per distinct destination
+          uint32_t todo = (p.dbg & 16) ? 0u : __ballot_sync(0xffffffffu, valid);
+          while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int d0 = __shfl_sync(0xffffffffu, dest, leader);
+            const bool mine = valid && dest == d0;
+            const uint32_t seg = __ballot_sync(0xffffffffu, mine);
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = mine ? val[j] : 0.f;
+#pragma unroll
+            for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+              const bool up = (lane & ofs) != 0;
+#pragma unroll
+              for (int j = 0; j < ofs; ++j) {
+                const float keep = up ? w[j + ofs] : w[j];
+                const float send = up ? w[j] : w[j + ofs];
+                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+              }
+            }
+            atomicAdd(p.nout + (int64_t)d0 * H + col0 + lane, w[0]);   // lane l holds column col0 + l
+            todo &= ~seg;
+          }
+        } else if (STAGE == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dot = fmaf(silu_fast(val[j]), sVec1[col0 + j], dot);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);               // accumulator stage drained
@@ -727,6 +749,11 @@ static int launch(Params& p, cudaStream_t st) {
     configured = true;
   }
   p.num_tiles = (int)((p.E + TILE_M - 1) / TILE_M);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("PEV_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   const int sms = sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   edge_mlp_kernel<STAGE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
