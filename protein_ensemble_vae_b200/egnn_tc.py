@@ -47,6 +47,42 @@ def packed_weight(W: torch.Tensor, transpose: bool = False, cache: dict | None =
     return out
 
 
+class _tf32_matmul:
+    """Context: allow TF32 tensor-core GEMMs for plain fp32 ``torch.matmul`` calls (restores the flag on exit)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+class NodeLinear(torch.autograd.Function):
+    """``x W^T + b`` for the node-level linears of the bf16 path (plain library GEMMs).
+
+    Forward in true fp32 (it feeds the 1e-2 output budget); the two backward products ``g W`` and ``g^T x`` run
+    on the tensor cores in TF32 -- gradients of the bf16 path already carry the bf16 edge MLP's noise (5e-2
+    relative, tools/grad_diag.py), three orders of magnitude above TF32's 5e-4.
+    """
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        return torch.addmm(b, x, W.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        with _tf32_matmul():
+            gx = g @ W if ctx.needs_input_grad[0] else None
+            gW = g.t() @ x if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.needs_input_grad[2] else None
+        return gx, gW, gb
+
+
 def _wgrad(g_bf16: torch.Tensor, act_bf16: torch.Tensor) -> torch.Tensor:
     """``g^T @ act`` over the edge dimension ([256,E] x [E,256]); plain library GEMM (cuBLAS bf16, fp32 out)."""
     try:
@@ -141,12 +177,13 @@ def egn_layer_bf16(layer, h, x, g: PackedGraph, dinv):
     W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
     Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                      # [512, 256]
     bias = torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
-    AB = torch.addmm(bias, h, Wcat.t())                                   # [N, 512]
+    AB = NodeLinear.apply(h, Wcat, bias)                                  # [N, 512]
     caches = layer.__dict__.setdefault("_pev_packed", ({}, {}))
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
     agg, x_new = FusedEdgeBF16.apply(AB, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
                                      layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
                                      layer.phi_x[2].bias, dinv, g, keep, caches)
-    h_new = layer.norm_h(h + layer.phi_h(torch.cat([h, agg], -1)))
+    q = layer.phi_h[1](NodeLinear.apply(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias))
+    h_new = layer.norm_h(h + NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias))
     return h_new, x_new
