@@ -101,11 +101,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// L2 prefetch of a contiguous global range through the TMA engine (no shared-memory destination)
-__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
                : "memory");
@@ -530,13 +525,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
 #pragma unroll
         for (int i = 0; i < RPT; ++i) rw_cur[i] = rw_nxt[i];
         if (next_tile < p.num_tiles) issue_rw(next_tile);
-        if (pt == 0 && !(p.dbg & 64)) {            // pull the tile two ahead (one contiguous 64 KB block) into L2
-          const int64_t ep = ((int64_t)tile + 2 * (int64_t)gridDim.x) * TILE_M;
-          if (ep < p.E) {
-            const int64_t rows = (p.E - ep) < TILE_M ? (p.E - ep) : TILE_M;
-            l2_prefetch(p.in0 + ep * H, (uint32_t)(rows * H * 2));
-          }
-        }
 #pragma unroll
         for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
           if (kc + PD < NUM_KCHUNKS) issue(tile, kc + PD);
@@ -643,13 +631,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) edge_mlp_kernel(const Params p
       float dot = 0.f;
       int dest = -1;
       if ((STAGE == 1 || STAGE == 3) && valid) dest = __ldg(p.row + e);
-      if (STAGE >= 3 && half == 0 && lane == 0 && !(p.dbg & 64)) {   // operand rows of this slice, two tiles ahead
-        const int t2 = tile + 2 * gridDim.x;
-        if (t2 < p.num_tiles) {
-          const int n2 = rows_of(t2);
-          if (n2 > 0) l2_prefetch(p.in1 + ((int64_t)t2 * TILE_M + q * 32) * H, (uint32_t)(n2 * H * 2));
-        }
-      }
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll
