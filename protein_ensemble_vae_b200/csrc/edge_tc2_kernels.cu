@@ -1,0 +1,654 @@
+// K1, bf16 tensor-core form, second generation ("v2"): the EGNN edge MLP (models/en_gnn_decoder.py:60-79) and its
+// backward on tcgen05, organised so that the CUDA-core roles stay near the MUFU floor (one tanh per activation):
+//
+//   * half domain: every pre-activation is carried as h = z/2 (the 1/2 is folded into the packed weights, the biases
+//     and the node-level A|B projections), so silu(z) = h + h tanh(h) and silu'(z) = (1 + r)/2 need no extra scaling;
+//   * orientation by epilogue: a GEMM whose epilogue reduces over EDGES (segment sums agg / column sums) is issued
+//     transposed, D^T[feature, edge] = W . X^T, so that a TMEM lane is a feature and the 32 registers of a tcgen05.ld
+//     are 32 consecutive edges -- segment sums become in-thread adds, stores and node loads are coalesced across lanes;
+//     a GEMM whose epilogue reduces over FEATURES (w = t.w6, gd2 = gu.wd) keeps lane = edge;
+//   * per-edge tensors that are produced by a feature-lane epilogue are kept in HBM as "tile images": per 128-edge tile
+//     a 64 KB block [fq 4][eh 2][fg 8][r 8][128 B] (feature f = 64 fq + 8 fg + r, edge e = 64 eh + 8 c + i stored at
+//     16-byte chunk c ^ r) -- exactly the SWIZZLE_128B shared-memory image of the tile, which the tensor core reads
+//     either as an MN-major operand (M = edges) or as a K-major operand (K = edges), so consumers copy it verbatim.
+//
+//   fwd1  hu = Ah_i + Bh_j + wdh d2 ; a = silu  --GEMM W2h (transposed)-->  hv (+b2h) -> HBM tile image,
+//         m = silu ; agg[row] += m (in-thread segment sums, one RED per segment per feature)
+//   fwd2  m = silu(hv)  --GEMM W5h (A operand MN-major)-->  hs (+b5h) [-> HBM, training], t = silu, w[e] = t.w6 + b6
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "../../include/pev_b200.h"
+#include "pev_common.cuh"
+#include "tc_common.cuh"
+
+namespace pev {
+namespace tc2 {
+using namespace tcx;
+
+constexpr int H = 256;
+constexpr int TILE_M = 128;             // edges per tile
+constexpr int KCHUNK = 64;              // bf16 per 128-byte swizzle row
+constexpr int NUM_KCHUNKS = H / KCHUNK;
+constexpr int UMMA_K = 16;
+constexpr int NUM_STAGES = 4;           // operand ring: 4 x 16 KB = one tile in flight
+constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
+constexpr int W_BYTES = H * H * 2;
+constexpr int TILE_IMG_BYTES = TILE_M * H * 2;   // 64 KB tile image
+constexpr int NA = 4;                   // destination rows of a tile staged in shared memory (fwd1 producer)
+constexpr int NUM_EPI_WARPS = 8;        // warps 0..7
+constexpr int MMA_WARP = 8;             // warp 8 (+ 9..11 register donors)
+constexpr int PROD_WARP0 = 12;          // warps 12..19
+constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (PROD_WARP0 + NUM_PROD_WARPS);   // 640
+constexpr int NUM_PROD_THREADS = 32 * NUM_PROD_WARPS;
+constexpr int NUM_EPI_THREADS = 32 * NUM_EPI_WARPS;
+constexpr int REGS_MMA_WG = 40;
+constexpr int REGS_PROD = 120;
+constexpr int TMEM_COLS = 512;
+
+struct Smem {
+  static constexpr int W_OFF = 0;
+  static constexpr int A_OFF = W_BYTES;
+  static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 4 x 256 floats
+  static constexpr int META_OFF = VEC_OFF + 4 * H * 4;                  // 2 x 128 floats
+  static constexpr int AROW_OFF = META_OFF + 2 * TILE_M * 4;            // 2 x NA x 256 floats
+  static constexpr int BAR_OFF = AROW_OFF + 2 * NA * H * 4;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+constexpr int SMEM_BYTES = Smem::TOTAL + 1024;
+
+struct Bars {
+  uint64_t* full;     // [NUM_STAGES] producers -> MMA
+  uint64_t* empty;    // [NUM_STAGES] MMA -> producers
+  uint64_t* tfull;    // [2] MMA -> epilogue
+  uint64_t* tempty;   // [2] epilogue -> MMA
+  uint64_t* w;        // weight image landed
+  uint32_t* tmem_slot;
+};
+__device__ __forceinline__ Bars make_bars(uint8_t* smem) {
+  uint64_t* b = reinterpret_cast<uint64_t*>(smem + Smem::BAR_OFF);
+  return Bars{b, b + NUM_STAGES, b + 2 * NUM_STAGES, b + 2 * NUM_STAGES + 2, b + 2 * NUM_STAGES + 4,
+              reinterpret_cast<uint32_t*>(b + 2 * NUM_STAGES + 5)};
+}
+__device__ __forceinline__ void init_bars(const Bars& B, int full_count) {
+  for (int s = 0; s < NUM_STAGES; ++s) {
+    mbar_init(&B.full[s], full_count);
+    mbar_init(&B.empty[s], 1);
+  }
+  for (int a = 0; a < 2; ++a) {
+    mbar_init(&B.tfull[a], 1);
+    mbar_init(&B.tempty[a], NUM_EPI_THREADS);
+  }
+  mbar_init(B.w, 1);
+  fence_barrier_init();
+}
+__device__ __forceinline__ void load_weight_image(uint8_t* sW, const void* Wp, uint64_t* bar) {
+  mbar_arrive_expect_tx(bar, W_BYTES);
+  for (int i = 0; i < W_BYTES / 16384; ++i)
+    bulk_g2s(sW + i * 16384, reinterpret_cast<const uint8_t*>(Wp) + i * 16384, 16384, bar);
+  mbar_wait(bar, 0);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+  return make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+}
+__device__ __forceinline__ void unpack8(const uint4 v, float (&o)[8]) {
+  o[0] = bf16_lo(v.x); o[1] = bf16_hi(v.x); o[2] = bf16_lo(v.y); o[3] = bf16_hi(v.y);
+  o[4] = bf16_lo(v.z); o[5] = bf16_hi(v.z); o[6] = bf16_lo(v.w); o[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ float sum32(const float (&m)[32]) {
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = (m[j] + m[j + 8]) + (m[j + 16] + m[j + 24]);
+  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+// =================================================================================================== fwd1
+struct Fwd1Params {
+  const float* ABh;       // [N,512] fp32, half domain: 0.5 (h Wa^T + b1) | 0.5 h Wb^T
+  const float* x;         // [N,3]
+  const int32_t* row;     // [E]
+  const int32_t* col;     // [E]
+  const float* wd;        // [256] (full domain; halved on load)
+  const float* b2;        // [256] (full domain; halved on load)
+  const void* W2hp;       // packed image of 0.5 W2
+  uint8_t* hvT;           // [num_tiles] x 64 KB tile images of hv = v/2 (bf16)
+  float* agg;             // [N,256] (+=)
+  int64_t E;
+  int num_tiles;
+  int dbg;                // PEV_TC2_DEBUG bit mask (profiling experiments only; 0 in production)
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem + Smem::W_OFF;
+  uint8_t* sA = smem + Smem::A_OFF;
+  float* sWd = reinterpret_cast<float*>(smem + Smem::VEC_OFF);
+  float* sMeta = reinterpret_cast<float*>(smem + Smem::META_OFF);
+  float* sArow = reinterpret_cast<float*>(smem + Smem::AROW_OFF);
+  const Bars B = make_bars(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int k = threadIdx.x; k < H; k += NUM_THREADS) sWd[k] = 0.5f * p.wd[k];
+  if (threadIdx.x == 0) init_bars(B, NUM_PROD_THREADS);
+  if (warp == MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *B.tmem_slot;
+
+  if (warp >= MMA_WARP && warp < PROD_WARP0) {
+    // ------------------------------------------------------------------ MMA issue: D^T[f, e] = W2h[f, :] . a[e, :]
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA_WG));
+    if (warp == MMA_WARP && lane == 0) {
+      load_weight_image(sW, p.W2hp, B.w);
+      constexpr uint32_t IDESC = idesc_bf16(128, 128, false, false);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&B.tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * H;
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.full[stage], phase);
+          tc_fence_after();
+          const uint32_t x_base = smem_u32(sA + stage * STAGE_BYTES);           // activations: [128 e][64 k]
+          const uint32_t w_base = smem_u32(sW + kc * (H * KCHUNK * 2));          // weights:     [256 f][64 k]
+#pragma unroll
+          for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)
+              if (!(p.dbg & 32)) umma_bf16(d0 + mh * 128, desc_kmajor(w_base + mh * 16384 + ks * UMMA_K * 2),
+                        desc_kmajor(x_base + ks * UMMA_K * 2), IDESC, (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&B.empty[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&B.tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= PROD_WARP0) {
+    // ------------------------------------------------------------------ producers: a = silu(hu) -> K-major ring
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    const int pt = threadIdx.x - 32 * PROD_WARP0;
+    const int chunk = pt & 7;
+    constexpr int RPT = (TILE_M * 8) / NUM_PROD_THREADS;    // 4 rows per thread per K-chunk
+    constexpr int RSTEP = NUM_PROD_THREADS / 8;             // 32
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    struct TileIdx { int mr, mc, rf, rl, nr[RPT], nc[RPT]; };
+    auto load_idx = [&](int tile, TileIdx& t) {
+      const int64_t e0 = (int64_t)tile * TILE_M;
+      const int64_t rem = p.E - e0;
+      const int nvalid = rem < TILE_M ? (int)rem : TILE_M;
+      t.mr = t.mc = -1;
+      if (pt < nvalid) { t.mr = __ldg(p.row + e0 + pt); t.mc = __ldg(p.col + e0 + pt); }
+      t.rf = __ldg(p.row + e0);
+      t.rl = __ldg(p.row + e0 + nvalid - 1);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = (pt >> 3) + RSTEP * i;
+        t.nr[i] = t.nc[i] = -1;
+        if (r < nvalid) { t.nr[i] = __ldg(p.row + e0 + r); t.nc[i] = __ldg(p.col + e0 + r); }
+      }
+    };
+    TileIdx nxt;
+    load_idx(blockIdx.x, nxt);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if (p.dbg & 64) {                                  // role ablation: ring handshake only
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.empty[stage], phase ^ 1);
+          fence_proxy_async();
+          mbar_arrive(&B.full[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
+      const TileIdx cur = nxt;
+      if (tile + (int)gridDim.x < p.num_tiles) load_idx(tile + gridDim.x, nxt);
+      float* meta = sMeta + (it & 1) * TILE_M;
+      float* arow = sArow + (it & 1) * NA * H;
+      const int span = cur.rl - cur.rf + 1;
+      const bool staged = span <= NA;
+      float xr[3] = {0.f, 0.f, 0.f}, xc[3] = {0.f, 0.f, 0.f};
+      if (cur.mr >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          xr[k] = __ldg(p.x + 3 * (int64_t)cur.mr + k);
+          xc[k] = __ldg(p.x + 3 * (int64_t)cur.mc + k);
+        }
+      }
+      float4 ar[(NA * H / 4) / NUM_PROD_THREADS];
+#pragma unroll
+      for (int j = 0; j < (NA * H / 4) / NUM_PROD_THREADS; ++j) {
+        const int idx = pt + NUM_PROD_THREADS * j;
+        ar[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (staged && idx < span * (H / 4))
+          ar[j] = __ldg(reinterpret_cast<const float4*>(p.ABh + (int64_t)(cur.rf + idx / (H / 4)) * 2 * H) + idx % (H / 4));
+      }
+      uint4 pf[2][RPT][2];
+      auto issue_b = [&](int kc, int buf) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          pf[buf][i][0] = pf[buf][i][1] = make_uint4(0u, 0u, 0u, 0u);
+          if (cur.nc[i] >= 0 && !(p.dbg & 1)) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.ABh + (int64_t)cur.nc[i] * 2 * H + H + kc * KCHUNK + chunk * 8);
+            pf[buf][i][0] = __ldg(src);
+            pf[buf][i][1] = __ldg(src + 1);
+          }
+        }
+      };
+      issue_b(0, 0);
+      if (pt < TILE_M) {
+        const float dx = xr[0] - xc[0], dy = xr[1] - xc[1], dz = xr[2] - xc[2];
+        meta[pt] = dx * dx + dy * dy + dz * dz;
+      }
+#pragma unroll
+      for (int j = 0; j < (NA * H / 4) / NUM_PROD_THREADS; ++j)
+        reinterpret_cast<float4*>(arow)[pt + NUM_PROD_THREADS * j] = ar[j];
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      float d2[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) d2[i] = meta[(pt >> 3) + RSTEP * i];
+#pragma unroll
+      for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+        if (kc + 1 < NUM_KCHUNKS) issue_b(kc + 1, (kc + 1) & 1);
+        mbar_wait(&B.empty[stage], phase ^ 1);
+        uint8_t* st = sA + stage * STAGE_BYTES;
+        const int k0 = kc * KCHUNK + chunk * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(sWd + k0), w1 = *reinterpret_cast<const float4*>(sWd + k0 + 4);
+        const float wd8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = (pt >> 3) + RSTEP * i;
+          uint4 out = make_uint4(0u, 0u, 0u, 0u);
+          if (cur.nr[i] >= 0) {
+            float4 a0, a1;
+            if (staged) {
+              const float4* src = reinterpret_cast<const float4*>(arow + (cur.nr[i] - cur.rf) * H + k0);
+              a0 = src[0]; a1 = src[1];
+            } else {
+              const float4* src = reinterpret_cast<const float4*>(p.ABh + (int64_t)cur.nr[i] * 2 * H + k0);
+              a0 = __ldg(src); a1 = __ldg(src + 1);
+            }
+            const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const uint4 b0 = pf[kc & 1][i][0], b1 = pf[kc & 1][i][1];
+            const float b8[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z),
+                                 __uint_as_float(b0.w), __uint_as_float(b1.x), __uint_as_float(b1.y),
+                                 __uint_as_float(b1.z), __uint_as_float(b1.w)};
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float hu = fmaf(wd8[j], d2[i], a8[j] + b8[j]);
+              o8[j] = (p.dbg & 16) ? hu : silu_h(hu);
+            }
+            out = pack8(o8);
+          }
+          *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
+        }
+        fence_proxy_async();
+        mbar_arrive(&B.full[stage]);
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane = feature, registers = edges
+    const int q = warp & 3, mh = warp >> 2;
+    const int f = mh * 128 + q * 32 + lane;
+    const float bias = 0.5f * __ldg(p.b2 + f);
+    float* aggcol = p.agg + f;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 128);
+    // tile-image offset of this thread's 128-byte row (feature f), edge half 0
+    const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
+    const int sw = f & 7;
+    auto flush = [&](int r, float s) {
+      if (r >= 0 && !(p.dbg & 4)) atomicAdd(aggcol + (int64_t)r * H, s);
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int64_t e0 = (int64_t)tile * TILE_M;
+      int myrow[4];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const int64_t e = e0 + cb * 32 + lane;
+        myrow[cb] = e < p.E ? __ldg(p.row + e) : -1;
+      }
+      uint8_t* img = p.hvT + (int64_t)tile * TILE_IMG_BYTES + img_row;
+      mbar_wait(&B.tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (p.dbg & 128) {                                 // role ablation: accumulator handshake only
+        tc_fence_before();
+        mbar_arrive(&B.tempty[acc]);
+        continue;
+      }
+      int cur = __shfl_sync(0xffffffffu, myrow[0], 0);
+      float seg = 0.f;
+      uint32_t raw[32];
+      tmem_ld32_issue(lane_addr + acc * H, raw);
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        tmem_wait();
+        float val[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + bias;
+        if (cb + 1 < 4) tmem_ld32_issue(lane_addr + acc * H + (cb + 1) * 32, raw);
+        else {
+          tc_fence_before();
+          mbar_arrive(&B.tempty[acc]);            // accumulator stage fully read
+        }
+        // hv -> HBM tile image (bf16): this thread's 32 edges are 4 chunks of its 128-byte row
+        uint8_t* dst = img + (cb >> 1) * 8192;
+        if (!(p.dbg & 2))
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
+                               val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
+          *reinterpret_cast<uint4*>(dst + ((((cb & 1) * 4 + k) ^ sw) << 4)) = pack8(o8);
+        }
+        float m[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m[j] = (p.dbg & 8) ? val[j] : silu_h(val[j]);
+        // segment sums over the 32 edges (uniform control flow: every lane sees the same edges)
+        int prev = __shfl_up_sync(0xffffffffu, myrow[cb], 1);
+        if (lane == 0) prev = cur;
+        const uint32_t bm = __ballot_sync(0xffffffffu, myrow[cb] != prev);
+        if (bm == 0u) {
+          seg += sum32(m);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if ((bm >> j) & 1u) {
+              flush(cur, seg);
+              seg = 0.f;
+              cur = __shfl_sync(0xffffffffu, myrow[cb], j);
+            }
+            seg += m[j];
+          }
+        }
+      }
+      flush(cur, seg);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =================================================================================================== fwd2
+struct Fwd2Params {
+  const uint8_t* hvT;     // tile images of hv
+  const void* W5hp;       // packed image of 0.5 W5
+  const float* b5;        // [256] full domain
+  const float* w6;        // [256]
+  const float* b6;        // [1]
+  __nv_bfloat16* hs;      // [E,256] hs = s/2 (training) or null
+  float* w;               // [E] (+=, zeroed by the launcher)
+  int64_t E;
+  int num_tiles;
+  int dbg;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem + Smem::W_OFF;
+  uint8_t* sA = smem + Smem::A_OFF;
+  float* sBias = reinterpret_cast<float*>(smem + Smem::VEC_OFF);
+  float* sW6 = sBias + H;
+  const Bars B = make_bars(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
+    sBias[k] = 0.5f * p.b5[k];
+    sW6[k] = p.w6[k];
+  }
+  if (threadIdx.x == 0) init_bars(B, NUM_PROD_THREADS);
+  if (warp == MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *B.tmem_slot;
+
+  if (warp >= MMA_WARP && warp < PROD_WARP0) {
+    // ------------------------------------------------------------------ MMA issue: D[e, n] = m[e, :] . W5h[n, :]
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA_WG));
+    if (warp == MMA_WARP && lane == 0) {
+      load_weight_image(sW, p.W5hp, B.w);
+      constexpr uint32_t IDESC = idesc_bf16(128, 256, true, false);             // A (activations) MN-major
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&B.tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * H;
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.full[stage], phase);
+          tc_fence_after();
+          const uint32_t x_base = smem_u32(sA + stage * STAGE_BYTES);           // [eh 2][fg 8][r 8][128 B]
+          const uint32_t w_base = smem_u32(sW + kc * (H * KCHUNK * 2));
+#pragma unroll
+          for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
+            if (!(p.dbg & 32)) umma_bf16(d0, desc_mnmajor(x_base + ks * 2048, 8192, 1024), desc_kmajor(w_base + ks * UMMA_K * 2), IDESC,
+                      (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&B.empty[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&B.tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= PROD_WARP0) {
+    // ------------------------------------------------------------------ producers: m = silu(hv), image -> ring verbatim
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    const int pt = threadIdx.x - 32 * PROD_WARP0;
+    constexpr int CPT = STAGE_BYTES / 16 / NUM_PROD_THREADS;   // 16-byte chunks per thread per stage (4)
+    constexpr int PD = 3;                                      // stages of load-ahead
+    int stage = 0;
+    uint32_t phase = 0;
+    uint4 pf[NUM_KCHUNKS][CPT];
+    auto issue = [&](int tile, int kc) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.hvT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES);
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) pf[kc][i] = (p.dbg & 1) ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + pt + NUM_PROD_THREADS * i);
+    };
+#pragma unroll
+    for (int kc = 0; kc < PD; ++kc) issue(blockIdx.x, kc);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int next_tile = tile + gridDim.x;
+      if (p.dbg & 64) {
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.empty[stage], phase ^ 1);
+          fence_proxy_async();
+          mbar_arrive(&B.full[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+        if (kc + PD < NUM_KCHUNKS) issue(tile, kc + PD);
+        else if (next_tile < p.num_tiles) issue(next_tile, kc + PD - NUM_KCHUNKS);
+        mbar_wait(&B.empty[stage], phase ^ 1);
+        uint4* st = reinterpret_cast<uint4*>(sA + stage * STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float v8[8];
+          unpack8(pf[kc][i], v8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v8[j] = silu_h(v8[j]);
+          st[pt + NUM_PROD_THREADS * i] = pack8(v8);
+        }
+        fence_proxy_async();
+        mbar_arrive(&B.full[stage]);
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane = edge, registers = features
+    const int q = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+    const float b6 = half == 0 ? __ldg(p.b6) : 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
+      const bool valid = e < p.E;
+      float dot = 0.f;
+      mbar_wait(&B.tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (p.dbg & 128) {
+        tc_fence_before();
+        mbar_arrive(&B.tempty[acc]);
+        continue;
+      }
+      uint32_t raw[32];
+      tmem_ld32_issue(lane_addr + acc * H, raw);
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const int col0 = half * 128 + cb * 32;
+        tmem_wait();
+        float val[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j4);
+          val[4 * j4] = __uint_as_float(raw[4 * j4]) + b.x;
+          val[4 * j4 + 1] = __uint_as_float(raw[4 * j4 + 1]) + b.y;
+          val[4 * j4 + 2] = __uint_as_float(raw[4 * j4 + 2]) + b.z;
+          val[4 * j4 + 3] = __uint_as_float(raw[4 * j4 + 3]) + b.w;
+        }
+        if (cb + 1 < 4) tmem_ld32_issue(lane_addr + acc * H + (cb + 1) * 32, raw);
+        else {
+          tc_fence_before();
+          mbar_arrive(&B.tempty[acc]);
+        }
+        if (p.hs && valid && !(p.dbg & 2)) {
+          uint4* dst = reinterpret_cast<uint4*>(p.hs + e * H + col0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
+                                 val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
+            dst[k] = pack8(o8);
+          }
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 w = *reinterpret_cast<const float4*>(sW6 + col0 + 4 * j4);
+          dot = fmaf(silu_h(val[4 * j4]), w.x, dot);
+          dot = fmaf(silu_h(val[4 * j4 + 1]), w.y, dot);
+          dot = fmaf(silu_h(val[4 * j4 + 2]), w.z, dot);
+          dot = fmaf(silu_h(val[4 * j4 + 3]), w.w, dot);
+        }
+      }
+      if (valid) atomicAdd(p.w + e, dot + b6);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// fp32 [256,256] (out,in) -> bf16 image of scale * W (or scale * W^T): 4 K-blocks of [256 rows x 128 B], SWIZZLE_128B
+__global__ void pack_weight_scaled_kernel(const float* __restrict__ W, int transpose, float scale,
+                                          __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * H) return;
+  const int n = idx / H, k = idx % H;
+  const float v = scale * (transpose ? W[k * H + n] : W[n * H + k]);
+  const int kb = k / KCHUNK, kl = k % KCHUNK;
+  const uint32_t byte = kb * (H * KCHUNK * 2) + sw128_offset(n, kl >> 3) + (kl & 7) * 2;
+  out[byte >> 1] = __float2bfloat16(v);
+}
+
+template <typename K>
+static int configure(K kernel, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(2, "%s: %s", name, cudaGetErrorString(e));
+  return 0;
+}
+static int debug_mask() {
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("PEV_TC2_DEBUG"); dbg = e ? atoi(e) : 0; }
+  return dbg;
+}
+static int grid_for(int num_tiles) {
+  const int sms = sm_count();
+  return num_tiles < sms ? num_tiles : sms;
+}
+
+}  // namespace tc2
+}  // namespace pev
+
+using namespace pev;
+typedef __nv_bfloat16 bf16_t;
+
+extern "C" {
+
+int pev_pack_weight_bf16_scaled(const float* W, int32_t transpose, float scale, void* packed, void* stream) {
+  PEV_REQUIRE(W && packed, "null argument");
+  tc2::pack_weight_scaled_kernel<<<(tc2::H * tc2::H + 255) / 256, 256, 0, as_stream(stream)>>>(
+      W, transpose, scale, reinterpret_cast<bf16_t*>(packed));
+  return after_launch("pack_weight_scaled_kernel");
+}
+
+int64_t pev_edge2_tile_image_bytes(int64_t num_edges) {
+  return ((num_edges + tc2::TILE_M - 1) / tc2::TILE_M) * (int64_t)tc2::TILE_IMG_BYTES;
+}
+
+int pev_edge2_fwd1(const float* ABh, const float* x, const float* wd, const void* W2hp, const float* b2,
+                   const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges, void* hvT, float* agg,
+                   void* stream) {
+  PEV_REQUIRE(ABh && x && wd && W2hp && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc2::H * (size_t)num_nodes, st);
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(row && col && hvT, "edge arrays missing");
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = tc2::configure(tc2::fwd1_kernel, "fwd1_kernel")) return rc;
+    configured = true;
+  }
+  tc2::Fwd1Params p = {};
+  p.ABh = ABh; p.x = x; p.row = row; p.col = col; p.wd = wd; p.b2 = b2; p.W2hp = W2hp;
+  p.hvT = reinterpret_cast<uint8_t*>(hvT); p.agg = agg; p.E = num_edges;
+  p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
+  p.dbg = tc2::debug_mask();
+  tc2::fwd1_kernel<<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  return after_launch("edge2_fwd1_kernel");
+}
+
+int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const float* w6, const float* b6,
+                   int64_t num_edges, float* w_out, void* hs_out, void* stream) {
+  PEV_REQUIRE(W5hp && b5 && w6 && b6 && num_edges >= 0, "bad argument");
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(hvT && w_out, "edge arrays missing");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = tc2::configure(tc2::fwd2_kernel, "fwd2_kernel")) return rc;
+    configured = true;
+  }
+  tc2::Fwd2Params p = {};
+  p.hvT = reinterpret_cast<const uint8_t*>(hvT); p.W5hp = W5hp; p.b5 = b5; p.w6 = w6; p.b6 = b6;
+  p.hs = reinterpret_cast<bf16_t*>(hs_out); p.w = w_out; p.E = num_edges;
+  p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
+  p.dbg = tc2::debug_mask();
+  tc2::fwd2_kernel<<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  return after_launch("edge2_fwd2_kernel");
+}
+
+}  // extern "C"
