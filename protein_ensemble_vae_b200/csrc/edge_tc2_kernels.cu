@@ -36,25 +36,26 @@ constexpr int NUM_STAGES = 4;           // operand ring: 4 x 16 KB = one tile in
 constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
 constexpr int W_BYTES = H * H * 2;
 constexpr int TILE_IMG_BYTES = TILE_M * H * 2;   // 64 KB tile image
-constexpr int NA = 4;                   // destination rows of a tile staged in shared memory (fwd1 producer)
-constexpr int NUM_EPI_WARPS = 8;        // warps 0..7
-constexpr int MMA_WARP = 8;             // warp 8 (+ 9..11 register donors)
-constexpr int PROD_WARP0 = 12;          // warps 12..19
-constexpr int NUM_PROD_WARPS = 8;
-constexpr int NUM_THREADS = 32 * (PROD_WARP0 + NUM_PROD_WARPS);   // 640
-constexpr int NUM_PROD_THREADS = 32 * NUM_PROD_WARPS;
+// Warp roles, aligned to warpgroups so that setmaxnreg can move registers between them:
+//   warps 0..7 epilogue (TMEM lane quarter = warp % 4), warp 8 MMA issue (+ 9..11 register donors),
+//   warps 12..27 producers.  896 threads x 72 registers at launch; then MMA group 40, producers 64, epilogue 104.
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int MMA_WARP = 8;
+constexpr int PROD_WARP0 = 12;
+constexpr int NUM_PROD_WARPS = 16;
+constexpr int NUM_THREADS = 32 * (PROD_WARP0 + NUM_PROD_WARPS);   // 896
+constexpr int NUM_PROD_THREADS = 32 * NUM_PROD_WARPS;             // 512
 constexpr int NUM_EPI_THREADS = 32 * NUM_EPI_WARPS;
 constexpr int REGS_MMA_WG = 40;
-constexpr int REGS_PROD = 120;
+constexpr int REGS_PROD = 64;
+constexpr int REGS_EPI = 104;
 constexpr int TMEM_COLS = 512;
 
 struct Smem {
   static constexpr int W_OFF = 0;
   static constexpr int A_OFF = W_BYTES;
   static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 4 x 256 floats
-  static constexpr int META_OFF = VEC_OFF + 4 * H * 4;                  // 2 x 128 floats
-  static constexpr int AROW_OFF = META_OFF + 2 * TILE_M * 4;            // 2 x NA x 256 floats
-  static constexpr int BAR_OFF = AROW_OFF + 2 * NA * H * 4;
+  static constexpr int BAR_OFF = VEC_OFF + 4 * H * 4;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 constexpr int SMEM_BYTES = Smem::TOTAL + 1024;
@@ -98,47 +99,91 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&o)[8]) {
   o[0] = bf16_lo(v.x); o[1] = bf16_hi(v.x); o[2] = bf16_lo(v.y); o[3] = bf16_hi(v.y);
   o[4] = bf16_lo(v.z); o[5] = bf16_hi(v.z); o[6] = bf16_lo(v.w); o[7] = bf16_hi(v.w);
 }
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint4 add_bf16x8(const uint4 a, const uint4 b) {
+  return make_uint4(add_bf16x2(a.x, b.x), add_bf16x2(a.y, b.y), add_bf16x2(a.z, b.z), add_bf16x2(a.w, b.w));
+}
 __device__ __forceinline__ float sum32(const float (&m)[32]) {
   float s[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = (m[j] + m[j + 8]) + (m[j + 16] + m[j + 24]);
   return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
+// sum of m[j] over the bits set in `msk` (warp-uniform mask; no branches)
+__device__ __forceinline__ float masked_sum32(const float (&m)[32], uint32_t msk) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s[j & 3] += ((msk >> j) & 1u) ? m[j] : 0.f;
+  return (s[0] + s[1]) + (s[2] + s[3]);
+}
+// 32-byte global store of two 16-byte chunks, in the order (lo, hi) or swapped (one full sector either way)
+__device__ __forceinline__ void st_pair_256(void* addr, const uint4 a, const uint4 b, uint32_t swap) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+      "@!q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+      "@q st.global.v8.b32 [%0], {%5, %6, %7, %8, %1, %2, %3, %4};\n\t}" ::"l"(addr),
+      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(swap)
+      : "memory");
+}
+__device__ __forceinline__ void st_256(void* addr, const uint4 a, const uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(addr), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// Common prologue: barriers, TMEM, role register budgets.  Returns the TMEM base address.
+#define PEV_TC2_PROLOGUE(FULL_COUNT)                                                          \
+  extern __shared__ __align__(1024) uint8_t smem_raw[];                                       \
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);                \
+  uint8_t* sW = smem + Smem::W_OFF;                                                           \
+  uint8_t* sA = smem + Smem::A_OFF;                                                           \
+  float* sVec = reinterpret_cast<float*>(smem + Smem::VEC_OFF);                               \
+  const Bars B = make_bars(smem);                                                             \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                 \
+  if (threadIdx.x == 0) init_bars(B, FULL_COUNT);                                             \
+  if (warp == MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
+
+#define PEV_TC2_SYNC_ROLES()                                                                  \
+  tc_fence_before();                                                                          \
+  __syncthreads();                                                                            \
+  tc_fence_after();                                                                           \
+  const uint32_t tmem_base = *B.tmem_slot;
+
+#define PEV_TC2_EPILOGUE()                                                                    \
+  tc_fence_before();                                                                          \
+  __syncthreads();                                                                            \
+  if (warp == MMA_WARP) {                                                                     \
+    tc_fence_after();                                                                         \
+    tmem_dealloc(tmem_base, TMEM_COLS);                                                       \
+  }
 
 // =================================================================================================== fwd1
 struct Fwd1Params {
-  const float* ABh;       // [N,512] fp32, half domain: 0.5 (h Wa^T + b1) | 0.5 h Wb^T
-  const float* x;         // [N,3]
-  const int32_t* row;     // [E]
-  const int32_t* col;     // [E]
-  const float* wd;        // [256] (full domain; halved on load)
-  const float* b2;        // [256] (full domain; halved on load)
-  const void* W2hp;       // packed image of 0.5 W2
-  uint8_t* hvT;           // [num_tiles] x 64 KB tile images of hv = v/2 (bf16)
-  float* agg;             // [N,256] (+=)
+  const __nv_bfloat16* ABh;   // [N,512] bf16, half domain: 0.5 (h Wa^T + b1) | 0.5 h Wb^T
+  const float* d2;            // [E] squared edge lengths
+  const int32_t* row;         // [E]
+  const int32_t* col;         // [E]
+  const float* wd;            // [256] (full domain; halved on load)
+  const float* b2;            // [256] (full domain; halved on load)
+  const void* W2hp;           // packed image of 0.5 W2
+  uint8_t* hvT;               // [num_tiles] x 64 KB tile images of hv = v/2 (bf16)
+  float* agg;                 // [N,256] (+=)
   int64_t E;
   int num_tiles;
-  int dbg;                // PEV_TC2_DEBUG bit mask (profiling experiments only; 0 in production)
+  int dbg;                    // PEV_TC2_DEBUG bit mask (profiling experiments only; 0 in production)
 };
 
+template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem + Smem::W_OFF;
-  uint8_t* sA = smem + Smem::A_OFF;
-  float* sWd = reinterpret_cast<float*>(smem + Smem::VEC_OFF);
-  float* sMeta = reinterpret_cast<float*>(smem + Smem::META_OFF);
-  float* sArow = reinterpret_cast<float*>(smem + Smem::AROW_OFF);
-  const Bars B = make_bars(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
+  const int dbg = DBG ? p.dbg : 0;
+  PEV_TC2_PROLOGUE(NUM_PROD_THREADS)
+  float* sWd = sVec;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) sWd[k] = 0.5f * p.wd[k];
-  if (threadIdx.x == 0) init_bars(B, NUM_PROD_THREADS);
-  if (warp == MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *B.tmem_slot;
+  PEV_TC2_SYNC_ROLES()
 
   if (warp >= MMA_WARP && warp < PROD_WARP0) {
     // ------------------------------------------------------------------ MMA issue: D^T[f, e] = W2h[f, :] . a[e, :]
@@ -162,8 +207,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
           for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
 #pragma unroll
             for (int mh = 0; mh < 2; ++mh)
-              if (!(p.dbg & 32)) umma_bf16(d0 + mh * 128, desc_kmajor(w_base + mh * 16384 + ks * UMMA_K * 2),
-                        desc_kmajor(x_base + ks * UMMA_K * 2), IDESC, (kc | ks) != 0 ? 1u : 0u);
+              if (!(dbg & 32))
+                umma_bf16(d0 + mh * 128, desc_kmajor(w_base + mh * 16384 + ks * UMMA_K * 2),
+                          desc_kmajor(x_base + ks * UMMA_K * 2), IDESC, (kc | ks) != 0 ? 1u : 0u);
           umma_commit(&B.empty[stage]);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -173,33 +219,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
     __syncwarp();
   } else if (warp >= PROD_WARP0) {
     // ------------------------------------------------------------------ producers: a = silu(hu) -> K-major ring
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
-    const int pt = threadIdx.x - 32 * PROD_WARP0;
-    const int chunk = pt & 7;
-    constexpr int RPT = (TILE_M * 8) / NUM_PROD_THREADS;    // 4 rows per thread per K-chunk
-    constexpr int RSTEP = NUM_PROD_THREADS / 8;             // 32
-    int stage = 0, it = 0;
+    // Warps are independent (no block barrier): warp pw owns rows 8 pw .. 8 pw + 7 of every tile; lane -> row
+    // (lane >> 3) + 4 i (i < 2), 16-byte column chunk lane & 7.  Row metadata (row, col, d2) is fetched one tile ahead,
+    // the A|B operand chunks one K-chunk ahead.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    const int pw = warp - PROD_WARP0;
+    const int chunk = lane & 7;
+    constexpr int RPT = 2;
+    const int r0 = pw * 8 + (lane >> 3);
+    int stage = 0;
     uint32_t phase = 0;
-    struct TileIdx { int mr, mc, rf, rl, nr[RPT], nc[RPT]; };
-    auto load_idx = [&](int tile, TileIdx& t) {
-      const int64_t e0 = (int64_t)tile * TILE_M;
-      const int64_t rem = p.E - e0;
-      const int nvalid = rem < TILE_M ? (int)rem : TILE_M;
-      t.mr = t.mc = -1;
-      if (pt < nvalid) { t.mr = __ldg(p.row + e0 + pt); t.mc = __ldg(p.col + e0 + pt); }
-      t.rf = __ldg(p.row + e0);
-      t.rl = __ldg(p.row + e0 + nvalid - 1);
+    struct Meta { int nr[RPT], nc[RPT]; float d2[RPT]; };
+    auto load_meta = [&](int tile, Meta& m) {
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const int r = (pt >> 3) + RSTEP * i;
-        t.nr[i] = t.nc[i] = -1;
-        if (r < nvalid) { t.nr[i] = __ldg(p.row + e0 + r); t.nc[i] = __ldg(p.col + e0 + r); }
+        int64_t e = (int64_t)tile * TILE_M + r0 + 4 * i;
+        e = e < p.E ? e : p.E - 1;                 // tail rows recompute the last edge; the epilogue drops them
+        m.nr[i] = __ldg(p.row + e);
+        m.nc[i] = __ldg(p.col + e);
+        m.d2[i] = __ldg(p.d2 + e);
       }
     };
-    TileIdx nxt;
-    load_idx(blockIdx.x, nxt);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      if (p.dbg & 64) {                                  // role ablation: ring handshake only
+    uint4 pfA[2][RPT], pfB[2][RPT];
+    auto issue = [&](const Meta& m, int kc, int slot) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        if (dbg & 1) { pfA[slot][i] = pfB[slot][i] = make_uint4(0u, 0u, 0u, 0u); continue; }
+        pfA[slot][i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)m.nr[i] * 2 * H + kc * KCHUNK + chunk * 8));
+        pfB[slot][i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)m.nc[i] * 2 * H + H + kc * KCHUNK + chunk * 8));
+      }
+    };
+    Meta mc, mn;
+    load_meta(blockIdx.x, mc);
+    mn = mc;
+    issue(mc, 0, 0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int next_tile = tile + gridDim.x;
+      if (dbg & 64) {                                  // role ablation: ring handshake only
         for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
           mbar_wait(&B.empty[stage], phase ^ 1);
           fence_proxy_async();
@@ -208,95 +264,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
         }
         continue;
       }
-      const TileIdx cur = nxt;
-      if (tile + (int)gridDim.x < p.num_tiles) load_idx(tile + gridDim.x, nxt);
-      float* meta = sMeta + (it & 1) * TILE_M;
-      float* arow = sArow + (it & 1) * NA * H;
-      const int span = cur.rl - cur.rf + 1;
-      const bool staged = span <= NA;
-      float xr[3] = {0.f, 0.f, 0.f}, xc[3] = {0.f, 0.f, 0.f};
-      if (cur.mr >= 0) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          xr[k] = __ldg(p.x + 3 * (int64_t)cur.mr + k);
-          xc[k] = __ldg(p.x + 3 * (int64_t)cur.mc + k);
-        }
-      }
-      float4 ar[(NA * H / 4) / NUM_PROD_THREADS];
-#pragma unroll
-      for (int j = 0; j < (NA * H / 4) / NUM_PROD_THREADS; ++j) {
-        const int idx = pt + NUM_PROD_THREADS * j;
-        ar[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (staged && idx < span * (H / 4))
-          ar[j] = __ldg(reinterpret_cast<const float4*>(p.ABh + (int64_t)(cur.rf + idx / (H / 4)) * 2 * H) + idx % (H / 4));
-      }
-      uint4 pf[2][RPT][2];
-      auto issue_b = [&](int kc, int buf) {
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          pf[buf][i][0] = pf[buf][i][1] = make_uint4(0u, 0u, 0u, 0u);
-          if (cur.nc[i] >= 0 && !(p.dbg & 1)) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.ABh + (int64_t)cur.nc[i] * 2 * H + H + kc * KCHUNK + chunk * 8);
-            pf[buf][i][0] = __ldg(src);
-            pf[buf][i][1] = __ldg(src + 1);
-          }
-        }
-      };
-      issue_b(0, 0);
-      if (pt < TILE_M) {
-        const float dx = xr[0] - xc[0], dy = xr[1] - xc[1], dz = xr[2] - xc[2];
-        meta[pt] = dx * dx + dy * dy + dz * dz;
-      }
-#pragma unroll
-      for (int j = 0; j < (NA * H / 4) / NUM_PROD_THREADS; ++j)
-        reinterpret_cast<float4*>(arow)[pt + NUM_PROD_THREADS * j] = ar[j];
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      float d2[RPT];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) d2[i] = meta[(pt >> 3) + RSTEP * i];
+      if (next_tile < p.num_tiles) load_meta(next_tile, mn);
 #pragma unroll
       for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
-        if (kc + 1 < NUM_KCHUNKS) issue_b(kc + 1, (kc + 1) & 1);
-        mbar_wait(&B.empty[stage], phase ^ 1);
-        uint8_t* st = sA + stage * STAGE_BYTES;
+        if (kc + 1 < NUM_KCHUNKS) issue(mc, kc + 1, (kc + 1) & 1);
+        else if (next_tile < p.num_tiles) issue(mn, 0, 0);
         const int k0 = kc * KCHUNK + chunk * 8;
         const float4 w0 = *reinterpret_cast<const float4*>(sWd + k0), w1 = *reinterpret_cast<const float4*>(sWd + k0 + 4);
         const float wd8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint4 out[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
-          const int r = (pt >> 3) + RSTEP * i;
-          uint4 out = make_uint4(0u, 0u, 0u, 0u);
-          if (cur.nr[i] >= 0) {
-            float4 a0, a1;
-            if (staged) {
-              const float4* src = reinterpret_cast<const float4*>(arow + (cur.nr[i] - cur.rf) * H + k0);
-              a0 = src[0]; a1 = src[1];
-            } else {
-              const float4* src = reinterpret_cast<const float4*>(p.ABh + (int64_t)cur.nr[i] * 2 * H + k0);
-              a0 = __ldg(src); a1 = __ldg(src + 1);
-            }
-            const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const uint4 b0 = pf[kc & 1][i][0], b1 = pf[kc & 1][i][1];
-            const float b8[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z),
-                                 __uint_as_float(b0.w), __uint_as_float(b1.x), __uint_as_float(b1.y),
-                                 __uint_as_float(b1.z), __uint_as_float(b1.w)};
-            float o8[8];
+          // Ah_i + Bh_j in packed bf16 (the rounding an autocast bf16 Linear applies to its output), then fp32
+          float s8[8], o8[8];
+          unpack8(add_bf16x8(pfA[kc & 1][i], pfB[kc & 1][i]), s8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float hu = fmaf(wd8[j], d2[i], a8[j] + b8[j]);
-              o8[j] = (p.dbg & 16) ? hu : silu_h(hu);
-            }
-            out = pack8(o8);
+          for (int j = 0; j < 8; ++j) {
+            const float hu = fmaf(wd8[j], mc.d2[i], s8[j]);
+            o8[j] = (dbg & 16) ? hu : silu_h(hu);
           }
-          *reinterpret_cast<uint4*>(st + sw128_offset(r, chunk)) = out;
+          out[i] = pack8(o8);
         }
+        mbar_wait(&B.empty[stage], phase ^ 1);
+        uint8_t* st = sA + stage * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) *reinterpret_cast<uint4*>(st + sw128_offset(r0 + 4 * i, chunk)) = out[i];
         fence_proxy_async();
         mbar_arrive(&B.full[stage]);
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
+      mc = mn;
     }
   } else {
     // ------------------------------------------------------------------ epilogue: lane = feature, registers = edges
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp & 3, mh = warp >> 2;
     const int f = mh * 128 + q * 32 + lane;
     const float bias = 0.5f * __ldg(p.b2 + f);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
     const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
     const int sw = f & 7;
     auto flush = [&](int r, float s) {
-      if (r >= 0 && !(p.dbg & 4)) atomicAdd(aggcol + (int64_t)r * H, s);
+      if (r >= 0 && !(dbg & 4)) atomicAdd(aggcol + (int64_t)r * H, s);
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
       uint8_t* img = p.hvT + (int64_t)tile * TILE_IMG_BYTES + img_row;
       mbar_wait(&B.tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      if (p.dbg & 128) {                                 // role ablation: accumulator handshake only
+      if (dbg & 128) {                                 // role ablation: accumulator handshake only
         tc_fence_before();
         mbar_arrive(&B.tempty[acc]);
         continue;
@@ -341,46 +342,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);            // accumulator stage fully read
         }
-        // hv -> HBM tile image (bf16): this thread's 32 edges are 4 chunks of its 128-byte row
-        uint8_t* dst = img + (cb >> 1) * 8192;
-        if (!(p.dbg & 2))
+        // hv -> HBM tile image (bf16): this thread's 32 edges are 4 chunks (two 32-byte sectors) of its 128-byte row
+        if (!(dbg & 2)) {
+          uint8_t* dst = img + (cb >> 1) * 8192;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
-                               val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
-          *reinterpret_cast<uint4*>(dst + ((((cb & 1) * 4 + k) ^ sw) << 4)) = pack8(o8);
+          for (int pr = 0; pr < 2; ++pr) {
+            const int c = (cb & 1) * 4 + 2 * pr;      // logical chunk of the pair's first half
+            const float lo8[8] = {val[16 * pr], val[16 * pr + 1], val[16 * pr + 2], val[16 * pr + 3],
+                                  val[16 * pr + 4], val[16 * pr + 5], val[16 * pr + 6], val[16 * pr + 7]};
+            const float hi8[8] = {val[16 * pr + 8], val[16 * pr + 9], val[16 * pr + 10], val[16 * pr + 11],
+                                  val[16 * pr + 12], val[16 * pr + 13], val[16 * pr + 14], val[16 * pr + 15]};
+            st_pair_256(dst + (((c ^ sw) & 6) << 4), pack8(lo8), pack8(hi8), (uint32_t)(sw & 1));
+          }
         }
         float m[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m[j] = (p.dbg & 8) ? val[j] : silu_h(val[j]);
+        for (int j = 0; j < 32; ++j) m[j] = (dbg & 8) ? val[j] : silu_h(val[j]);
         // segment sums over the 32 edges (uniform control flow: every lane sees the same edges)
         int prev = __shfl_up_sync(0xffffffffu, myrow[cb], 1);
         if (lane == 0) prev = cur;
-        const uint32_t bm = __ballot_sync(0xffffffffu, myrow[cb] != prev);
+        uint32_t bm = __ballot_sync(0xffffffffu, myrow[cb] != prev);
         if (bm == 0u) {
           seg += sum32(m);
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if ((bm >> j) & 1u) {
-              flush(cur, seg);
-              seg = 0.f;
-              cur = __shfl_sync(0xffffffffu, myrow[cb], j);
-            }
-            seg += m[j];
+          int lo = 0;
+          while (bm) {
+            const int jb = __ffs(bm) - 1;
+            bm &= bm - 1u;
+            flush(cur, seg + masked_sum32(m, ((1u << jb) - 1u) & ~((1u << lo) - 1u)));
+            seg = 0.f;
+            cur = __shfl_sync(0xffffffffu, myrow[cb], jb);
+            lo = jb;
           }
+          seg = masked_sum32(m, ~((1u << lo) - 1u));
         }
       }
       flush(cur, seg);
     }
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
+  PEV_TC2_EPILOGUE()
 }
 
 // =================================================================================================== fwd2
@@ -397,26 +397,17 @@ struct Fwd2Params {
   int dbg;
 };
 
+template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem + Smem::W_OFF;
-  uint8_t* sA = smem + Smem::A_OFF;
-  float* sBias = reinterpret_cast<float*>(smem + Smem::VEC_OFF);
-  float* sW6 = sBias + H;
-  const Bars B = make_bars(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
+  const int dbg = DBG ? p.dbg : 0;
+  PEV_TC2_PROLOGUE(NUM_PROD_THREADS)
+  float* sBias = sVec;
+  float* sW6 = sVec + H;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
     sBias[k] = 0.5f * p.b5[k];
     sW6[k] = p.w6[k];
   }
-  if (threadIdx.x == 0) init_bars(B, NUM_PROD_THREADS);
-  if (warp == MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *B.tmem_slot;
+  PEV_TC2_SYNC_ROLES()
 
   if (warp >= MMA_WARP && warp < PROD_WARP0) {
     // ------------------------------------------------------------------ MMA issue: D[e, n] = m[e, :] . W5h[n, :]
@@ -438,8 +429,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
           const uint32_t w_base = smem_u32(sW + kc * (H * KCHUNK * 2));
 #pragma unroll
           for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
-            if (!(p.dbg & 32)) umma_bf16(d0, desc_mnmajor(x_base + ks * 2048, 8192, 1024), desc_kmajor(w_base + ks * UMMA_K * 2), IDESC,
-                      (kc | ks) != 0 ? 1u : 0u);
+            if (!(dbg & 32))
+              umma_bf16(d0, desc_mnmajor(x_base + ks * 2048, 8192, 1024), desc_kmajor(w_base + ks * UMMA_K * 2), IDESC,
+                        (kc | ks) != 0 ? 1u : 0u);
           umma_commit(&B.empty[stage]);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -449,9 +441,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
     __syncwarp();
   } else if (warp >= PROD_WARP0) {
     // ------------------------------------------------------------------ producers: m = silu(hv), image -> ring verbatim
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     const int pt = threadIdx.x - 32 * PROD_WARP0;
-    constexpr int CPT = STAGE_BYTES / 16 / NUM_PROD_THREADS;   // 16-byte chunks per thread per stage (4)
+    constexpr int CPT = STAGE_BYTES / 16 / NUM_PROD_THREADS;   // 16-byte chunks per thread per stage (2)
     constexpr int PD = 3;                                      // stages of load-ahead
     int stage = 0;
     uint32_t phase = 0;
@@ -459,13 +451,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
     auto issue = [&](int tile, int kc) {
       const uint4* src = reinterpret_cast<const uint4*>(p.hvT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES);
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) pf[kc][i] = (p.dbg & 1) ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + pt + NUM_PROD_THREADS * i);
+      for (int i = 0; i < CPT; ++i)
+        pf[kc][i] = (dbg & 1) ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + pt + NUM_PROD_THREADS * i);
     };
 #pragma unroll
     for (int kc = 0; kc < PD; ++kc) issue(blockIdx.x, kc);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int next_tile = tile + gridDim.x;
-      if (p.dbg & 64) {
+      if (dbg & 64) {                                  // role ablation: ring handshake only
         for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
           mbar_wait(&B.empty[stage], phase ^ 1);
           fence_proxy_async();
@@ -478,16 +471,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
       for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
         if (kc + PD < NUM_KCHUNKS) issue(tile, kc + PD);
         else if (next_tile < p.num_tiles) issue(next_tile, kc + PD - NUM_KCHUNKS);
-        mbar_wait(&B.empty[stage], phase ^ 1);
-        uint4* st = reinterpret_cast<uint4*>(sA + stage * STAGE_BYTES);
+        uint4 out[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           float v8[8];
           unpack8(pf[kc][i], v8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v8[j] = silu_h(v8[j]);
-          st[pt + NUM_PROD_THREADS * i] = pack8(v8);
+          out[i] = pack8(v8);
         }
+        mbar_wait(&B.empty[stage], phase ^ 1);
+        uint4* st = reinterpret_cast<uint4*>(sA + stage * STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) st[pt + NUM_PROD_THREADS * i] = out[i];
         fence_proxy_async();
         mbar_arrive(&B.full[stage]);
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
@@ -495,6 +491,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
     }
   } else {
     // ------------------------------------------------------------------ epilogue: lane = edge, registers = features
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
     const float b6 = half == 0 ? __ldg(p.b6) : 0.f;
@@ -506,7 +503,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
       float dot = 0.f;
       mbar_wait(&B.tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      if (p.dbg & 128) {
+      if (dbg & 128) {                                 // role ablation: accumulator handshake only
         tc_fence_before();
         mbar_arrive(&B.tempty[acc]);
         continue;
@@ -531,13 +528,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);
         }
-        if (p.hs && valid && !(p.dbg & 2)) {
-          uint4* dst = reinterpret_cast<uint4*>(p.hs + e * H + col0);
+        if (p.hs && valid && !(dbg & 2)) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(p.hs + e * H + col0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
-                                 val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
-            dst[k] = pack8(o8);
+          for (int pr = 0; pr < 2; ++pr) {
+            const float lo8[8] = {val[16 * pr], val[16 * pr + 1], val[16 * pr + 2], val[16 * pr + 3],
+                                  val[16 * pr + 4], val[16 * pr + 5], val[16 * pr + 6], val[16 * pr + 7]};
+            const float hi8[8] = {val[16 * pr + 8], val[16 * pr + 9], val[16 * pr + 10], val[16 * pr + 11],
+                                  val[16 * pr + 12], val[16 * pr + 13], val[16 * pr + 14], val[16 * pr + 15]};
+            st_256(dst + 32 * pr, pack8(lo8), pack8(hi8));
           }
         }
 #pragma unroll
@@ -552,13 +551,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
       if (valid) atomicAdd(p.w + e, dot + b6);
     }
   }
+  PEV_TC2_EPILOGUE()
+}
 
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
+// d2[e] = |x[row[e]] - x[col[e]]|^2  (models/en_gnn_decoder.py:61-62), one thread per edge
+__global__ void edge_d2_kernel(const float* __restrict__ x, const int32_t* __restrict__ row,
+                               const int32_t* __restrict__ col, int64_t E, float* __restrict__ d2) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t i = row[e], j = col[e];
+  const float dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+  d2[e] = dx * dx + dy * dy + dz * dz;
 }
 
 // fp32 [256,256] (out,in) -> bf16 image of scale * W (or scale * W^T): 4 K-blocks of [256 rows x 128 B], SWIZZLE_128B
@@ -608,25 +611,35 @@ int64_t pev_edge2_tile_image_bytes(int64_t num_edges) {
   return ((num_edges + tc2::TILE_M - 1) / tc2::TILE_M) * (int64_t)tc2::TILE_IMG_BYTES;
 }
 
-int pev_edge2_fwd1(const float* ABh, const float* x, const float* wd, const void* W2hp, const float* b2,
+int pev_edge_d2(const float* x, const int32_t* row, const int32_t* col, int64_t num_edges, float* d2, void* stream) {
+  PEV_REQUIRE(num_edges >= 0, "bad argument");
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(x && row && col && d2, "null argument");
+  tc2::edge_d2_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, as_stream(stream)>>>(x, row, col, num_edges, d2);
+  return after_launch("edge_d2_kernel");
+}
+
+int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void* W2hp, const float* b2,
                    const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges, void* hvT, float* agg,
                    void* stream) {
-  PEV_REQUIRE(ABh && x && wd && W2hp && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
+  PEV_REQUIRE(ABh && wd && W2hp && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
   if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc2::H * (size_t)num_nodes, st);
   if (num_edges == 0) return 0;
-  PEV_REQUIRE(row && col && hvT, "edge arrays missing");
+  PEV_REQUIRE(row && col && hvT && d2, "edge arrays missing");
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd1_kernel, "fwd1_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<0>, "fwd1_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<1>, "fwd1_kernel")) return rc;
     configured = true;
   }
   tc2::Fwd1Params p = {};
-  p.ABh = ABh; p.x = x; p.row = row; p.col = col; p.wd = wd; p.b2 = b2; p.W2hp = W2hp;
+  p.ABh = reinterpret_cast<const bf16_t*>(ABh); p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.b2 = b2; p.W2hp = W2hp;
   p.hvT = reinterpret_cast<uint8_t*>(hvT); p.agg = agg; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  tc2::fwd1_kernel<<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  if (p.dbg) tc2::fwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  else tc2::fwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
   return after_launch("edge2_fwd1_kernel");
 }
 
@@ -639,7 +652,8 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd2_kernel, "fwd2_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<0>, "fwd2_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<1>, "fwd2_kernel")) return rc;
     configured = true;
   }
   tc2::Fwd2Params p = {};
@@ -647,7 +661,8 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   p.hs = reinterpret_cast<bf16_t*>(hs_out); p.w = w_out; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  tc2::fwd2_kernel<<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
   return after_launch("edge2_fwd2_kernel");
 }
 

@@ -14,6 +14,8 @@ B200); storing the SiLU derivatives keeps every transcendental out of the backwa
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -22,6 +24,7 @@ from ._lib import f32c, ptr, stream
 from .graph import PackedGraph
 
 H = 256
+USE_V2 = os.environ.get("PEV_EDGE_V2", "1") != "0"      # v2 edge kernels (csrc/edge_tc2_kernels.cu)
 
 
 def supports(layer) -> bool:
@@ -175,12 +178,20 @@ class FusedEdgeBF16(torch.autograd.Function):
 def egn_layer_bf16(layer, h, x, g: PackedGraph, dinv):
     """One EGNN layer, edge MLP on the tensor cores; ``layer`` is an ``EGNLayer`` (parameter holder)."""
     W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
-    Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                      # [512, 256]
-    bias = torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
-    AB = NodeLinear.apply(h, Wcat, bias)                                  # [N, 512]
     caches = layer.__dict__.setdefault("_pev_packed", ({}, {}))
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
+    if not keep and USE_V2:
+        from . import egnn_tc2
+        agg, x_new, _ = egnn_tc2.edge_forward(
+            egnn_tc2.node_projection_half(layer, h), x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
+            layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight, layer.phi_x[2].bias, dinv, g, False,
+            layer.__dict__.setdefault("_pev_packed2", ({}, {})))
+        q = layer.phi_h[1](NodeLinear.apply(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias))
+        return layer.norm_h(h + NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias)), x_new
+    Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                      # [512, 256]
+    bias = torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
+    AB = NodeLinear.apply(h, Wcat, bias)                                  # [N, 512]
     agg, x_new = FusedEdgeBF16.apply(AB, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
                                      layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
                                      layer.phi_x[2].bias, dinv, g, keep, caches)

@@ -76,3 +76,48 @@ def rows_to_tile_image(rows: torch.Tensor) -> torch.Tensor:
     v = torch.empty_like(u)
     v.scatter_(5, idx, u)
     return v.view(T, TILE * H)
+
+
+# ------------------------------------------------------------------------------------------------ layer forward
+def edge_forward(ABh: torch.Tensor, x: torch.Tensor, wd, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches):
+    """Edge half of one EGNN layer on the v2 kernels.
+
+    ``ABh`` is the bf16 ``[N,512]`` half-domain node projection.  Returns ``(agg[N,256], x'[N,3], saved)`` where
+    ``saved`` holds what the backward kernels need (``hvT`` tile images, ``hs`` rows, ``w``, ``d2``) when ``keep``.
+    """
+    L = _lib.lib()
+    N, E = g.num_nodes, g.num_edges
+    dev = x.device
+    x = f32c(x)
+    wd, b2, b5 = f32c(wd.detach()), f32c(b2.detach()), f32c(b5.detach())
+    w6v, b6v = f32c(w6.detach()).reshape(-1), f32c(b6.detach()).reshape(-1)
+    dinv = f32c(dinv)
+    with torch.cuda.device_of(x):
+        st = stream(x)
+        W2hp = packed_weight_scaled(W2, 0.5, cache=caches[0])
+        W5hp = packed_weight_scaled(W5, 0.5, cache=caches[1])
+        d2 = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+        hvT = alloc_tile_image(E, dev)
+        hs = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
+        agg = torch.empty(N, H, dtype=torch.float32, device=dev)
+        w = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+        x_out = torch.empty_like(x)
+        L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2), st)
+        with _lib.profiled("edge2_fwd1"):
+            L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E,
+                   ptr(hvT), ptr(agg), st)
+        with _lib.profiled("edge2_fwd2"):
+            L.call("pev_edge2_fwd2", ptr(hvT), ptr(W5hp), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(hs), st)
+        L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
+               None, ptr(x_out), st)
+    saved = (hvT, hs, w, d2) if keep else None
+    return agg, x_out, saved
+
+
+def node_projection_half(layer, h: torch.Tensor) -> torch.Tensor:
+    """``ABh = 0.5 [h Wa^T + b1 | h Wb^T]`` as bf16 ``[N,512]`` (node-level library GEMM, TF32 tensor cores)."""
+    from .egnn_tc import NodeLinear
+    W1 = layer.phi_e[0].weight
+    Wcat = 0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)
+    bias = 0.5 * torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
+    return NodeLinear.apply(h, Wcat, bias).to(torch.bfloat16)

@@ -31,7 +31,7 @@ b2, b5, w6 = (torch.randn(H, device=dev) * 0.1 for _ in range(3))
 b6 = torch.randn(1, device=dev)
 wd = W1[:, 2 * H].contiguous()
 Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)
-ABh = (0.5 * (h @ Wcat.t() + torch.cat([b1, torch.zeros_like(b1)]))).contiguous()
+ABh = (0.5 * (h @ Wcat.t() + torch.cat([b1, torch.zeros_like(b1)]))).to(torch.bfloat16).contiguous()
 row, col = g.row.long(), g.col.long()
 
 
@@ -45,7 +45,7 @@ def bf(t):
 
 
 d2 = ((x[row] - x[col]) ** 2).sum(-1, keepdim=True)
-hu = ABh[row, :H] + ABh[col, H:] + 0.5 * wd * d2
+hu = (ABh[row, :H] + ABh[col, H:]).float() + 0.5 * wd * d2
 a = hu + hu * torch.tanh(hu)
 hv = bf(a) @ bf(0.5 * W2).t() + 0.5 * b2
 m = hv + hv * torch.tanh(hv)
@@ -63,10 +63,13 @@ hvT = T2.alloc_tile_image(E, dev)
 agg = torch.empty(N, H, device=dev)
 w = torch.empty(E, device=dev)
 hs_out = torch.empty(E, H, dtype=torch.bfloat16, device=dev)
+d2k = torch.empty(E, device=dev)
+L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2k), st)
+print(f"d2  rel err {rel(d2k, d2.squeeze(-1)):.3e}")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 for rep in range(reps + 1):
     ev[0].record()
-    L.call("pev_edge2_fwd1", ptr(ABh), ptr(x), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E, ptr(hvT),
+    L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2k), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E, ptr(hvT),
            ptr(agg), st)
     ev[1].record()
     L.call("pev_edge2_fwd2", ptr(hvT), ptr(W5hp), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(hs_out), st)
