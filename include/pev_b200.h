@@ -141,6 +141,47 @@ int pev_edge_prologue_bwd_bf16(const void* gu /*bf16 [E,256]*/, const float* gd2
                                int64_t num_edges, float* gAB, float* gx_accum, float* gwd_part,
                                void* stream);
 
+/* ---------------------------------------------------------------- K1 (bf16 tensor-core form, v2)
+ * Second-generation fused edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79), H = 256
+ * (csrc/edge_tc2_kernels.cu).  Conventions:
+ *  - half domain: pre-activations are carried as h = z/2; weight images are packed with scale 0.5
+ *    (pev_pack_weight_bf16_scaled), biases are halved inside the kernels, and the node projection is
+ *    ABh = 0.5 [h Wa^T + b1 | h Wb^T] stored as bf16 [N,512];
+ *  - tile image: a per-edge [E,256] bf16 tensor stored per 128-edge tile as the 64 KB SWIZZLE_128B
+ *    shared-memory image [fq 4][eh 2][fg 8][r 8][128 B] (feature 64 fq + 8 fg + r, edge 64 eh + 8 c + i
+ *    in 16-byte chunk c ^ r); pev_edge2_tile_image_bytes(E) is the buffer size. */
+int pev_pack_weight_bf16_scaled(const float* W /*[256,256] row-major (out,in)*/, int32_t transpose,
+                                float scale, void* packed /*131072 bytes*/, void* stream);
+int64_t pev_edge2_tile_image_bytes(int64_t num_edges);
+/* d2[e] = |x[row[e]] - x[col[e]]|^2 (models/en_gnn_decoder.py:61-62). */
+int pev_edge_d2(const float* x, const int32_t* row, const int32_t* col, int64_t num_edges,
+                float* d2 /*[E]*/, void* stream);
+/* fwd1: hu = Ah_i + Bh_j + (wd/2) d2, a = silu(2 hu), hv = a (W2/2)^T + b2/2 -> hvT tile images;
+ * agg[N,256] = segment_sum(silu(2 hv)) (zeroed inside; one fp32 atomic per segment and feature). */
+int pev_edge2_fwd1(const void* ABh /*bf16 [N,512]*/, const float* d2 /*[E]*/, const float* wd,
+                   const void* W2hp, const float* b2, const int32_t* row, const int32_t* col,
+                   int64_t num_nodes, int64_t num_edges, void* hvT /*tile images*/,
+                   float* agg /*[N,256]*/, void* stream);
+/* fwd2: m = silu(2 hv), hs = m (W5/2)^T + b5/2, t = silu(2 hs), w = t . w6 + b6 -> w[E] (zeroed
+ * inside); hs_out (bf16 [E,256]) is written when not NULL (kept for the backward pass). */
+int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const float* w6,
+                   const float* b6 /*[1]*/, int64_t num_edges, float* w_out /*[E]*/,
+                   void* hs_out /*bf16 [E,256] or NULL*/, void* stream);
+
+/* bwd2 (backward of fwd2 and of the aggregation; SURVEY.md 8a, half domain: d silu(2h)/dh = 1 + r(h)):
+ * ghs = gw w6 (1 + r(hs)), gm = ghs (W5/2) + gagg[row], ghv = gm (1 + r(hv)) -> ghvT tile images;
+ * db2h[256] = sum_e ghv (zeroed inside; db2 = db2h / 2).  W5thp = pack(W5, transpose=1, scale=0.5). */
+int pev_edge2_bwd2(const void* hs /*bf16 [E,256]*/, const float* gw /*[E]*/, const float* w6,
+                   const void* W5thp, const float* gagg /*[N,256]*/, const int32_t* row,
+                   const void* hvT, int64_t num_edges, void* ghvT /*tile images*/, float* db2h,
+                   void* stream);
+/* bwd1 (backward of fwd1): ga = ghv (W2/2), ghu = ga (1 + r(hu)) with hu rebuilt from ABh, d2, wd;
+ * writes ghu (bf16 [E,256] = dL/dhu) and gd2[e] = ghu . (wd/2) (zeroed inside).
+ * W2thp = pack(W2, transpose=1, scale=0.5). */
+int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh /*bf16 [N,512]*/,
+                   const float* d2, const int32_t* row, const int32_t* col, const float* wd,
+                   int64_t num_edges, void* ghu /*bf16 [E,256]*/, float* gd2 /*[E]*/, void* stream);
+
 /* ---------------------------------------------------------------- K3: losses
  * Forward accumulators: acc_global[2*PEV_NUM_TERMS] doubles (numerator, denominator per term;
  * pre-zeroed) and acc_sample[B*8] doubles (per conformer: rec_ca, rec_n, rec_c numerators,

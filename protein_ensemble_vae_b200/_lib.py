@@ -65,6 +65,8 @@ _PROTOS_TC = {
     "pev_edge_d2": (c_int32, [_P, _P, _P, _L, _P, _P]),
     "pev_edge2_fwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
     "pev_edge2_fwd2": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "pev_edge2_bwd2": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "pev_edge2_bwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
 }
 
 

@@ -554,6 +554,468 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
   PEV_TC2_EPILOGUE()
 }
 
+// 32-byte global load of two 16-byte chunks stored in the order (lo, hi) or swapped (see st_pair_256)
+__device__ __forceinline__ void ld_pair_256(const void* addr, uint32_t swap, uint4& a, uint4& b) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+      "@!q ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+      "@q ld.global.v8.b32 {%4, %5, %6, %7, %0, %1, %2, %3}, [%8];\n\t}"
+      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+      : "l"(addr), "r"(swap));
+}
+__device__ __forceinline__ void ld_256(const void* addr, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(addr));
+}
+
+// =================================================================================================== bwd2
+//   ghs = gw w6 (1 + r(hs))  --GEMM (W5/2) (transposed)-->  gm ; ghv = (gm + gagg[row]) (1 + r(hv)) -> HBM tile image,
+//   db2 += sum_e ghv (in-thread).   [d silu(2h)/dh = 1 + r(h)]
+struct Bwd2Params {
+  const __nv_bfloat16* hs;    // [E,256] hs = s/2
+  const float* gw;            // [E] dL/dw
+  const float* w6;            // [256]
+  const void* W5thp;          // packed image of 0.5 W5^T
+  const float* gagg;          // [N,256] dL/dagg
+  const int32_t* row;         // [E]
+  const uint8_t* hvT;         // tile images of hv
+  uint8_t* ghvT;              // tile images of ghv = dL/dhv (out)
+  float* db2h;                // [256] (+=) sum_e ghv
+  int64_t E;
+  int num_tiles;
+  int dbg;
+};
+
+template <int DBG>
+__global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p) {
+  const int dbg = DBG ? p.dbg : 0;
+  PEV_TC2_PROLOGUE(NUM_PROD_THREADS)
+  float* sW6 = sVec;
+  for (int k = threadIdx.x; k < H; k += NUM_THREADS) sW6[k] = p.w6[k];
+  PEV_TC2_SYNC_ROLES()
+
+  if (warp >= MMA_WARP && warp < PROD_WARP0) {
+    // ------------------------------------------------------------------ MMA issue: D^T[f, e] = W5h^T[f, :] . ghs[e, :]
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA_WG));
+    if (warp == MMA_WARP && lane == 0) {
+      load_weight_image(sW, p.W5thp, B.w);
+      constexpr uint32_t IDESC = idesc_bf16(128, 128, false, false);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&B.tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * H;
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.full[stage], phase);
+          tc_fence_after();
+          const uint32_t x_base = smem_u32(sA + stage * STAGE_BYTES);
+          const uint32_t w_base = smem_u32(sW + kc * (H * KCHUNK * 2));
+#pragma unroll
+          for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)
+              if (!(dbg & 32))
+                umma_bf16(d0 + mh * 128, desc_kmajor(w_base + mh * 16384 + ks * UMMA_K * 2),
+                          desc_kmajor(x_base + ks * UMMA_K * 2), IDESC, (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&B.empty[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&B.tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= PROD_WARP0) {
+    // ------------------------------------------------------------------ producers: ghs -> K-major ring (rows = edges)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    const int pw = warp - PROD_WARP0;
+    const int chunk = lane & 7;
+    constexpr int RPT = 2;
+    const int r0 = pw * 8 + (lane >> 3);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint4 pf[2][RPT];
+    float gwc[RPT], gwn[RPT];
+    auto load_meta = [&](int tile, float (&g)[RPT]) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int64_t e = (int64_t)tile * TILE_M + r0 + 4 * i;
+        g[i] = e < p.E ? __ldg(p.gw + e) : 0.f;          // tail rows contribute exact zeros
+      }
+    };
+    auto issue = [&](int tile, int kc, int slot) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        int64_t e = (int64_t)tile * TILE_M + r0 + 4 * i;
+        e = e < p.E ? e : p.E - 1;
+        pf[slot][i] = (dbg & 1) ? make_uint4(0u, 0u, 0u, 0u)
+                                : __ldg(reinterpret_cast<const uint4*>(p.hs + e * H + kc * KCHUNK + chunk * 8));
+      }
+    };
+    load_meta(blockIdx.x, gwc);
+    issue(blockIdx.x, 0, 0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int next_tile = tile + gridDim.x;
+      if (dbg & 64) {
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.empty[stage], phase ^ 1);
+          fence_proxy_async();
+          mbar_arrive(&B.full[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
+      if (next_tile < p.num_tiles) load_meta(next_tile, gwn);
+#pragma unroll
+      for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+        if (kc + 1 < NUM_KCHUNKS) issue(tile, kc + 1, (kc + 1) & 1);
+        else if (next_tile < p.num_tiles) issue(next_tile, 0, 0);
+        const int k0 = kc * KCHUNK + chunk * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(sW6 + k0), w1 = *reinterpret_cast<const float4*>(sW6 + k0 + 4);
+        const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint4 out[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          float h8[8], o8[8];
+          unpack8(pf[kc & 1][i], h8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = gwc[i] * fmaf(w8[j], silu_grad_r(h8[j]), w8[j]);
+          out[i] = pack8(o8);
+        }
+        mbar_wait(&B.empty[stage], phase ^ 1);
+        uint8_t* st = sA + stage * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) *reinterpret_cast<uint4*>(st + sw128_offset(r0 + 4 * i, chunk)) = out[i];
+        fence_proxy_async();
+        mbar_arrive(&B.full[stage]);
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) gwc[i] = gwn[i];
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane = feature, registers = edges
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+    const int q = warp & 3, mh = warp >> 2;
+    const int f = mh * 128 + q * 32 + lane;
+    const float* gaggcol = p.gagg + f;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 128);
+    const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
+    const int sw = f & 7;
+    const uint32_t swap = (uint32_t)(sw & 1);
+    float dbacc = 0.f;
+    // byte offset inside a tile image of the 32-byte pair `pr` of batch `cb` for this thread's feature row
+    auto pair_off = [&](int cb, int pr) -> uint32_t {
+      return img_row + (uint32_t)((cb >> 1) * 8192) + (uint32_t)(((((cb & 1) * 4 + 2 * pr) ^ sw) & 6) << 4);
+    };
+    // The CTA's tiles are walked as a flat sequence of 32-edge batches (4 per tile), each in two steps of 16 edges
+    // (one 32-byte pair of the thread's image row, 16 TMEM columns).  Row ids are fetched two batches ahead, the
+    // gagg values of a batch's first / last row one batch ahead, hv one step ahead.
+    const int nb = 4 * ((p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+    auto tile_of = [&](int bi) { return (int)blockIdx.x + (bi >> 2) * (int)gridDim.x; };
+    auto batch_row = [&](int bi) -> int {
+      const int64_t e = (int64_t)tile_of(bi) * TILE_M + (bi & 3) * 32 + lane;
+      return e < p.E ? __ldg(p.row + e) : -1;
+    };
+    auto batch_ga = [&](int myrow, float& gF, float& gL) {
+      const int rF = __shfl_sync(0xffffffffu, myrow, 0), rL = __shfl_sync(0xffffffffu, myrow, 31);
+      gF = rF >= 0 ? __ldg(gaggcol + (int64_t)rF * H) : 0.f;
+      gL = rL >= 0 ? __ldg(gaggcol + (int64_t)rL * H) : 0.f;
+    };
+    int row_c = batch_row(0), row_n = nb > 1 ? batch_row(1) : -1;
+    float gaF, gaL, gaFn = 0.f, gaLn = 0.f;
+    batch_ga(row_c, gaF, gaL);
+    uint4 hvn[2];                                  // hv of the next step (lo, hi chunk)
+    ld_pair_256(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES + pair_off(0, 0), swap, hvn[0], hvn[1]);
+#pragma unroll 1
+    for (int bi = 0; bi < nb; ++bi) {
+      const int cb = bi & 3, it = bi >> 2, acc = it & 1;
+      const int tile = tile_of(bi);
+      const int row_nn = bi + 2 < nb ? batch_row(bi + 2) : -1;
+      if (bi + 1 < nb) batch_ga(row_n, gaFn, gaLn);
+      if (cb == 0) {
+        mbar_wait(&B.tfull[acc], (it >> 1) & 1);
+        tc_fence_after();
+      }
+      if (dbg & 128) {
+        if (cb == 3) {
+          tc_fence_before();
+          mbar_arrive(&B.tempty[acc]);
+        }
+        continue;
+      }
+      const uint8_t* src = p.hvT + (int64_t)tile * TILE_IMG_BYTES;
+      uint8_t* dst = p.ghvT + (int64_t)tile * TILE_IMG_BYTES;
+      // segments of the 32-edge batch (uniform control flow: every lane sees the same edges)
+      const int prev = __shfl_up_sync(0xffffffffu, row_c, 1);
+      const uint32_t bm = __ballot_sync(0xffffffffu, lane != 0 && row_c != prev);
+      const bool one = bm != 0u && (bm & (bm - 1u)) == 0u;
+      const uint32_t low = bm - 1u;                // one boundary: edges before it
+      float ga_run = gaF;                          // several boundaries: running value / row
+      int r_run = __shfl_sync(0xffffffffu, row_c, 0);
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        uint32_t raw[16];
+        tmem_ld16_issue(lane_addr + acc * H + cb * 32 + pr * 16, raw);
+        // r(hv) of the 16 edges while the TMEM load is in flight
+        float r[16];
+        {
+          float h8[8];
+          unpack8(hvn[0], h8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = silu_grad_r(h8[j]);
+          unpack8(hvn[1], h8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[8 + j] = silu_grad_r(h8[j]);
+        }
+        if (pr == 0) ld_pair_256(src + pair_off(cb, 1), swap, hvn[0], hvn[1]);
+        else if (bi + 1 < nb)
+          ld_pair_256(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES + pair_off((bi + 1) & 3, 0), swap, hvn[0], hvn[1]);
+        tmem_wait();
+        if (cb == 3 && pr == 1) {
+          tc_fence_before();
+          mbar_arrive(&B.tempty[acc]);
+        }
+        float gv[16];
+        if (bm == 0u) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gv[j] = __uint_as_float(raw[j]) + gaF;
+        } else if (one) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gv[j] = __uint_as_float(raw[j]) + (((low >> (16 * pr + j)) & 1u) ? gaF : gaL);
+        } else {                                   // several short segments (not a banded graph): edge by edge
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int rj = __shfl_sync(0xffffffffu, row_c, 16 * pr + j);
+            if (rj != r_run) {
+              r_run = rj;
+              ga_run = rj >= 0 ? __ldg(gaggcol + (int64_t)rj * H) : 0.f;
+            }
+            gv[j] = __uint_as_float(raw[j]) + ga_run;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gv[j] = fmaf(gv[j], r[j], gv[j]);
+        dbacc += ((gv[0] + gv[1]) + (gv[2] + gv[3])) + ((gv[4] + gv[5]) + (gv[6] + gv[7])) +
+                 (((gv[8] + gv[9]) + (gv[10] + gv[11])) + ((gv[12] + gv[13]) + (gv[14] + gv[15])));
+        if (!(dbg & 2)) {
+          const float lo8[8] = {gv[0], gv[1], gv[2], gv[3], gv[4], gv[5], gv[6], gv[7]};
+          const float hi8[8] = {gv[8], gv[9], gv[10], gv[11], gv[12], gv[13], gv[14], gv[15]};
+          st_pair_256(dst + pair_off(cb, pr), pack8(lo8), pack8(hi8), swap);
+        }
+      }
+      row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
+    }
+    atomicAdd(p.db2h + f, dbacc);
+  }
+  PEV_TC2_EPILOGUE()
+}
+
+// =================================================================================================== bwd1
+//   ghv (tile images, TMA -> MN-major A operand)  --GEMM (W2/2)-->  ga ; ghu = ga (1 + r(hu)), hu rebuilt from ABh, d2 ;
+//   ghu -> HBM rows, gd2[e] = ghu . (wd/2).   Block: 16 epilogue warps (lane = edge; TMEM lane quarter = warp % 4,
+//   column quarter = warp / 4), warp 16 = MMA issue, warp 17 = TMA loads.
+constexpr int B1_EPI_WARPS = 16;
+constexpr int B1_MMA_WARP = 16;
+constexpr int B1_TMA_WARP = 17;
+constexpr int B1_THREADS = 32 * (B1_EPI_WARPS + 4);     // 640 -> 96 registers at launch
+constexpr int B1_REGS_EPI = 104;
+
+struct Bwd1Params {
+  const uint8_t* ghvT;        // tile images of ghv
+  const void* W2thp;          // packed image of 0.5 W2^T
+  const __nv_bfloat16* ABh;   // [N,512]
+  const float* d2;            // [E]
+  const int32_t* row;         // [E]
+  const int32_t* col;         // [E]
+  const float* wd;            // [256] (full domain; halved on load)
+  __nv_bfloat16* ghu;         // [E,256] (out) dL/dhu
+  float* gd2;                 // [E] (+=, zeroed by the launcher)
+  int64_t E;
+  int num_tiles;
+  int dbg;
+};
+
+template <int DBG>
+__global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p) {
+  const int dbg = DBG ? p.dbg : 0;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem + Smem::W_OFF;
+  uint8_t* sA = smem + Smem::A_OFF;
+  float* sWd = reinterpret_cast<float*>(smem + Smem::VEC_OFF);
+  const Bars B = make_bars(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < H; k += B1_THREADS) sWd[k] = 0.5f * p.wd[k];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(&B.full[s], 1);
+      mbar_init(&B.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&B.tfull[a], 1);
+      mbar_init(&B.tempty[a], 32 * B1_EPI_WARPS);
+    }
+    mbar_init(B.w, 1);
+    fence_barrier_init();
+  }
+  if (warp == B1_MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *B.tmem_slot;
+
+  if (warp >= B1_EPI_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA_WG));
+    if (warp == B1_MMA_WARP && lane == 0) {
+      // ---------------------------------------------------------------- MMA issue: D[e, j] = ghv[e, :] . W2h^T[j, :]
+      load_weight_image(sW, p.W2thp, B.w);
+      constexpr uint32_t IDESC = idesc_bf16(128, 256, true, false);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&B.tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * H;
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.full[stage], phase);
+          tc_fence_after();
+          const uint32_t x_base = smem_u32(sA + stage * STAGE_BYTES);
+          const uint32_t w_base = smem_u32(sW + kc * (H * KCHUNK * 2));
+#pragma unroll
+          for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks)
+            if (!(dbg & 32))
+              umma_bf16(d0, desc_mnmajor(x_base + ks * 2048, 8192, 1024), desc_kmajor(w_base + ks * UMMA_K * 2), IDESC,
+                        (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&B.empty[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&B.tfull[acc]);
+      }
+    } else if (warp == B1_TMA_WARP && lane == 0) {
+      // ---------------------------------------------------------------- TMA: tile image K-chunks -> ring, verbatim
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
+          mbar_wait(&B.empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&B.full[stage], STAGE_BYTES);
+          bulk_g2s(sA + stage * STAGE_BYTES, p.ghvT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES, STAGE_BYTES,
+                   &B.full[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane = edge, registers = features
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B1_REGS_EPI));
+    const int q = warp & 3, cq = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    auto load_meta = [&](int tile, int& nr, int& nc, float& dd) {
+      int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
+      e = e < p.E ? e : p.E - 1;
+      nr = __ldg(p.row + e);
+      nc = __ldg(p.col + e);
+      dd = __ldg(p.d2 + e);
+    };
+    int nr, nc, nrn = 0, ncn = 0;
+    float dd, ddn = 0.f;
+    load_meta(blockIdx.x, nr, nc, dd);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int64_t e = (int64_t)tile * TILE_M + q * 32 + lane;
+      const bool valid = e < p.E;
+      const int next_tile = tile + gridDim.x;
+      if (next_tile < p.num_tiles) load_meta(next_tile, nrn, ncn, ddn);
+      const __nv_bfloat16* arow = p.ABh + (int64_t)nr * 2 * H + cq * 64;
+      const __nv_bfloat16* brow = p.ABh + (int64_t)nc * 2 * H + H + cq * 64;
+      uint4 a4[4], b4[4];
+      ld_256(arow, a4[0], a4[1]);
+      ld_256(arow + 16, a4[2], a4[3]);
+      ld_256(brow, b4[0], b4[1]);
+      ld_256(brow + 16, b4[2], b4[3]);
+      float dot = 0.f;
+      mbar_wait(&B.tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (dbg & 128) {
+        tc_fence_before();
+        mbar_arrive(&B.tempty[acc]);
+        nr = nrn; nc = ncn; dd = ddn;
+        continue;
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int col0 = cq * 64 + b * 32;
+        uint32_t raw[32];
+        tmem_ld32_issue(lane_addr + acc * H + b * 32, raw);
+        uint4 s4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = add_bf16x8(a4[k], b4[k]);
+        if (b == 0) {
+          ld_256(arow + 32, a4[0], a4[1]);
+          ld_256(arow + 48, a4[2], a4[3]);
+          ld_256(brow + 32, b4[0], b4[1]);
+          ld_256(brow + 48, b4[2], b4[3]);
+        }
+        float r[32];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float s8[8];
+          unpack8(s4[k], s8);
+          const float4 w0 = *reinterpret_cast<const float4*>(sWd + col0 + 8 * k);
+          const float4 w1 = *reinterpret_cast<const float4*>(sWd + col0 + 8 * k + 4);
+          const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[8 * k + j] = silu_grad_r(fmaf(w8[j], dd, s8[j]));
+        }
+        tmem_wait();
+        if (b == 1) {
+          tc_fence_before();
+          mbar_arrive(&B.tempty[acc]);
+        }
+        float gu[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 w = *reinterpret_cast<const float4*>(sWd + col0 + 4 * k);
+          gu[4 * k] = fmaf(__uint_as_float(raw[4 * k]), r[4 * k], __uint_as_float(raw[4 * k]));
+          gu[4 * k + 1] = fmaf(__uint_as_float(raw[4 * k + 1]), r[4 * k + 1], __uint_as_float(raw[4 * k + 1]));
+          gu[4 * k + 2] = fmaf(__uint_as_float(raw[4 * k + 2]), r[4 * k + 2], __uint_as_float(raw[4 * k + 2]));
+          gu[4 * k + 3] = fmaf(__uint_as_float(raw[4 * k + 3]), r[4 * k + 3], __uint_as_float(raw[4 * k + 3]));
+          dot = fmaf(gu[4 * k], w.x, dot);
+          dot = fmaf(gu[4 * k + 1], w.y, dot);
+          dot = fmaf(gu[4 * k + 2], w.z, dot);
+          dot = fmaf(gu[4 * k + 3], w.w, dot);
+        }
+        if (valid && !(dbg & 2)) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(p.ghu + e * H + col0);
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {
+            const float lo8[8] = {gu[16 * pr], gu[16 * pr + 1], gu[16 * pr + 2], gu[16 * pr + 3],
+                                  gu[16 * pr + 4], gu[16 * pr + 5], gu[16 * pr + 6], gu[16 * pr + 7]};
+            const float hi8[8] = {gu[16 * pr + 8], gu[16 * pr + 9], gu[16 * pr + 10], gu[16 * pr + 11],
+                                  gu[16 * pr + 12], gu[16 * pr + 13], gu[16 * pr + 14], gu[16 * pr + 15]};
+            st_256(dst + 32 * pr, pack8(lo8), pack8(hi8));
+          }
+        }
+      }
+      if (valid) atomicAdd(p.gd2 + e, dot);
+      nr = nrn; nc = ncn; dd = ddn;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == B1_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // d2[e] = |x[row[e]] - x[col[e]]|^2  (models/en_gnn_decoder.py:61-62), one thread per edge
 __global__ void edge_d2_kernel(const float* __restrict__ x, const int32_t* __restrict__ row,
                                const int32_t* __restrict__ col, int64_t E, float* __restrict__ d2) {
@@ -664,6 +1126,54 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
   else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
   return after_launch("edge2_fwd2_kernel");
+}
+
+int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void* W5thp, const float* gagg,
+                   const int32_t* row, const void* hvT, int64_t num_edges, void* ghvT, float* db2h, void* stream) {
+  PEV_REQUIRE(w6 && W5thp && db2h && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(db2h, 0, sizeof(float) * tc2::H, st);
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(hs && gw && gagg && row && hvT && ghvT, "edge arrays missing");
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = tc2::configure(tc2::bwd2_kernel<0>, "bwd2_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::bwd2_kernel<1>, "bwd2_kernel")) return rc;
+    configured = true;
+  }
+  tc2::Bwd2Params p = {};
+  p.hs = reinterpret_cast<const bf16_t*>(hs); p.gw = gw; p.w6 = w6; p.W5thp = W5thp; p.gagg = gagg; p.row = row;
+  p.hvT = reinterpret_cast<const uint8_t*>(hvT); p.ghvT = reinterpret_cast<uint8_t*>(ghvT); p.db2h = db2h;
+  p.E = num_edges;
+  p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
+  p.dbg = tc2::debug_mask();
+  if (p.dbg) tc2::bwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  else tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  return after_launch("edge2_bwd2_kernel");
+}
+
+int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const float* d2, const int32_t* row,
+                   const int32_t* col, const float* wd, int64_t num_edges, void* ghu, float* gd2, void* stream) {
+  PEV_REQUIRE(W2thp && wd && num_edges >= 0, "bad argument");
+  if (num_edges == 0) return 0;
+  PEV_REQUIRE(ghvT && ABh && d2 && row && col && ghu && gd2, "edge arrays missing");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = tc2::configure(tc2::bwd1_kernel<0>, "bwd1_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::bwd1_kernel<1>, "bwd1_kernel")) return rc;
+    configured = true;
+  }
+  tc2::Bwd1Params p = {};
+  p.ghvT = reinterpret_cast<const uint8_t*>(ghvT); p.W2thp = W2thp; p.ABh = reinterpret_cast<const bf16_t*>(ABh);
+  p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.ghu = reinterpret_cast<bf16_t*>(ghu); p.gd2 = gd2;
+  p.E = num_edges;
+  p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
+  p.dbg = tc2::debug_mask();
+  if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  return after_launch("edge2_bwd1_kernel");
 }
 
 }  // extern "C"

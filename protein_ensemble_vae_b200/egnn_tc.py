@@ -65,15 +65,16 @@ class _tf32_matmul:
 class NodeLinear(torch.autograd.Function):
     """``x W^T + b`` for the node-level linears of the bf16 path (plain library GEMMs).
 
-    Forward in true fp32 (it feeds the 1e-2 output budget); the two backward products ``g W`` and ``g^T x`` run
-    on the tensor cores in TF32 -- gradients of the bf16 path already carry the bf16 edge MLP's noise (5e-2
-    relative, tools/grad_diag.py), three orders of magnitude above TF32's 5e-4.
+    All three products (forward, ``g W`` and ``g^T x``) run on the tensor cores in TF32 with fp32 accumulation:
+    TF32's 5e-4 relative rounding is an order of magnitude below the bf16 edge MLP's own (4e-3) and well inside the
+    1e-2 output budget of the bf16 path; the fp32 path (``precision="fp32"``) never comes here.
     """
 
     @staticmethod
     def forward(ctx, x, W, b):
         ctx.save_for_backward(x, W)
-        return torch.addmm(b, x, W.t())
+        with _tf32_matmul():
+            return torch.addmm(b, x, W.t())
 
     @staticmethod
     def backward(ctx, g):
@@ -84,6 +85,17 @@ class NodeLinear(torch.autograd.Function):
             gW = g.t() @ x if ctx.needs_input_grad[1] else None
         gb = g.sum(0) if ctx.needs_input_grad[2] else None
         return gx, gW, gb
+
+
+def apply_tf32(module, x):
+    """Run an ``nn.Linear`` / ``nn.Sequential`` of the decoder with its linears on :class:`NodeLinear` (bf16 path)."""
+    if isinstance(module, nn.Linear):
+        return NodeLinear.apply(x, module.weight, module.bias)
+    if isinstance(module, nn.Sequential):
+        for m in module:
+            x = apply_tf32(m, x)
+        return x
+    return module(x)
 
 
 def _wgrad(g_bf16: torch.Tensor, act_bf16: torch.Tensor) -> torch.Tensor:

@@ -144,6 +144,13 @@ class EGNNDecoder(nn.Module):
         g = band_graph(lengths, self.max_neighbors, device)
         return g, (g.dinv if self.degree_normalize else None)
 
+    def _run(self, module, x):
+        """Node-level heads: plain modules on the fp32 path, TF32 tensor-core linears on the bf16 path."""
+        if self.precision == "bf16" and x.is_cuda:
+            from .egnn_tc import apply_tf32
+            return apply_tf32(module, x)
+        return module(x)
+
     def forward(self, z_g: torch.Tensor, z_l: torch.Tensor, mask: torch.Tensor | None = None):
         """``z_g[B,zg], z_l[B,L,zl], mask[B,L]|None -> (N, CA, C)[B,L,3], seq_logits[B,L,20]``."""
         B, L, _ = z_l.shape
@@ -166,13 +173,13 @@ class EGNNDecoder(nn.Module):
         conf_of = torch.repeat_interleave(torch.arange(B, device=device),
                                           torch.tensor(lengths, device=device), output_size=N)
         z = torch.cat([z_g.index_select(0, conf_of), zl_p], -1)
-        x = self.latent_to_coords(z)                            # :237
-        h = self.input_embedding(z)                             # :240
+        x = self._run(self.latent_to_coords, z)                 # :237
+        h = self._run(self.input_embedding, z)                  # :240
         g, dinv = self._graph(lengths, device)
         for layer in self.layers:                               # :248-250
             h, x = _layer_forward(layer, h, x, g, dinv, self.precision)
             h = self.dropout(h)
-        logits = self.sequence_head(h)                          # :253
+        logits = self._run(self.sequence_head, h)               # :253
         x_n, x_c = self._backbone(h, x, g)
 
         def unpack(t, width):
@@ -185,8 +192,8 @@ class EGNNDecoder(nn.Module):
 
     def _backbone(self, h, x_ca, g):
         """N / C placement and the 3-step peptide pull (``:260-310``), vectorised over the packed batch."""
-        n_dir = self.n_offset_head(h)[:, :3]                    # 4th channel unused in the reference too
-        c_dir = self.c_offset_head(h)[:, :3]
+        n_dir = self._run(self.n_offset_head, h)[:, :3]         # 4th channel unused in the reference too
+        c_dir = self._run(self.c_offset_head, h)[:, :3]
         x_n = x_ca + F.normalize(n_dir, dim=-1) * N_CA_LENGTH
         x_c = x_ca + F.normalize(c_dir, dim=-1) * CA_C_LENGTH
         N = x_ca.shape[0]
