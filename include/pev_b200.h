@@ -146,7 +146,8 @@ int pev_edge_prologue_bwd_bf16(const void* gu /*bf16 [E,256]*/, const float* gd2
  * (csrc/edge_tc2_kernels.cu).  Conventions:
  *  - half domain: pre-activations are carried as h = z/2; weight images are packed with scale 0.5
  *    (pev_pack_weight_bf16_scaled), biases are halved inside the kernels, and the node projection is
- *    ABh = 0.5 [h Wa^T + b1 | h Wb^T] stored as bf16 [N,512];
+ *    ABh = 0.5 [h Wa^T + b1 | h Wb^T] staged as fp16 [N,512] (11-bit significand: its rounding adds to the
+ *    first edge linear's output; the GEMM operands a, m and the weights are bf16);
  *  - tile image: a per-edge [E,256] bf16 tensor stored per 128-edge tile as the 64 KB SWIZZLE_128B
  *    shared-memory image [fq 4][eh 2][fg 8][r 8][128 B] (feature 64 fq + 8 fg + r, edge 64 eh + 8 c + i
  *    in 16-byte chunk c ^ r); pev_edge2_tile_image_bytes(E) is the buffer size. */
@@ -158,7 +159,7 @@ int pev_edge_d2(const float* x, const int32_t* row, const int32_t* col, int64_t 
                 float* d2 /*[E]*/, void* stream);
 /* fwd1: hu = Ah_i + Bh_j + (wd/2) d2, a = silu(2 hu), hv = a (W2/2)^T + b2/2 -> hvT tile images;
  * agg[N,256] = segment_sum(silu(2 hv)) (zeroed inside; one fp32 atomic per segment and feature). */
-int pev_edge2_fwd1(const void* ABh /*bf16 [N,512]*/, const float* d2 /*[E]*/, const float* wd,
+int pev_edge2_fwd1(const void* ABh /*fp16 [N,512]*/, const float* d2 /*[E]*/, const float* wd,
                    const void* W2hp, const float* b2, const int32_t* row, const int32_t* col,
                    int64_t num_nodes, int64_t num_edges, void* hvT /*tile images*/,
                    float* agg /*[N,256]*/, void* stream);
@@ -178,9 +179,22 @@ int pev_edge2_bwd2(const void* hs /*bf16 [E,256]*/, const float* gw /*[E]*/, con
 /* bwd1 (backward of fwd1): ga = ghv (W2/2), ghu = ga (1 + r(hu)) with hu rebuilt from ABh, d2, wd;
  * writes ghu (bf16 [E,256] = dL/dhu) and gd2[e] = ghu . (wd/2) (zeroed inside).
  * W2thp = pack(W2, transpose=1, scale=0.5). */
-int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh /*bf16 [N,512]*/,
+int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh /*fp16 [N,512]*/,
                    const float* d2, const int32_t* row, const int32_t* col, const float* wd,
                    int64_t num_edges, void* ghu /*bf16 [E,256]*/, float* gd2 /*[E]*/, void* stream);
+
+/* Weight gradients of the two 256x256 edge linears as split-K tcgen05 GEMMs over the edge dimension; both
+ * operands are rebuilt on the fly (nothing but hs / hvT / ghvT is read from HBM).  `workspace` holds one
+ * 256x256 fp32 partial per CTA (pev_edge2_wgrad_workspace_bytes()); the partials are summed in a fixed order.
+ *   wgrad5: dW5[k,f] = sum_e gs[e,k] m[e,f] (full-domain gradient of phi_x.0.weight), db5[256] = sum_e ghs
+ *           (half domain: db5 = result / 2), dw6[256] = sum_e gw silu(s)  (db5, dw6 zeroed inside)
+ *   wgrad2: dW2[f,j] = sum_e gv[e,f] a[e,j] (full-domain gradient of phi_e.2.weight) */
+int64_t pev_edge2_wgrad_workspace_bytes(void);
+int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* hvT, int64_t num_edges,
+                     float* workspace, float* dW5 /*[256,256]*/, float* db5h, float* dw6, void* stream);
+int pev_edge2_wgrad2(const void* ghvT, const void* ABh, const float* d2, const int32_t* row,
+                     const int32_t* col, const float* wd, int64_t num_edges, float* workspace,
+                     float* dW2 /*[256,256]*/, void* stream);
 
 /* ---------------------------------------------------------------- K3: losses
  * Forward accumulators: acc_global[2*PEV_NUM_TERMS] doubles (numerator, denominator per term;

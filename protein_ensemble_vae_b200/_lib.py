@@ -67,6 +67,9 @@ _PROTOS_TC = {
     "pev_edge2_fwd2": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "pev_edge2_bwd2": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "pev_edge2_bwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "pev_edge2_wgrad_workspace_bytes": (c_int64, []),
+    "pev_edge2_wgrad5": (c_int32, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
+    "pev_edge2_wgrad2": (c_int32, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
 }
 
 

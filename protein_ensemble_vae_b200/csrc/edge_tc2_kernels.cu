@@ -16,6 +16,7 @@
 //         m = silu ; agg[row] += m (in-thread segment sums, one RED per segment per feature)
 //   fwd2  m = silu(hv)  --GEMM W5h (A operand MN-major)-->  hs (+b5h) [-> HBM, training], t = silu, w[e] = t.w6 + b6
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -99,13 +100,20 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&o)[8]) {
   o[0] = bf16_lo(v.x); o[1] = bf16_hi(v.x); o[2] = bf16_lo(v.y); o[3] = bf16_hi(v.y);
   o[4] = bf16_lo(v.z); o[5] = bf16_hi(v.z); o[6] = bf16_lo(v.w); o[7] = bf16_hi(v.w);
 }
-__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+// The node projection ABh is staged in HBM as fp16 (11-bit significand: its rounding adds to the first edge
+// linear's output, and bf16 would double the path's error); A_i + B_j is formed with one packed add and widened.
+__device__ __forceinline__ void add_f16x2_to_f32(uint32_t a, uint32_t b, float& lo, float& hi) {
   uint32_t r;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo), "=f"(hi)
+      : "r"(r));
 }
-__device__ __forceinline__ uint4 add_bf16x8(const uint4 a, const uint4 b) {
-  return make_uint4(add_bf16x2(a.x, b.x), add_bf16x2(a.y, b.y), add_bf16x2(a.z, b.z), add_bf16x2(a.w, b.w));
+__device__ __forceinline__ void add_f16x8_to_f32(const uint4 a, const uint4 b, float (&o)[8]) {
+  add_f16x2_to_f32(a.x, b.x, o[0], o[1]);
+  add_f16x2_to_f32(a.y, b.y, o[2], o[3]);
+  add_f16x2_to_f32(a.z, b.z, o[4], o[5]);
+  add_f16x2_to_f32(a.w, b.w, o[6], o[7]);
 }
 __device__ __forceinline__ float sum32(const float (&m)[32]) {
   float s[8];
@@ -163,7 +171,7 @@ __device__ __forceinline__ void st_256(void* addr, const uint4 a, const uint4 b)
 
 // =================================================================================================== fwd1
 struct Fwd1Params {
-  const __nv_bfloat16* ABh;   // [N,512] bf16, half domain: 0.5 (h Wa^T + b1) | 0.5 h Wb^T
+  const __half* ABh;           // [N,512] fp16, half domain: 0.5 (h Wa^T + b1) | 0.5 h Wb^T
   const float* d2;            // [E] squared edge lengths
   const int32_t* row;         // [E]
   const int32_t* col;         // [E]
@@ -275,9 +283,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
         uint4 out[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
-          // Ah_i + Bh_j in packed bf16 (the rounding an autocast bf16 Linear applies to its output), then fp32
           float s8[8], o8[8];
-          unpack8(add_bf16x8(pfA[kc & 1][i], pfB[kc & 1][i]), s8);
+          add_f16x8_to_f32(pfA[kc & 1][i], pfB[kc & 1][i], s8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float hu = fmaf(wd8[j], mc.d2[i], s8[j]);
@@ -826,7 +833,7 @@ constexpr int B1_REGS_EPI = 104;
 struct Bwd1Params {
   const uint8_t* ghvT;        // tile images of ghv
   const void* W2thp;          // packed image of 0.5 W2^T
-  const __nv_bfloat16* ABh;   // [N,512]
+  const __half* ABh;           // [N,512] fp16
   const float* d2;            // [E]
   const int32_t* row;         // [E]
   const int32_t* col;         // [E]
@@ -932,8 +939,8 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
       const bool valid = e < p.E;
       const int next_tile = tile + gridDim.x;
       if (next_tile < p.num_tiles) load_meta(next_tile, nrn, ncn, ddn);
-      const __nv_bfloat16* arow = p.ABh + (int64_t)nr * 2 * H + cq * 64;
-      const __nv_bfloat16* brow = p.ABh + (int64_t)nc * 2 * H + H + cq * 64;
+      const __half* arow = p.ABh + (int64_t)nr * 2 * H + cq * 64;
+      const __half* brow = p.ABh + (int64_t)nc * 2 * H + H + cq * 64;
       uint4 a4[4], b4[4];
       ld_256(arow, a4[0], a4[1]);
       ld_256(arow + 16, a4[2], a4[3]);
@@ -953,9 +960,14 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
         const int col0 = cq * 64 + b * 32;
         uint32_t raw[32];
         tmem_ld32_issue(lane_addr + acc * H + b * 32, raw);
-        uint4 s4[4];
+        float sab[32];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s4[k] = add_bf16x8(a4[k], b4[k]);
+        for (int k = 0; k < 4; ++k) {
+          float s8[8];
+          add_f16x8_to_f32(a4[k], b4[k], s8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sab[8 * k + j] = s8[j];
+        }
         if (b == 0) {
           ld_256(arow + 32, a4[0], a4[1]);
           ld_256(arow + 48, a4[2], a4[3]);
@@ -965,13 +977,11 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
         float r[32];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float s8[8];
-          unpack8(s4[k], s8);
           const float4 w0 = *reinterpret_cast<const float4*>(sWd + col0 + 8 * k);
           const float4 w1 = *reinterpret_cast<const float4*>(sWd + col0 + 8 * k + 4);
           const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[8 * k + j] = silu_grad_r(fmaf(w8[j], dd, s8[j]));
+          for (int j = 0; j < 8; ++j) r[8 * k + j] = silu_grad_r(fmaf(w8[j], dd, sab[8 * k + j]));
         }
         tmem_wait();
         if (b == 1) {
@@ -1014,6 +1024,328 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// =================================================================================================== wgrad
+// Weight gradients as split-K GEMMs over the edge dimension, accumulated in TMEM over all tiles of a CTA (2 x 256
+// columns = the whole 256 x 256 fp32 matrix) and written once per CTA to a partial buffer; wgrad_reduce_kernel sums
+// the partials in a fixed order (deterministic).  Both operands are rebuilt on the fly, nothing but hs / hvT / ghvT
+// is read from HBM.  The ring unit is a HALF tile (64 edges): 32 KB of each operand, 3 stages.
+//   MODE 5:  dW5h[k, f] = sum_e ghs[e, k] m[e, f]       A = ghs (MN-major, rows = edges), B = m = silu(hv) (K-major image)
+//            + column sums db5h[k] = sum_e ghs[e, k], dW6[k] = sum_e gw[e] t[e, k]  (in the row producers' registers)
+//   MODE 2:  dW2h[f, j] = sum_e ghv[e, f] a[e, j]       A = ghv (K-major image via TMA), B = a = silu(hu) (MN-major, rows = edges)
+// Warps: 0..15 row producers (4 per 64-column block, 16 rows each), 16 MMA issue, 17 TMA (MODE 2), 20..27 image
+// producers (MODE 5).  After the main loop warps 0..7 flush TMEM.
+constexpr int WG_HALF_BYTES = 64 * H * 2;          // 32 KB: one operand of a half tile
+constexpr int WG_STAGE_BYTES = 2 * WG_HALF_BYTES;  // 64 KB
+constexpr int WG_STAGES = 3;
+constexpr int WG_ROW_WARPS = 16;
+constexpr int WG_MMA_WARP = 16;
+constexpr int WG_TMA_WARP = 17;
+constexpr int WG_IMG_WARP0 = 20;
+constexpr int WG_IMG_WARPS = 8;
+constexpr int WG_VEC_OFF = WG_STAGES * WG_STAGE_BYTES;                 // 4 x 256 floats
+constexpr int WG_BAR_OFF = WG_VEC_OFF + 4 * H * 4;
+constexpr int WG_SMEM_BYTES = WG_BAR_OFF + 128 + 1024;
+template <int MODE> struct WgCfg {
+  static constexpr int WARPS = MODE == 5 ? WG_IMG_WARP0 + WG_IMG_WARPS : 20;
+  static constexpr int THREADS = 32 * WARPS;                            // 896 (72 regs) / 640 (96 regs)
+  static constexpr int FULL_COUNT = MODE == 5 ? 32 * (WG_ROW_WARPS + WG_IMG_WARPS) : 32 * WG_ROW_WARPS + 1;
+};
+
+struct WgradParams {
+  // MODE 5
+  const __nv_bfloat16* hs;    // [E,256]
+  const float* gw;            // [E]
+  const float* w6;            // [256]
+  const uint8_t* hvT;         // tile images of hv
+  float* db5h;                // [256] (+=)
+  float* dw6;                 // [256] (+=)
+  // MODE 2
+  const uint8_t* ghvT;        // tile images of ghv
+  const __half* ABh;           // [N,512] fp16
+  const float* d2;            // [E]
+  const int32_t* row;
+  const int32_t* col;
+  const float* wd;            // [256] (full domain; halved on load)
+  // both
+  float* partial;             // [gridDim.x][256*256] fp32
+  int64_t E;
+  int num_tiles;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* sVec = reinterpret_cast<float*>(smem + WG_VEC_OFF);          // MODE 5: w6 | db5h | dw6 ; MODE 2: wd/2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_BAR_OFF);
+  uint64_t* full = bars;                   // [WG_STAGES]
+  uint64_t* empty = bars + WG_STAGES;      // [WG_STAGES]
+  uint64_t* done = bars + 2 * WG_STAGES;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < H; k += WgCfg<MODE>::THREADS) {
+    sVec[k] = MODE == 5 ? p.w6[k] : 0.5f * p.wd[k];
+    sVec[H + k] = 0.f;
+    sVec[2 * H + k] = 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full[s], WgCfg<MODE>::FULL_COUNT);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nh = 2 * ((p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);   // half tiles of this CTA
+  auto tile_of = [&](int hi) { return (int)blockIdx.x + (hi >> 1) * (int)gridDim.x; };
+
+  if (warp < WG_ROW_WARPS) {
+    // ------------------------------------------------------------------ row producers: [64 rows][64 columns] blocks
+    const int cq = warp & 3;                        // 64-column block of this warp
+    const int chunk = lane & 7;
+    const int rl0 = (warp >> 2) * 16 + (lane >> 3); // local rows rl0 + 4 i, i < 4
+    const int c0 = cq * KCHUNK + chunk * 8;         // first of this thread's 8 columns
+    float v8[8];                                    // MODE 5: w6 ; MODE 2: wd/2
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v8[j] = sVec[c0 + j];
+    int stage = 0;
+    uint32_t phase = 0;
+    if constexpr (MODE == 5) {
+      float cs0[8], cs1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs0[j] = cs1[j] = 0.f;
+      uint4 pf[4];
+      float gwv[4];
+      auto issue = [&](int hi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t e = (int64_t)tile_of(hi) * TILE_M + (hi & 1) * 64 + rl0 + 4 * i;
+          const int64_t ec = e < p.E ? e : p.E - 1;
+          pf[i] = __ldg(reinterpret_cast<const uint4*>(p.hs + ec * H + c0));
+          gwv[i] = e < p.E ? __ldg(p.gw + e) : 0.f;
+        }
+      };
+      issue(0);
+      for (int hi = 0; hi < nh; ++hi) {
+        uint4 out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float h8[8], o8[8];
+          unpack8(pf[i], h8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t;
+            const float r = silu_grad_r(h8[j], t);
+            o8[j] = gwv[i] * fmaf(v8[j], r, v8[j]);
+            cs0[j] += o8[j];
+            cs1[j] = fmaf(gwv[i], t, cs1[j]);
+          }
+          out[i] = pack8(o8);
+        }
+        if (hi + 1 < nh) issue(hi + 1);
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * WG_STAGE_BYTES + cq * 8192;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(st + sw128_offset(rl0 + 4 * i, chunk)) = out[i];
+        fence_proxy_async();
+        mbar_arrive(&full[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      // column sums: lanes l, l^8, l^16, l^24 share columns -> shared -> one global atomic per column per CTA
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a0 = cs0[j], a1 = cs1[j];
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        if (lane < 8) {
+          atomicAdd(&sVec[H + c0 + j], a0);
+          atomicAdd(&sVec[2 * H + c0 + j], a1);
+        }
+      }
+    } else {
+      uint4 pfA[4], pfB[4];
+      float dd[4], ddn[4];
+      int nr[4], nc[4];
+      auto load_meta = [&](int hi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int64_t e = (int64_t)tile_of(hi) * TILE_M + (hi & 1) * 64 + rl0 + 4 * i;
+          e = e < p.E ? e : p.E - 1;                 // tail rows: finite values, multiplied by ghv = 0
+          nr[i] = __ldg(p.row + e);
+          nc[i] = __ldg(p.col + e);
+          ddn[i] = __ldg(p.d2 + e);
+        }
+      };
+      auto issue = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pfA[i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)nr[i] * 2 * H + c0));
+          pfB[i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)nc[i] * 2 * H + H + c0));
+        }
+      };
+      load_meta(0);
+      issue();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dd[i] = ddn[i];
+      if (nh > 1) load_meta(1);
+      for (int hi = 0; hi < nh; ++hi) {
+        uint4 out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float s8[8], o8[8];
+          add_f16x8_to_f32(pfA[i], pfB[i], s8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = silu_h(fmaf(v8[j], dd[i], s8[j]));
+          out[i] = pack8(o8);
+        }
+        if (hi + 1 < nh) {
+          issue();                                   // operands of half tile hi + 1 (its metadata is in nr / nc / ddn)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dd[i] = ddn[i];
+          if (hi + 2 < nh) load_meta(hi + 2);
+        }
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * WG_STAGE_BYTES + WG_HALF_BYTES + cq * 8192;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(st + sw128_offset(rl0 + 4 * i, chunk)) = out[i];
+        fence_proxy_async();
+        mbar_arrive(&full[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == WG_MMA_WARP) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issue (accumulates over every half tile)
+      constexpr uint32_t IDESC = MODE == 5 ? idesc_bf16(128, 256, true, false) : idesc_bf16(128, 256, false, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int hi = 0; hi < nh; ++hi) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * WG_STAGE_BYTES);
+        const uint32_t b_base = a_base + WG_HALF_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const uint32_t acc = (hi | ks) != 0 ? 1u : 0u;
+            if constexpr (MODE == 5)
+              umma_bf16(tmem_base + mh * H, desc_mnmajor(a_base + mh * 16384 + ks * 2048, 8192, 1024),
+                        desc_kmajor(b_base + ks * UMMA_K * 2), IDESC, acc);
+            else
+              umma_bf16(tmem_base + mh * H, desc_kmajor(a_base + mh * 16384 + ks * UMMA_K * 2),
+                        desc_mnmajor(b_base + ks * 2048, 8192, 1024), IDESC, acc);
+          }
+        umma_commit(&empty[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else if (MODE == 2 && warp == WG_TMA_WARP) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA: ghv image half (4 x 8 KB) -> A operand
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int hi = 0; hi < nh; ++hi) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], WG_HALF_BYTES);
+        const uint8_t* src = p.ghvT + (int64_t)tile_of(hi) * TILE_IMG_BYTES + (hi & 1) * 8192;
+        uint8_t* dst = smem + stage * WG_STAGE_BYTES;
+#pragma unroll
+        for (int fq = 0; fq < 4; ++fq) bulk_g2s(dst + fq * 8192, src + fq * 16384, 8192, &full[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (MODE == 5 && warp >= WG_IMG_WARP0) {
+    // ------------------------------------------------------------------ image producers: m = silu(hv), K-major B operand
+    const int pt = threadIdx.x - 32 * WG_IMG_WARP0;            // 0..255
+    constexpr int CPT = WG_HALF_BYTES / 16 / (32 * WG_IMG_WARPS);   // 8 chunks per thread per half tile
+    int stage = 0;
+    uint32_t phase = 0;
+    uint4 pf[CPT];
+    auto issue = [&](int hi) {
+      const uint8_t* src = p.hvT + (int64_t)tile_of(hi) * TILE_IMG_BYTES + (hi & 1) * 8192;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        const int idx = pt + 256 * i;                            // chunk of the 32 KB half: fq = idx >> 9
+        pf[i] = __ldg(reinterpret_cast<const uint4*>(src + (idx >> 9) * 16384 + (idx & 511) * 16));
+      }
+    };
+    issue(0);
+    for (int hi = 0; hi < nh; ++hi) {
+      uint4 out[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        float h8[8];
+        unpack8(pf[i], h8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h8[j] = silu_h(h8[j]);
+        out[i] = pack8(h8);
+      }
+      if (hi + 1 < nh) issue(hi + 1);
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint4* st = reinterpret_cast<uint4*>(smem + stage * WG_STAGE_BYTES + WG_HALF_BYTES);
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) st[pt + 256 * i] = out[i];
+      fence_proxy_async();
+      mbar_arrive(&full[stage]);
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+
+  // -------------------------------------------------------------------- flush: TMEM -> this CTA's partial matrix
+  if (warp < 8) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3, mh = warp >> 2;
+    float* dstrow = p.partial + (int64_t)blockIdx.x * H * H + (int64_t)(mh * 128 + q * 32 + lane) * H;
+#pragma unroll 1
+    for (int cb = 0; cb < 8; ++cb) {
+      uint32_t raw[32];
+      tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * H + cb * 32), raw);
+      tmem_wait();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<uint4*>(dstrow + cb * 32 + 4 * k) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (MODE == 5 && threadIdx.x < H) {
+    atomicAdd(p.db5h + threadIdx.x, sVec[H + threadIdx.x]);
+    atomicAdd(p.dw6 + threadIdx.x, sVec[2 * H + threadIdx.x]);
+  }
+  if (warp == WG_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// out[i] = scale * sum_g partial[g][i]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int G, float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * H) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int g = 0;
+  for (; g + 3 < G; g += 4) {
+    s0 += partial[(int64_t)g * H * H + i];
+    s1 += partial[(int64_t)(g + 1) * H * H + i];
+    s2 += partial[(int64_t)(g + 2) * H * H + i];
+    s3 += partial[(int64_t)(g + 3) * H * H + i];
+  }
+  for (; g < G; ++g) s0 += partial[(int64_t)g * H * H + i];
+  out[i] = scale * ((s0 + s1) + (s2 + s3));
 }
 
 // d2[e] = |x[row[e]] - x[col[e]]|^2  (models/en_gnn_decoder.py:61-62), one thread per edge
@@ -1060,6 +1392,24 @@ static int grid_for(int num_tiles) {
 using namespace pev;
 typedef __nv_bfloat16 bf16_t;
 
+template <int MODE>
+static int launch_wgrad(tc2::WgradParams& p, float scale, float* dW, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc2::wgrad_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc2::WG_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(2, "wgrad_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  p.num_tiles = (int)((p.E + tc2::TILE_M - 1) / tc2::TILE_M);
+  const int grid = tc2::grid_for(p.num_tiles);
+  tc2::wgrad_kernel<MODE><<<grid, tc2::WgCfg<MODE>::THREADS, tc2::WG_SMEM_BYTES, st>>>(p);
+  if (int rc = after_launch(MODE == 5 ? "edge2_wgrad5_kernel" : "edge2_wgrad2_kernel")) return rc;
+  tc2::wgrad_reduce_kernel<<<tc2::H * tc2::H / 256, 256, 0, st>>>(p.partial, grid, scale, dW);
+  return after_launch("wgrad_reduce_kernel");
+}
+
+
 extern "C" {
 
 int pev_pack_weight_bf16_scaled(const float* W, int32_t transpose, float scale, void* packed, void* stream) {
@@ -1096,7 +1446,7 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
     configured = true;
   }
   tc2::Fwd1Params p = {};
-  p.ABh = reinterpret_cast<const bf16_t*>(ABh); p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.b2 = b2; p.W2hp = W2hp;
+  p.ABh = reinterpret_cast<const __half*>(ABh); p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.b2 = b2; p.W2hp = W2hp;
   p.hvT = reinterpret_cast<uint8_t*>(hvT); p.agg = agg; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
@@ -1166,7 +1516,7 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
     configured = true;
   }
   tc2::Bwd1Params p = {};
-  p.ghvT = reinterpret_cast<const uint8_t*>(ghvT); p.W2thp = W2thp; p.ABh = reinterpret_cast<const bf16_t*>(ABh);
+  p.ghvT = reinterpret_cast<const uint8_t*>(ghvT); p.W2thp = W2thp; p.ABh = reinterpret_cast<const __half*>(ABh);
   p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.ghu = reinterpret_cast<bf16_t*>(ghu); p.gd2 = gd2;
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
@@ -1174,6 +1524,40 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SMEM_BYTES, st>>>(p);
   else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SMEM_BYTES, st>>>(p);
   return after_launch("edge2_bwd1_kernel");
+}
+
+int64_t pev_edge2_wgrad_workspace_bytes(void) { return (int64_t)sm_count() * tc2::H * tc2::H * (int64_t)sizeof(float); }
+
+int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* hvT, int64_t num_edges,
+                     float* workspace, float* dW5, float* db5, float* dw6, void* stream) {
+  PEV_REQUIRE(w6 && dW5 && db5 && dw6 && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(db5, 0, sizeof(float) * tc2::H, st);
+  cudaMemsetAsync(dw6, 0, sizeof(float) * tc2::H, st);
+  if (num_edges == 0) {
+    cudaMemsetAsync(dW5, 0, sizeof(float) * tc2::H * tc2::H, st);
+    return 0;
+  }
+  PEV_REQUIRE(hs && gw && hvT && workspace, "edge arrays missing");
+  tc2::WgradParams p = {};
+  p.hs = reinterpret_cast<const bf16_t*>(hs); p.gw = gw; p.w6 = w6; p.hvT = reinterpret_cast<const uint8_t*>(hvT);
+  p.db5h = db5; p.dw6 = dw6; p.partial = workspace; p.E = num_edges;
+  return launch_wgrad<5>(p, 0.5f, dW5, st);
+}
+
+int pev_edge2_wgrad2(const void* ghvT, const void* ABh, const float* d2, const int32_t* row, const int32_t* col,
+                     const float* wd, int64_t num_edges, float* workspace, float* dW2, void* stream) {
+  PEV_REQUIRE(wd && dW2 && num_edges >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  if (num_edges == 0) {
+    cudaMemsetAsync(dW2, 0, sizeof(float) * tc2::H * tc2::H, st);
+    return 0;
+  }
+  PEV_REQUIRE(ghvT && ABh && d2 && row && col && workspace, "edge arrays missing");
+  tc2::WgradParams p = {};
+  p.ghvT = reinterpret_cast<const uint8_t*>(ghvT); p.ABh = reinterpret_cast<const __half*>(ABh); p.d2 = d2;
+  p.row = row; p.col = col; p.wd = wd; p.partial = workspace; p.E = num_edges;
+  return launch_wgrad<2>(p, 0.5f, dW2, st);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@ from .graph import PackedGraph
 
 H = 256
 USE_V2 = os.environ.get("PEV_EDGE_V2", "1") != "0"      # v2 edge kernels (csrc/edge_tc2_kernels.cu)
+NODE_TF32_FORWARD = os.environ.get("PEV_NODE_TF32", "1") != "0"
 
 
 def supports(layer) -> bool:
@@ -71,8 +72,10 @@ class NodeLinear(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, W, b):
+    def forward(ctx, x, W, b, fp32_forward=False):
         ctx.save_for_backward(x, W)
+        if fp32_forward or not NODE_TF32_FORWARD:   # ill-conditioned consumers (N / C direction heads)
+            return torch.addmm(b, x, W.t())
         with _tf32_matmul():
             return torch.addmm(b, x, W.t())
 
@@ -84,16 +87,16 @@ class NodeLinear(torch.autograd.Function):
             gx = g @ W if ctx.needs_input_grad[0] else None
             gW = g.t() @ x if ctx.needs_input_grad[1] else None
         gb = g.sum(0) if ctx.needs_input_grad[2] else None
-        return gx, gW, gb
+        return gx, gW, gb, None
 
 
-def apply_tf32(module, x):
+def apply_tf32(module, x, fp32_forward=False):
     """Run an ``nn.Linear`` / ``nn.Sequential`` of the decoder with its linears on :class:`NodeLinear` (bf16 path)."""
     if isinstance(module, nn.Linear):
-        return NodeLinear.apply(x, module.weight, module.bias)
+        return NodeLinear.apply(x, module.weight, module.bias, fp32_forward)
     if isinstance(module, nn.Sequential):
         for m in module:
-            x = apply_tf32(m, x)
+            x = apply_tf32(m, x, fp32_forward)
         return x
     return module(x)
 
@@ -193,14 +196,9 @@ def egn_layer_bf16(layer, h, x, g: PackedGraph, dinv):
     caches = layer.__dict__.setdefault("_pev_packed", ({}, {}))
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
-    if not keep and USE_V2:
+    if USE_V2:
         from . import egnn_tc2
-        agg, x_new, _ = egnn_tc2.edge_forward(
-            egnn_tc2.node_projection_half(layer, h), x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
-            layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight, layer.phi_x[2].bias, dinv, g, False,
-            layer.__dict__.setdefault("_pev_packed2", ({}, {})))
-        q = layer.phi_h[1](NodeLinear.apply(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias))
-        return layer.norm_h(h + NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias)), x_new
+        return egnn_tc2.egn_layer_v2(layer, h, x, g, dinv)
     Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                      # [512, 256]
     bias = torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
     AB = NodeLinear.apply(h, Wcat, bias)                                  # [N, 512]

@@ -78,46 +78,126 @@ def rows_to_tile_image(rows: torch.Tensor) -> torch.Tensor:
     return v.view(T, TILE * H)
 
 
-# ------------------------------------------------------------------------------------------------ layer forward
-def edge_forward(ABh: torch.Tensor, x: torch.Tensor, wd, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches):
-    """Edge half of one EGNN layer on the v2 kernels.
+# ------------------------------------------------------------------------------------------------ one layer
+_WORKSPACE: dict = {}
 
-    ``ABh`` is the bf16 ``[N,512]`` half-domain node projection.  Returns ``(agg[N,256], x'[N,3], saved)`` where
-    ``saved`` holds what the backward kernels need (``hvT`` tile images, ``hs`` rows, ``w``, ``d2``) when ``keep``.
+
+def _wgrad_workspace(device) -> torch.Tensor:
+    ws = _WORKSPACE.get(device)
+    if ws is None:
+        ws = torch.empty(_lib.lib().cdll.pev_edge2_wgrad_workspace_bytes() // 4, dtype=torch.float32, device=device)
+        _WORKSPACE[device] = ws
+    return ws
+
+
+class FusedEdgeV2(torch.autograd.Function):
+    """(ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3]) on the v2 kernels.
+
+    ``ABh`` is the fp32 half-domain node projection ``0.5 [h Wa^T + b1 | h Wb^T]`` (rounded to fp16 here, once).
+    Forward: ``pev_edge_d2`` -> ``pev_edge2_fwd1`` -> ``pev_edge2_fwd2`` -> exact-order coordinate update (K2).
+    Kept for the backward pass: the ``hv`` tile images and ``hs`` rows (bf16, 2 x 2.47 GB per layer at config 2),
+    ``w``, ``d2`` and the fp16 ``ABh``.  Backward: K2 backward -> ``bwd2`` (ghv) -> ``wgrad5`` ->
+    ``bwd1`` (ghu) -> ``wgrad2`` -> segmented row / column sums of ``ghu``; the activations a, m and the SiLU
+    derivatives are rebuilt inside the kernels (one tanh each) instead of being stored.
     """
-    L = _lib.lib()
-    N, E = g.num_nodes, g.num_edges
-    dev = x.device
-    x = f32c(x)
-    wd, b2, b5 = f32c(wd.detach()), f32c(b2.detach()), f32c(b5.detach())
-    w6v, b6v = f32c(w6.detach()).reshape(-1), f32c(b6.detach()).reshape(-1)
-    dinv = f32c(dinv)
-    with torch.cuda.device_of(x):
-        st = stream(x)
-        W2hp = packed_weight_scaled(W2, 0.5, cache=caches[0])
-        W5hp = packed_weight_scaled(W5, 0.5, cache=caches[1])
-        d2 = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
-        hvT = alloc_tile_image(E, dev)
-        hs = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
-        agg = torch.empty(N, H, dtype=torch.float32, device=dev)
-        w = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
-        x_out = torch.empty_like(x)
-        L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2), st)
-        with _lib.profiled("edge2_fwd1"):
-            L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E,
-                   ptr(hvT), ptr(agg), st)
-        with _lib.profiled("edge2_fwd2"):
-            L.call("pev_edge2_fwd2", ptr(hvT), ptr(W5hp), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(hs), st)
-        L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
-               None, ptr(x_out), st)
-    saved = (hvT, hs, w, d2) if keep else None
-    return agg, x_out, saved
+
+    @staticmethod
+    def forward(ctx, ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches):
+        L = _lib.lib()
+        N, E = g.num_nodes, g.num_edges
+        dev = x.device
+        x = f32c(x)
+        wd, b2, b5 = f32c(wd), f32c(b2), f32c(b5)
+        w6v, b6v = f32c(w6).reshape(-1), f32c(b6).reshape(-1)
+        dinv = f32c(dinv)
+        with torch.cuda.device_of(x):
+            st = stream(x)
+            ABb = ABh.detach().to(torch.float16).contiguous()   # fp16 staging (see edge_tc2_kernels.cu)
+            W2hp = packed_weight_scaled(W2, 0.5, cache=caches[0])
+            W5hp = packed_weight_scaled(W5, 0.5, cache=caches[1])
+            d2 = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+            hvT = alloc_tile_image(E, dev)
+            hs = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
+            agg = torch.empty(N, H, dtype=torch.float32, device=dev)
+            w = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+            x_out = torch.empty_like(x)
+            L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2), st)
+            with _lib.profiled("edge2_fwd1"):
+                L.call("pev_edge2_fwd1", ptr(ABb), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E,
+                       ptr(hvT), ptr(agg), st)
+            with _lib.profiled("edge2_fwd2"):
+                L.call("pev_edge2_fwd2", ptr(hvT), ptr(W5hp), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(hs), st)
+            L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
+                   None, ptr(x_out), st)
+        ctx.g, ctx.caches = g, caches
+        if keep:
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, hs, w, d2)
+        else:
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None)
+        return agg, x_out
+
+    @staticmethod
+    def backward(ctx, gagg, gxo):
+        x, wd, W2, W5, w6v, dinv, ABb, hvT, hs, w, d2 = ctx.saved_tensors
+        if hs is None:
+            raise RuntimeError("FusedEdgeV2 ran with keep=False (no_grad); backward is unavailable")
+        g = ctx.g
+        N, E = g.num_nodes, g.num_edges
+        gagg, gxo = f32c(gagg), f32c(gxo)
+        bf, f32 = torch.bfloat16, torch.float32
+        L = _lib.lib()
+        with torch.cuda.device_of(x):
+            dev, st = x.device, stream(x)
+            W5thp = packed_weight_scaled(W5, 0.5, transpose=True, cache=ctx.caches[1])
+            W2thp = packed_weight_scaled(W2, 0.5, transpose=True, cache=ctx.caches[0])
+            ws = _wgrad_workspace(dev)
+            gw = torch.empty(max(E, 1), dtype=f32, device=dev)
+            gx = torch.empty(N, 3, dtype=f32, device=dev)
+            L.call("pev_scatter_coord_bwd", None, ptr(gxo), ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.row),
+                   ptr(g.col), ptr(g.col_ptr), ptr(g.csc_perm), N, E, H, None, ptr(gw), ptr(gx), st)
+            ghvT = alloc_tile_image(E, dev)
+            db2h = torch.empty(H, dtype=f32, device=dev)
+            with _lib.profiled("edge2_bwd2"):
+                L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6v), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E,
+                       ptr(ghvT), ptr(db2h), st)
+            gW5 = torch.empty(H, H, dtype=f32, device=dev)
+            db5h, gw6 = torch.empty(H, dtype=f32, device=dev), torch.empty(H, dtype=f32, device=dev)
+            with _lib.profiled("edge2_wgrad5"):
+                L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6v), ptr(hvT), E, ptr(ws), ptr(gW5), ptr(db5h),
+                       ptr(gw6), st)
+            ghu = torch.empty(E, H, dtype=bf, device=dev)
+            gd2 = torch.empty(max(E, 1), dtype=f32, device=dev)
+            with _lib.profiled("edge2_bwd1"):
+                L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABb), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E,
+                       ptr(ghu), ptr(gd2), st)
+            gW2 = torch.empty(H, H, dtype=f32, device=dev)
+            with _lib.profiled("edge2_wgrad2"):
+                L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(ABb), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ws),
+                       ptr(gW2), st)
+            del ghvT
+            gAB = torch.empty(N, 2 * H, dtype=f32, device=dev)
+            part = torch.empty(N, H, dtype=f32, device=dev)
+            with _lib.profiled("edge_prologue_bwd"):
+                L.call("pev_edge_prologue_bwd_bf16", ptr(ghu), ptr(gd2), ptr(x), ptr(g.row_ptr), ptr(g.row), ptr(g.col),
+                       ptr(g.col_ptr), ptr(g.csc_perm), N, E, ptr(gAB), ptr(gx), ptr(part), st)
+            gwd = 0.5 * part.sum(0)                     # hu = ... + (wd/2) d2
+            gb6 = gw[:E].sum().reshape(1)
+        return (gAB, gx, gwd, gW2, 0.5 * db2h, gW5, 0.5 * db5h, gw6.reshape(1, H), gb6, None, None, None, None)
 
 
-def node_projection_half(layer, h: torch.Tensor) -> torch.Tensor:
-    """``ABh = 0.5 [h Wa^T + b1 | h Wb^T]`` as bf16 ``[N,512]`` (node-level library GEMM, TF32 tensor cores)."""
+def egn_layer_v2(layer, h, x, g, dinv):
+    """One EGNN layer with the edge MLP on the v2 kernels; ``layer`` is an ``EGNLayer`` (parameter holder)."""
     from .egnn_tc import NodeLinear
-    W1 = layer.phi_e[0].weight
-    Wcat = 0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)
+    W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
+    keep = torch.is_grad_enabled() and any(
+        t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
+    Wcat = 0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                # half domain
     bias = 0.5 * torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
-    return NodeLinear.apply(h, Wcat, bias).to(torch.bfloat16)
+    ABh = NodeLinear.apply(h, Wcat, bias)                                 # fp32 [N,512]
+    caches = layer.__dict__.setdefault("_pev_packed2", ({}, {}))
+    agg, x_new = FusedEdgeV2.apply(ABh, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
+                                   layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
+                                   layer.phi_x[2].bias, dinv, g, keep, caches)
+    q = layer.phi_h[1](NodeLinear.apply(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias))
+    h_new = layer.norm_h(h + NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias))
+    return h_new, x_new

@@ -144,11 +144,12 @@ class EGNNDecoder(nn.Module):
         g = band_graph(lengths, self.max_neighbors, device)
         return g, (g.dinv if self.degree_normalize else None)
 
-    def _run(self, module, x):
-        """Node-level heads: plain modules on the fp32 path, TF32 tensor-core linears on the bf16 path."""
+    def _run(self, module, x, fp32_forward=False):
+        """Node-level heads: plain modules on the fp32 path, TF32 tensor-core linears on the bf16 path
+        (``fp32_forward`` keeps the forward product in fp32 for the ill-conditioned N / C direction heads)."""
         if self.precision == "bf16" and x.is_cuda:
             from .egnn_tc import apply_tf32
-            return apply_tf32(module, x)
+            return apply_tf32(module, x, fp32_forward)
         return module(x)
 
     def forward(self, z_g: torch.Tensor, z_l: torch.Tensor, mask: torch.Tensor | None = None):
@@ -192,8 +193,8 @@ class EGNNDecoder(nn.Module):
 
     def _backbone(self, h, x_ca, g):
         """N / C placement and the 3-step peptide pull (``:260-310``), vectorised over the packed batch."""
-        n_dir = self._run(self.n_offset_head, h)[:, :3]         # 4th channel unused in the reference too
-        c_dir = self._run(self.c_offset_head, h)[:, :3]
+        n_dir = self._run(self.n_offset_head, h, True)[:, :3]        # 4th channel unused in the reference too
+        c_dir = self._run(self.c_offset_head, h, True)[:, :3]
         x_n = x_ca + F.normalize(n_dir, dim=-1) * N_CA_LENGTH
         x_c = x_ca + F.normalize(c_dir, dim=-1) * CA_C_LENGTH
         N = x_ca.shape[0]

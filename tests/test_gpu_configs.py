@@ -80,30 +80,19 @@ def test_mixed_lengths_config3_padding_and_batch_invariance():
         assert float(o[mask == 0].abs().max()) == 0.0
 
 
-def _emulate_autocast_edge_mlp(dec):
-    """Reference point for 'bf16 edge MLP': the fp32 path with the two 256x256 edge linears evaluated the way
-    torch.autocast would (bf16 operands and outputs, fp32 accumulation)."""
-    import torch.nn.functional as F
-    bf = torch.bfloat16
-    for layer in dec.layers:
-        for lin in (layer.phi_e[2], layer.phi_x[0]):
-            def fwd(x, lin=lin):
-                return F.linear(x.to(bf).float(), lin.weight.to(bf).float(), lin.bias).to(bf).float()
-            lin.forward = fwd
-
-
 def test_decoder_bf16_tracks_fp32_at_config2_depth():
     """6 layers, L=256.  CA coordinates and logits of the tcgen05 path stay within 1e-2 of the fp32 exact-order
-    path (measured 1.6e-5 and 3e-3).  N / C = CA + 1.46 normalize(head(h)) are ill-conditioned at random init
-    (normalising near-zero direction vectors): there the yardstick is an ideal bf16 edge MLP -- the fp32 path with
-    autocast-style rounding of the two edge linears -- which drifts by 4.5e-2 at this depth; the tensor-core
-    path must not drift more than that (tools/bf16_drift.py prints the table for 1-8 layers)."""
+    path.  N / C = CA + 1.46 normalize(head(h)) are ill-conditioned at random init (normalising near-zero
+    direction vectors): there the yardstick is an ideal bf16 edge MLP -- the fp32 path with the three edge linears
+    rounded the way torch.autocast would (tests/bf16_yardstick.py); the tensor-core path must not drift more
+    than 1.5x that (tools/bf16_drift.py prints the table for 1-8 layers)."""
+    from bf16_yardstick import emulate_autocast_edge_mlp
     d32, dac, d16 = (_decoder(6, p, seed=5) for p in ("fp32", "fp32", "bf16"))
     dac.load_state_dict(d32.state_dict())
     d16.load_state_dict(d32.state_dict())
-    _emulate_autocast_edge_mlp(dac)
+    dac.precision = "autocast-emu"
     zg, zl = torch.randn(4, 64, device=DEV), torch.randn(4, 256, 32, device=DEV)
-    with torch.no_grad():
+    with torch.no_grad(), emulate_autocast_edge_mlp():
         ref, emu, got = d32(zg, zl), dac(zg, zl), d16(zg, zl)
     assert rel_err(got[1], ref[1]) < 1e-2 and rel_err(got[3], ref[3]) < 1e-2
     for r, e, g in zip(ref, emu, got):

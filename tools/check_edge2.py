@@ -31,7 +31,7 @@ b2, b5, w6 = (torch.randn(H, device=dev) * 0.1 for _ in range(3))
 b6 = torch.randn(1, device=dev)
 wd = W1[:, 2 * H].contiguous()
 Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)
-ABh = (0.5 * (h @ Wcat.t() + torch.cat([b1, torch.zeros_like(b1)]))).to(torch.bfloat16).contiguous()
+ABh = (0.5 * (h @ Wcat.t() + torch.cat([b1, torch.zeros_like(b1)]))).to(torch.float16).contiguous()
 row, col = g.row.long(), g.col.long()
 
 

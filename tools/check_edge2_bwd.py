@@ -24,7 +24,7 @@ N, E = g.num_nodes, g.num_edges
 torch.manual_seed(0)
 bf16 = torch.bfloat16
 x = torch.randn(N, 3, device=dev) * 3
-ABh = (torch.randn(N, 2 * H, device=dev) * 0.5).to(bf16)
+ABh = (torch.randn(N, 2 * H, device=dev) * 0.5).to(torch.float16)
 wd = torch.randn(H, device=dev) * 0.02
 W2, W5 = torch.randn(H, H, device=dev) / 16, torch.randn(H, H, device=dev) / 16
 w6 = torch.randn(H, device=dev) * 0.1
@@ -70,7 +70,10 @@ ghu_k = torch.empty(E, H, dtype=bf16, device=dev)
 gd2_k = torch.empty(E, device=dev)
 d2k = torch.empty(E, device=dev)
 L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2k), st)
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+ws = torch.empty(L.cdll.pev_edge2_wgrad_workspace_bytes() // 4, device=dev)
+dW5_k, dW2_k = torch.empty(H, H, device=dev), torch.empty(H, H, device=dev)
+db5h_k, dw6_k = torch.empty(H, device=dev), torch.empty(H, device=dev)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 for rep in range(reps + 1):
     ev[0].record()
     L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ghvT),
@@ -79,9 +82,13 @@ for rep in range(reps + 1):
     L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABh), ptr(d2k), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ghu_k),
            ptr(gd2_k), st)
     ev[2].record()
+    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(hvT), E, ptr(ws), ptr(dW5_k), ptr(db5h_k), ptr(dw6_k), st)
+    ev[3].record()
+    L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(ABh), ptr(d2k), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ws), ptr(dW2_k), st)
+    ev[4].record()
     torch.cuda.synchronize()
-ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(2)]
-print(f"B={B} L={Lr} W={Wn} N={N} E={E} ms bwd2={ms[0]:.3f} bwd1={ms[1]:.3f}")
+ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+print(f"B={B} L={Lr} W={Wn} N={N} E={E} ms bwd2={ms[0]:.3f} bwd1={ms[1]:.3f} wgrad5={ms[2]:.3f} wgrad2={ms[3]:.3f}")
 ghv_k = T2.tile_image_to_rows(ghvT, E).float()
 print(f"ghv  rel err {rel(ghv_k, ghv):.3e}")
 print(f"db2h rel err {rel(db2h_k, db2h):.3e}")
@@ -90,3 +97,14 @@ ga2 = ghv_k @ bf(0.5 * W2)
 ghu2 = ga2 * one_plus_r(hu)
 print(f"ghu  rel err {rel(ghu_k.float(), ghu2):.3e}   (vs end-to-end reference {rel(ghu_k.float(), ghu):.3e})")
 print(f"gd2  rel err {rel(gd2_k, ghu2 @ (0.5 * wd)):.3e}")
+# weight gradients
+hsf, hvf = hs.float(), hv.float()
+m = hvf + hvf * torch.tanh(hvf)
+tt = hsf + hsf * torch.tanh(hsf)
+dW5 = 0.5 * bf(ghs).t().double() @ bf(m).double()
+print(f"dW5  rel err {rel(dW5_k, dW5):.3e}")
+print(f"db5h rel err {rel(db5h_k, ghs.double().sum(0)):.3e}")
+print(f"dw6  rel err {rel(dw6_k, (gw[:, None].double() * tt.double()).sum(0)):.3e}")
+a = hu + hu * torch.tanh(hu)
+dW2 = 0.5 * ghv_k.t().double() @ bf(a).double()
+print(f"dW2  rel err {rel(dW2_k, dW2):.3e}")
