@@ -196,6 +196,19 @@ int pev_edge2_wgrad2(const void* ghvT, const void* ABh, const float* d2, const i
                      const int32_t* col, const float* wd, int64_t num_edges, float* workspace,
                      float* dW2 /*[256,256]*/, void* stream);
 
+/* ---------------------------------------------------------------- node-level kernels (bf16 path)
+ * y = LayerNorm(x + res) (models/en_gnn_decoder.py:72-73; res may be NULL), fp32, one warp per row,
+ * D = 256 or 512; also writes r = x + res (if r_out != NULL), mean[N], rstd[N] for the backward pass. */
+int pev_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                          float eps, int64_t N, int32_t D, float* r_out, float* y, float* mean,
+                          float* rstd, void* stream);
+/* One pass over gy and r: gr = dL/dr and the column sums dgamma[D], dbeta[D] (zeroed inside). */
+int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const float* mean,
+                      const float* rstd, int64_t N, int32_t D, float* gr, float* dgamma, float* dbeta,
+                      void* stream);
+/* out[D] = sum over rows of g[N,D] (bias gradients of the node-level linears; zeroed inside). */
+int pev_column_sum(const float* g, int64_t N, int32_t D, float* out, void* stream);
+
 /* ---------------------------------------------------------------- K3: losses
  * Forward accumulators: acc_global[2*PEV_NUM_TERMS] doubles (numerator, denominator per term;
  * pre-zeroed) and acc_sample[B*8] doubles (per conformer: rec_ca, rec_n, rec_c numerators,

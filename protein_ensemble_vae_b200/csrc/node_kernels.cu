@@ -1,0 +1,200 @@
+// Node-level kernels of the EGNN layer: y = LayerNorm(x + res) (models/en_gnn_decoder.py:72-73, `h = norm_h(h + h_update)`)
+// and its backward, one warp per row, fp32.  HBM-bound streams: forward reads x, res and writes r = x + res, y
+// (+ mean, rstd); backward reads gy, r and writes gr in ONE pass, with the column sums d gamma = sum gy xhat and
+// d beta = sum gy accumulated in registers across the rows a warp visits (grid-stride), then block -> global atomics.
+#include "../../include/pev_b200.h"
+#include "pev_common.cuh"
+
+namespace pev {
+
+template <int D>   // D = 256 or 512: D / 128 float4 per lane
+__global__ void __launch_bounds__(256)
+add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, int64_t N, float* __restrict__ r_out,
+                         float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  constexpr int V = D / 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g4[V], b4[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    g4[k] = reinterpret_cast<const float4*>(gamma)[lane + 32 * k];
+    b4[k] = reinterpret_cast<const float4*>(beta)[lane + 32 * k];
+  }
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      v[k] = reinterpret_cast<const float4*>(x + row * D)[lane + 32 * k];
+      if (res) {
+        const float4 q = reinterpret_cast<const float4*>(res + row * D)[lane + 32 * k];
+        v[k].x += q.x; v[k].y += q.y; v[k].z += q.z; v[k].w += q.w;
+      }
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mu = warp_sum(s) * (1.0f / D);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float a = v[k].x - mu, b = v[k].y - mu, c = v[k].z - mu, d = v[k].w - mu;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rs = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      if (r_out) reinterpret_cast<float4*>(r_out + row * D)[lane + 32 * k] = v[k];
+      float4 o;
+      o.x = (v[k].x - mu) * rs * g4[k].x + b4[k].x;
+      o.y = (v[k].y - mu) * rs * g4[k].y + b4[k].y;
+      o.z = (v[k].z - mu) * rs * g4[k].z + b4[k].z;
+      o.w = (v[k].w - mu) * rs * g4[k].w + b4[k].w;
+      reinterpret_cast<float4*>(y + row * D)[lane + 32 * k] = o;
+    }
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ r, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int64_t N,
+                     float* __restrict__ gr, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int V = D / 128;
+  __shared__ float sG[D], sB[D];
+  const int lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) sG[k] = sB[k] = 0.f;
+  __syncthreads();
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g4[V], dg[V], db[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    g4[k] = reinterpret_cast<const float4*>(gamma)[lane + 32 * k];
+    dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[V], gg[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float4 g = reinterpret_cast<const float4*>(gy + row * D)[lane + 32 * k];
+      const float4 v = reinterpret_cast<const float4*>(r + row * D)[lane + 32 * k];
+      xh[k] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+      db[k].x += g.x; db[k].y += g.y; db[k].z += g.z; db[k].w += g.w;
+      dg[k].x = fmaf(g.x, xh[k].x, dg[k].x); dg[k].y = fmaf(g.y, xh[k].y, dg[k].y);
+      dg[k].z = fmaf(g.z, xh[k].z, dg[k].z); dg[k].w = fmaf(g.w, xh[k].w, dg[k].w);
+      gg[k] = make_float4(g.x * g4[k].x, g.y * g4[k].y, g.z * g4[k].z, g.w * g4[k].w);
+      s1 += (gg[k].x + gg[k].y) + (gg[k].z + gg[k].w);
+      s2 += (gg[k].x * xh[k].x + gg[k].y * xh[k].y) + (gg[k].z * xh[k].z + gg[k].w * xh[k].w);
+    }
+    const float m1 = warp_sum(s1) * (1.0f / D), m2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float4 o;
+      o.x = rs * (gg[k].x - m1 - xh[k].x * m2);
+      o.y = rs * (gg[k].y - m1 - xh[k].y * m2);
+      o.z = rs * (gg[k].z - m1 - xh[k].z * m2);
+      o.w = rs * (gg[k].w - m1 - xh[k].w * m2);
+      reinterpret_cast<float4*>(gr + row * D)[lane + 32 * k] = o;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    atomicAdd(&sG[c], dg[k].x); atomicAdd(&sG[c + 1], dg[k].y); atomicAdd(&sG[c + 2], dg[k].z); atomicAdd(&sG[c + 3], dg[k].w);
+    atomicAdd(&sB[c], db[k].x); atomicAdd(&sB[c + 1], db[k].y); atomicAdd(&sB[c + 2], db[k].z); atomicAdd(&sB[c + 3], db[k].w);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    atomicAdd(dgamma + k, sG[k]);
+    atomicAdd(dbeta + k, sB[k]);
+  }
+}
+
+// out[c] = sum_rows g[row, c]  (bias gradients): block of 256 threads owns 64 columns x 4 row lanes
+__global__ void __launch_bounds__(256)
+column_sum_kernel(const float* __restrict__ g, int64_t N, int D, float* __restrict__ out) {
+  __shared__ float4 sm[256];
+  const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;          // 16 float4 columns x 16 row lanes
+  const int col4 = blockIdx.x * 16 + c4;                            // float4 column index
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col4 * 4 < D) {
+    for (int64_t row = (int64_t)blockIdx.y * 16 + rl; row < N; row += (int64_t)gridDim.y * 16) {
+      const float4 v = reinterpret_cast<const float4*>(g + row * D)[col4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0 && col4 * 4 < D) {
+    for (int k = 1; k < 16; ++k) {
+      const float4 v = sm[k * 16 + c4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(out + 4 * col4, acc.x); atomicAdd(out + 4 * col4 + 1, acc.y);
+    atomicAdd(out + 4 * col4 + 2, acc.z); atomicAdd(out + 4 * col4 + 3, acc.w);
+  }
+}
+
+static int rows_grid(int64_t N) {
+  int64_t g = (N + 7) / 8;                      // 8 warps per block
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace pev
+
+using namespace pev;
+
+extern "C" {
+
+int pev_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps,
+                          int64_t N, int32_t D, float* r_out, float* y, float* mean, float* rstd, void* stream) {
+  PEV_REQUIRE(N >= 0 && (D == 256 || D == 512), "D must be 256 or 512");
+  if (N == 0) return 0;
+  PEV_REQUIRE(x && gamma && beta && y && mean && rstd, "null argument");
+  cudaStream_t st = as_stream(stream);
+  if (D == 256)
+    add_layernorm_fwd_kernel<256><<<rows_grid(N), 256, 0, st>>>(x, res, gamma, beta, eps, N, r_out, y, mean, rstd);
+  else
+    add_layernorm_fwd_kernel<512><<<rows_grid(N), 256, 0, st>>>(x, res, gamma, beta, eps, N, r_out, y, mean, rstd);
+  return after_launch("add_layernorm_fwd_kernel");
+}
+
+int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const float* mean, const float* rstd,
+                      int64_t N, int32_t D, float* gr, float* dgamma, float* dbeta, void* stream) {
+  PEV_REQUIRE(N >= 0 && (D == 256 || D == 512) && dgamma && dbeta, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st);
+  cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st);
+  if (N == 0) return 0;
+  PEV_REQUIRE(gy && r && gamma && mean && rstd && gr, "null argument");
+  if (D == 256)
+    layernorm_bwd_kernel<256><<<rows_grid(N), 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, dgamma, dbeta);
+  else
+    layernorm_bwd_kernel<512><<<rows_grid(N), 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, dgamma, dbeta);
+  return after_launch("layernorm_bwd_kernel");
+}
+
+int pev_column_sum(const float* g, int64_t N, int32_t D, float* out, void* stream) {
+  PEV_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && out, "bad argument (D must be a multiple of 4)");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(out, 0, sizeof(float) * D, st);
+  if (N == 0) return 0;
+  PEV_REQUIRE(g, "null argument");
+  const int gx = (D / 4 + 15) / 16;
+  int64_t gy = (N + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8 / gx + 1;
+  if (gy > cap) gy = cap;
+  column_sum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(g, N, D, out);
+  return after_launch("column_sum_kernel");
+}
+
+}  // extern "C"

@@ -63,6 +63,60 @@ class _tf32_matmul:
         return False
 
 
+def column_sum(g: torch.Tensor) -> torch.Tensor:
+    """``g.sum(0)`` of a contiguous fp32 ``[N,D]`` (bias gradients) on ``pev_column_sum``."""
+    N, D = g.shape
+    if D % 4 or g.dtype != torch.float32:
+        return g.sum(0)
+    with torch.cuda.device_of(g):
+        out = torch.empty(D, dtype=torch.float32, device=g.device)
+        _lib.lib().call("pev_column_sum", ptr(g), N, D, ptr(out), stream(g))
+    return out
+
+
+class AddLayerNorm(torch.autograd.Function):
+    """``LayerNorm(x + res)`` (``res`` may be None) on ``pev_add_layernorm_fwd`` / ``pev_layernorm_bwd``."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        x = f32c(x)
+        res = f32c(res)
+        N, D = x.shape
+        with torch.cuda.device_of(x):
+            r = torch.empty_like(x) if res is not None else x
+            y = torch.empty_like(x)
+            mean = torch.empty(N, dtype=torch.float32, device=x.device)
+            rstd = torch.empty(N, dtype=torch.float32, device=x.device)
+            g_, b_ = f32c(gamma.detach()), f32c(beta.detach())
+            _lib.lib().call("pev_add_layernorm_fwd", ptr(x), ptr(res), ptr(g_), ptr(b_), float(eps), N, D,
+                            ptr(r) if res is not None else None, ptr(y), ptr(mean), ptr(rstd), stream(x))
+        ctx.save_for_backward(r, g_, mean, rstd)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        r, gamma, mean, rstd = ctx.saved_tensors
+        gy = f32c(gy)
+        N, D = r.shape
+        with torch.cuda.device_of(r):
+            gr = torch.empty_like(r)
+            dg = torch.empty(D, dtype=torch.float32, device=r.device)
+            db = torch.empty(D, dtype=torch.float32, device=r.device)
+            _lib.lib().call("pev_layernorm_bwd", ptr(gy), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), N, D, ptr(gr),
+                            ptr(dg), ptr(db), stream(r))
+        return gr, (gr if ctx.has_res else None), dg, db, None
+
+
+def layer_norm(module: nn.LayerNorm, x, res=None):
+    """``module(x + res)`` through :class:`AddLayerNorm` when the shape is supported, else plain torch."""
+    D = x.shape[-1]
+    if (x.is_cuda and x.dim() == 2 and D in (256, 512) and module.elementwise_affine and module.bias is not None
+            and tuple(module.normalized_shape) == (D,)):
+        return AddLayerNorm.apply(x, res, module.weight, module.bias, module.eps)
+    return module(x if res is None else x + res)
+
+
 class NodeLinear(torch.autograd.Function):
     """``x W^T + b`` for the node-level linears of the bf16 path (plain library GEMMs).
 
@@ -86,7 +140,7 @@ class NodeLinear(torch.autograd.Function):
         with _tf32_matmul():
             gx = g @ W if ctx.needs_input_grad[0] else None
             gW = g.t() @ x if ctx.needs_input_grad[1] else None
-        gb = g.sum(0) if ctx.needs_input_grad[2] else None
+        gb = column_sum(g) if ctx.needs_input_grad[2] else None
         return gx, gW, gb, None
 
 
@@ -98,6 +152,8 @@ def apply_tf32(module, x, fp32_forward=False):
         for m in module:
             x = apply_tf32(m, x, fp32_forward)
         return x
+    if isinstance(module, nn.LayerNorm):
+        return layer_norm(module, x)
     return module(x)
 
 

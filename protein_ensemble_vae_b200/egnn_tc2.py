@@ -187,7 +187,7 @@ class FusedEdgeV2(torch.autograd.Function):
 
 def egn_layer_v2(layer, h, x, g, dinv):
     """One EGNN layer with the edge MLP on the v2 kernels; ``layer`` is an ``EGNLayer`` (parameter holder)."""
-    from .egnn_tc import NodeLinear
+    from .egnn_tc import NodeLinear, layer_norm
     W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
@@ -199,5 +199,5 @@ def egn_layer_v2(layer, h, x, g, dinv):
                                    layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
                                    layer.phi_x[2].bias, dinv, g, keep, caches)
     q = layer.phi_h[1](NodeLinear.apply(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias))
-    h_new = layer.norm_h(h + NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias))
+    h_new = layer_norm(layer.norm_h, NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias), h)
     return h_new, x_new

@@ -181,3 +181,29 @@ def test_no_grad_decode_keeps_nothing():
     # N-CA and CA-C bonds are fixed-length offsets (models/en_gnn_decoder.py:289-293); C is never pulled
     assert torch.allclose((c - ca).norm(dim=-1), torch.full((5, 70), 1.52, device="cuda"), atol=1e-4)
 
+
+
+def test_add_layernorm_and_column_sum_match_torch():
+    """Node-level kernels of the bf16 path (csrc/node_kernels.cu) against torch fp32 (1e-5)."""
+    from protein_ensemble_vae_b200.egnn_tc import AddLayerNorm, column_sum
+    torch.manual_seed(3)
+    for D, N in ((256, 1000), (512, 333)):
+        x = torch.randn(N, D, device="cuda", requires_grad=True)
+        res = torch.randn(N, D, device="cuda", requires_grad=True)
+        ln = torch.nn.LayerNorm(D).cuda()
+        with torch.no_grad():
+            ln.weight.uniform_(0.5, 1.5)
+            ln.bias.uniform_(-0.5, 0.5)
+        coef = torch.randn(N, D, device="cuda")
+        y = AddLayerNorm.apply(x, res, ln.weight, ln.bias, ln.eps)
+        (y * coef).sum().backward()
+        got = (y.detach(), x.grad.clone(), res.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone())
+        x.grad = res.grad = ln.weight.grad = ln.bias.grad = None
+        y2 = ln(x + res)
+        (y2 * coef).sum().backward()
+        ref = (y2.detach(), x.grad, res.grad, ln.weight.grad, ln.bias.grad)
+        for a, b in zip(got, ref):
+            assert rel_err(a, b) < 1e-5
+        y3 = AddLayerNorm.apply(x.detach(), None, ln.weight, ln.bias, ln.eps)
+        assert rel_err(y3, ln(x.detach())) < 1e-5
+        assert rel_err(column_sum(coef), coef.sum(0)) < 1e-5
