@@ -252,20 +252,44 @@ def run_gpu(args):
     if rank == 0:
         hbm, tf, which = peaks()
         E = lib_edges(L) * B
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of edge_mlp_kernel<1> from the ncu --set full
-        # capture in profiles/ (1074.9 B per edge at B=32, training mode: it writes v and a as bf16), per launch
-        roof = {"bound": "tensor", "kernel": "edge_mlp_kernel<1> (tcgen05 GEMM W2 + gather/SiLU/segment-sum)",
-                "achieved": None, "peak": tf, "unit": "TFLOP/s", "frac": None, "traffic": 1074.9 * E,
-                "traffic_source": "profiles/r01_edge_kernels_ncu.md", "peak_source": which}
-        ev = prof.get("edge_mlp1", []) if prof else []
-        if ev:
+        # Per-kernel rooflines of the tcgen05 edge kernels, timed live with CUDA events inside the timed region
+        # (_lib.profiled).  Algorithmic bytes per edge = the bf16 [E,256] streams a kernel must read / write (512 B
+        # each) + the per-edge scalars; algorithmic flops per edge = 2 * 256 * 256 per GEMM.
+        # "traffic" of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the
+        # ncu --set full capture in profiles/ (scaled from its B=32 launch by the edge count).
+        KSPEC = {  # tag: (kernel, streams read+written, extra bytes per edge, tcgen05 GEMMs, tanh per edge-feature)
+            "edge2_fwd1": ("fwd1_kernel", 1, 16, 1, 2),
+            "edge2_fwd2": ("fwd2_kernel", 2, 4, 1, 2),
+            "edge2_bwd2": ("bwd2_kernel", 3, 8, 1, 2),
+            "edge2_bwd1": ("bwd1_kernel", 2, 20, 1, 1),
+            "edge2_wgrad5": ("wgrad_kernel<5>", 2, 4, 1, 2),
+            "edge2_wgrad2": ("wgrad_kernel<2>", 1, 12, 1, 1),
+            "edge2_sums": ("edge_sums_kernel", 2, 8, 0, 0),
+        }
+        kernels = {}
+        for tag, (kname, streams, extra, gemms, tanhs) in KSPEC.items():
+            ev = prof.get(tag, []) if prof else []
+            if not ev:
+                continue
             tot = sum(s.elapsed_time(e) for s, e in ev)
             per = tot / len(ev)
-            roof["achieved"] = 2.0 * E * 256 * 256 / (per * 1e-3) / 1e12
-            roof["frac"] = roof["achieved"] / tf
-            roof["ms_per_launch"] = per
-            roof["launches_timed"] = len(ev)
-            roof["share_of_step"] = tot / ms
+            nbytes = (512.0 * streams + extra) * E
+            kernels[tag] = {"kernel": kname, "ms_per_launch": per, "launches_timed": len(ev), "share_of_step": tot / ms,
+                            "algorithmic_gb": nbytes / 1e9, "hbm_gbs": nbytes / (per * 1e-3) / 1e9,
+                            "hbm_frac": nbytes / (per * 1e-3) / 1e9 / hbm,
+                            "tensor_tflops": gemms * 2.0 * E * 256 * 256 / (per * 1e-3) / 1e12,
+                            "tensor_frac": gemms * 2.0 * E * 256 * 256 / (per * 1e-3) / 1e12 / tf,
+                            "mufu_frac": tanhs * 256.0 * E / (per * 1e-3) / (148 * 16 * 1.965e9)}
+        dom = max(kernels, key=lambda t: kernels[t]["share_of_step"]) if kernels else None
+        roof = {"bound": "hbm", "kernel": None, "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": which, "kernels": kernels}
+        if dom:
+            k = kernels[dom]
+            roof.update({"kernel": f"{k['kernel']} ({dom})", "achieved": k["hbm_gbs"], "frac": k["hbm_frac"],
+                         "ms_per_launch": k["ms_per_launch"], "launches_timed": k["launches_timed"],
+                         "share_of_step": k["share_of_step"], "tensor_frac": k["tensor_frac"],
+                         "traffic": NCU_TRAFFIC_PER_EDGE.get(dom, 0.0) * E or None,
+                         "traffic_source": "profiles/r01_edge2_kernels_ncu.md"})
         cpu = None
         if not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
@@ -294,6 +318,10 @@ def run_gpu(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per edge of each v2 edge kernel (ncu --set full, profiles/)
+NCU_TRAFFIC_PER_EDGE = {}
 
 
 def lib_edges(L, W=40):

@@ -183,6 +183,16 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh /*fp16 [
                    const float* d2, const int32_t* row, const int32_t* col, const float* wd,
                    int64_t num_edges, void* ghu /*bf16 [E,256]*/, float* gd2 /*[E]*/, void* stream);
 
+/* Segment sums of ghu over CSR rows / CSC columns (gA | gB = dL/dABh, fp32 [N,512]) and
+ * gwdh[256] = sum_e d2[e] ghu[e] (zeroed inside; dL/dwd = gwdh / 2): one warp per node, deterministic order. */
+int pev_edge2_sums(const void* ghu /*bf16 [E,256]*/, const float* d2, const int32_t* row_ptr,
+                   const int32_t* col_ptr, const int32_t* csc_perm, int64_t num_nodes, int64_t num_edges,
+                   float* gAB /*[N,512]*/, float* gwdh /*[256]*/, void* stream);
+/* gx[i] += sum over the edges at node i of +-2 gd2[e] (x_row - x_col): the coordinate part of
+ * pev_edge_prologue_bwd on its own (d d2 / d x). */
+int pev_edge_coord_bwd_accum(const float* gd2, const float* x, const int32_t* row_ptr, const int32_t* row,
+                             const int32_t* col, const int32_t* col_ptr, const int32_t* csc_perm,
+                             int64_t num_nodes, int64_t num_edges, float* gx_accum, void* stream);
 /* Weight gradients of the two 256x256 edge linears as split-K tcgen05 GEMMs over the edge dimension; both
  * operands are rebuilt on the fly (nothing but hs / hvT / ghvT is read from HBM).  `workspace` holds one
  * 256x256 fp32 partial per CTA (pev_edge2_wgrad_workspace_bytes()); the partials are summed in a fixed order.

@@ -71,6 +71,8 @@ _PROTOS_TC = {
     "pev_add_layernorm_fwd": (c_int32, [_P, _P, _P, _P, c_float, _L, _I, _P, _P, _P, _P, _P]),
     "pev_layernorm_bwd": (c_int32, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "pev_column_sum": (c_int32, [_P, _L, _I, _P, _P]),
+    "pev_edge2_sums": (c_int32, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
+    "pev_edge_coord_bwd_accum": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pev_edge2_wgrad_workspace_bytes": (c_int64, []),
     "pev_edge2_wgrad5": (c_int32, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
     "pev_edge2_wgrad2": (c_int32, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),

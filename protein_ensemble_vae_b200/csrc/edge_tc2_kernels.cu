@@ -33,7 +33,7 @@ constexpr int TILE_M = 128;             // edges per tile
 constexpr int KCHUNK = 64;              // bf16 per 128-byte swizzle row
 constexpr int NUM_KCHUNKS = H / KCHUNK;
 constexpr int UMMA_K = 16;
-constexpr int NUM_STAGES = 4;           // operand ring: 4 x 16 KB = one tile in flight
+constexpr int MAX_STAGES = 4;           // operand ring: up to 4 x 16 KB K-chunks in flight
 constexpr int STAGE_BYTES = TILE_M * KCHUNK * 2;
 constexpr int W_BYTES = H * H * 2;
 constexpr int TILE_IMG_BYTES = TILE_M * H * 2;   // 64 KB tile image
@@ -52,14 +52,21 @@ constexpr int REGS_PROD = 64;
 constexpr int REGS_EPI = 104;
 constexpr int TMEM_COLS = 512;
 
-struct Smem {
+// Dynamic shared memory: resident weight image | operand ring | 4 x 256 floats | per-warp staging | barriers.
+template <int STAGES, int VEC_FLOATS, int STG_BYTES>
+struct SmemL {
+  static constexpr int NSTAGE = STAGES;
   static constexpr int W_OFF = 0;
   static constexpr int A_OFF = W_BYTES;
-  static constexpr int VEC_OFF = A_OFF + NUM_STAGES * STAGE_BYTES;      // 4 x 256 floats
-  static constexpr int BAR_OFF = VEC_OFF + 4 * H * 4;
+  static constexpr int VEC_OFF = A_OFF + STAGES * STAGE_BYTES;          // per-feature vectors (bias, wd, w6)
+  static constexpr int STG_OFF = VEC_OFF + VEC_FLOATS * 4;              // per-warp staging of tile-image stores
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256;
+  static constexpr int BYTES = TOTAL + 1024;                            // slack for manual 1024-byte alignment
+  static_assert(BYTES <= 232448, "shared memory budget");
 };
-constexpr int SMEM_BYTES = Smem::TOTAL + 1024;
+using SmemT = SmemL<2, 256, 8 * 8192>;   // feature-lane epilogues (fwd1, bwd2): 2-stage ring + 8 x 2 x 4 KB image staging
+using SmemN = SmemL<4, 1024, 0>;         // edge-lane epilogues (fwd2, bwd1): 4-stage ring
 
 struct Bars {
   uint64_t* full;     // [NUM_STAGES] producers -> MMA
@@ -69,13 +76,13 @@ struct Bars {
   uint64_t* w;        // weight image landed
   uint32_t* tmem_slot;
 };
-__device__ __forceinline__ Bars make_bars(uint8_t* smem) {
-  uint64_t* b = reinterpret_cast<uint64_t*>(smem + Smem::BAR_OFF);
-  return Bars{b, b + NUM_STAGES, b + 2 * NUM_STAGES, b + 2 * NUM_STAGES + 2, b + 2 * NUM_STAGES + 4,
-              reinterpret_cast<uint32_t*>(b + 2 * NUM_STAGES + 5)};
+__device__ __forceinline__ Bars make_bars(uint8_t* bar_base) {
+  uint64_t* b = reinterpret_cast<uint64_t*>(bar_base);
+  return Bars{b, b + MAX_STAGES, b + 2 * MAX_STAGES, b + 2 * MAX_STAGES + 2, b + 2 * MAX_STAGES + 4,
+              reinterpret_cast<uint32_t*>(b + 2 * MAX_STAGES + 5)};
 }
 __device__ __forceinline__ void init_bars(const Bars& B, int full_count) {
-  for (int s = 0; s < NUM_STAGES; ++s) {
+  for (int s = 0; s < MAX_STAGES; ++s) {
     mbar_init(&B.full[s], full_count);
     mbar_init(&B.empty[s], 1);
   }
@@ -144,13 +151,14 @@ __device__ __forceinline__ void st_256(void* addr, const uint4 a, const uint4 b)
 }
 
 // Common prologue: barriers, TMEM, role register budgets.  Returns the TMEM base address.
-#define PEV_TC2_PROLOGUE(FULL_COUNT)                                                          \
+#define PEV_TC2_PROLOGUE(SM, FULL_COUNT)                                                      \
+  constexpr int NUM_STAGES = SM::NSTAGE;                                                      \
   extern __shared__ __align__(1024) uint8_t smem_raw[];                                       \
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);                \
-  uint8_t* sW = smem + Smem::W_OFF;                                                           \
-  uint8_t* sA = smem + Smem::A_OFF;                                                           \
-  float* sVec = reinterpret_cast<float*>(smem + Smem::VEC_OFF);                               \
-  const Bars B = make_bars(smem);                                                             \
+  uint8_t* sW = smem + SM::W_OFF;                                                             \
+  uint8_t* sA = smem + SM::A_OFF;                                                             \
+  float* sVec = reinterpret_cast<float*>(smem + SM::VEC_OFF);                                 \
+  const Bars B = make_bars(smem + SM::BAR_OFF);                                               \
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                 \
   if (threadIdx.x == 0) init_bars(B, FULL_COUNT);                                             \
   if (warp == MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
@@ -188,7 +196,7 @@ struct Fwd1Params {
 template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(NUM_PROD_THREADS)
+  PEV_TC2_PROLOGUE(SmemT, NUM_PROD_THREADS)
   float* sWd = sVec;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) sWd[k] = 0.5f * p.wd[k];
   PEV_TC2_SYNC_ROLES()
@@ -310,9 +318,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
     const float bias = 0.5f * __ldg(p.b2 + f);
     float* aggcol = p.agg + f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 128);
-    // tile-image offset of this thread's 128-byte row (feature f), edge half 0
-    const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
+    // tile-image offset of this warp's 32 rows (features f - lane .. + 31), edge half 0: 4 KB contiguous
+    const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
     const int sw = f & 7;
+    uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;      // two 4 KB buffers, one per edge half
     auto flush = [&](int r, float s) {
       if (r >= 0 && !(dbg & 4)) atomicAdd(aggcol + (int64_t)r * H, s);
     };
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
         const int64_t e = e0 + cb * 32 + lane;
         myrow[cb] = e < p.E ? __ldg(p.row + e) : -1;
       }
-      uint8_t* img = p.hvT + (int64_t)tile * TILE_IMG_BYTES + img_row;
+      uint8_t* img = p.hvT + (int64_t)tile * TILE_IMG_BYTES + img_blk;
       mbar_wait(&B.tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       if (dbg & 128) {                                 // role ablation: accumulator handshake only
@@ -349,17 +358,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);            // accumulator stage fully read
         }
-        // hv -> HBM tile image (bf16): this thread's 32 edges are 4 chunks (two 32-byte sectors) of its 128-byte row
+        // hv -> HBM tile image (bf16).  This warp's 32 feature rows x 64 edges are 4 KB contiguous in the image: the
+        // rows are staged in shared memory (swizzled chunk positions: conflict-free) and written by one TMA bulk copy
+        // per edge half -- full lines, no per-lane global stores.
         if (!(dbg & 2)) {
-          uint8_t* dst = img + (cb >> 1) * 8192;
+          uint8_t* sbuf = stg + (cb >> 1) * 4096;
+          if ((cb & 1) == 0) {
+            if (lane == 0) bulk_wait_read_1();        // the bulk copy that last used this buffer has read it
+            __syncwarp();
+          }
 #pragma unroll
-          for (int pr = 0; pr < 2; ++pr) {
-            const int c = (cb & 1) * 4 + 2 * pr;      // logical chunk of the pair's first half
-            const float lo8[8] = {val[16 * pr], val[16 * pr + 1], val[16 * pr + 2], val[16 * pr + 3],
-                                  val[16 * pr + 4], val[16 * pr + 5], val[16 * pr + 6], val[16 * pr + 7]};
-            const float hi8[8] = {val[16 * pr + 8], val[16 * pr + 9], val[16 * pr + 10], val[16 * pr + 11],
-                                  val[16 * pr + 12], val[16 * pr + 13], val[16 * pr + 14], val[16 * pr + 15]};
-            st_pair_256(dst + (((c ^ sw) & 6) << 4), pack8(lo8), pack8(hi8), (uint32_t)(sw & 1));
+          for (int k = 0; k < 4; ++k) {
+            const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
+                                 val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
+            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((((cb & 1) * 4 + k) ^ sw) << 4)) = pack8(o8);
+          }
+          if (cb & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) bulk_s2g(img + (cb >> 1) * 8192, sbuf, 4096);
           }
         }
         float m[32];
@@ -386,6 +403,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
       }
       flush(cur, seg);
     }
+    if (lane == 0) bulk_wait_all();
   }
   PEV_TC2_EPILOGUE()
 }
@@ -407,7 +425,7 @@ struct Fwd2Params {
 template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(NUM_PROD_THREADS)
+  PEV_TC2_PROLOGUE(SmemN, NUM_PROD_THREADS)
   float* sBias = sVec;
   float* sW6 = sVec + H;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
@@ -561,6 +579,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
   PEV_TC2_EPILOGUE()
 }
 
+__device__ __forceinline__ uint4 sel4(uint32_t c, const uint4 a, const uint4 b) {   // c ? a : b
+  return make_uint4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
 // 32-byte global load of two 16-byte chunks stored in the order (lo, hi) or swapped (see st_pair_256)
 __device__ __forceinline__ void ld_pair_256(const void* addr, uint32_t swap, uint4& a, uint4& b) {
   asm volatile(
@@ -597,7 +618,7 @@ struct Bwd2Params {
 template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(NUM_PROD_THREADS)
+  PEV_TC2_PROLOGUE(SmemT, NUM_PROD_THREADS)
   float* sW6 = sVec;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) sW6[k] = p.w6[k];
   PEV_TC2_SYNC_ROLES()
@@ -719,7 +740,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     };
     // The CTA's tiles are walked as a flat sequence of 32-edge batches (4 per tile), each in two steps of 16 edges
     // (one 32-byte pair of the thread's image row, 16 TMEM columns).  Row ids are fetched two batches ahead, the
-    // gagg values of a batch's first / last row one batch ahead, hv one step ahead.
+    // gagg values of a batch's first / last row one batch ahead, hv one batch (two steps) ahead.
     const int nb = 4 * ((p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
     auto tile_of = [&](int bi) { return (int)blockIdx.x + (bi >> 2) * (int)gridDim.x; };
     auto batch_row = [&](int bi) -> int {
@@ -734,8 +755,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     int row_c = batch_row(0), row_n = nb > 1 ? batch_row(1) : -1;
     float gaF, gaL, gaFn = 0.f, gaLn = 0.f;
     batch_ga(row_c, gaF, gaL);
-    uint4 hvn[2];                                  // hv of the next step (lo, hi chunk)
-    ld_pair_256(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES + pair_off(0, 0), swap, hvn[0], hvn[1]);
+    uint4 hvq[2][2];                               // hv pair `pr` of the batch in flight: loaded one batch ahead
+    ld_256(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES + pair_off(0, 0), hvq[0][0], hvq[0][1]);
+    ld_256(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES + pair_off(0, 1), hvq[1][0], hvq[1][1]);
+    uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;       // staging of this warp's 32 rows x 64 edges: 2 x 4 KB
+    const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
 #pragma unroll 1
     for (int bi = 0; bi < nb; ++bi) {
       const int cb = bi & 3, it = bi >> 2, acc = it & 1;
@@ -751,10 +775,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);
         }
+        row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
         continue;
       }
-      const uint8_t* src = p.hvT + (int64_t)tile * TILE_IMG_BYTES;
-      uint8_t* dst = p.ghvT + (int64_t)tile * TILE_IMG_BYTES;
       // segments of the 32-edge batch (uniform control flow: every lane sees the same edges)
       const int prev = __shfl_up_sync(0xffffffffu, row_c, 1);
       const uint32_t bm = __ballot_sync(0xffffffffu, lane != 0 && row_c != prev);
@@ -762,6 +785,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       const uint32_t low = bm - 1u;                // one boundary: edges before it
       float ga_run = gaF;                          // several boundaries: running value / row
       int r_run = __shfl_sync(0xffffffffu, row_c, 0);
+      uint8_t* stg_row = stg + (cb >> 1) * 4096 + lane * 128;
+      if (!(dbg & 2) && (cb & 1) == 0) {
+        if (lane == 0) bulk_wait_read_1();         // the bulk copy that last used this buffer has read it
+        __syncwarp();
+      }
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr) {
         uint32_t raw[16];
@@ -769,17 +797,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         // r(hv) of the 16 edges while the TMEM load is in flight
         float r[16];
         {
+          // the two 16-byte chunks of the pair sit in swizzled order: pick them at use time (selecting right
+          // after the load would expose its latency)
           float h8[8];
-          unpack8(hvn[0], h8);
+          unpack8(sel4(swap, hvq[pr][1], hvq[pr][0]), h8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = silu_grad_r(h8[j]);
-          unpack8(hvn[1], h8);
+          unpack8(sel4(swap, hvq[pr][0], hvq[pr][1]), h8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[8 + j] = silu_grad_r(h8[j]);
         }
-        if (pr == 0) ld_pair_256(src + pair_off(cb, 1), swap, hvn[0], hvn[1]);
-        else if (bi + 1 < nb)
-          ld_pair_256(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES + pair_off((bi + 1) & 3, 0), swap, hvn[0], hvn[1]);
+        if (bi + 1 < nb)                            // the same pair of the next batch (two 16-edge steps ahead)
+          ld_256(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES + pair_off((bi + 1) & 3, pr), hvq[pr][0], hvq[pr][1]);
         tmem_wait();
         if (cb == 3 && pr == 1) {
           tc_fence_before();
@@ -807,14 +836,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         for (int j = 0; j < 16; ++j) gv[j] = fmaf(gv[j], r[j], gv[j]);
         dbacc += ((gv[0] + gv[1]) + (gv[2] + gv[3])) + ((gv[4] + gv[5]) + (gv[6] + gv[7])) +
                  (((gv[8] + gv[9]) + (gv[10] + gv[11])) + ((gv[12] + gv[13]) + (gv[14] + gv[15])));
-        if (!(dbg & 2)) {
+        if (!(dbg & 2)) {                           // ghv -> staging (swizzled chunk positions of the image row)
           const float lo8[8] = {gv[0], gv[1], gv[2], gv[3], gv[4], gv[5], gv[6], gv[7]};
           const float hi8[8] = {gv[8], gv[9], gv[10], gv[11], gv[12], gv[13], gv[14], gv[15]};
-          st_pair_256(dst + pair_off(cb, pr), pack8(lo8), pack8(hi8), swap);
+          const int c = (cb & 1) * 4 + 2 * pr;
+          *reinterpret_cast<uint4*>(stg_row + ((c ^ sw) << 4)) = pack8(lo8);
+          *reinterpret_cast<uint4*>(stg_row + (((c + 1) ^ sw) << 4)) = pack8(hi8);
         }
+      }
+      if (!(dbg & 2) && (cb & 1)) {                 // 32 rows x 64 edges complete: one 4 KB TMA bulk store
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0)
+          bulk_s2g(p.ghvT + (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192, stg + (cb >> 1) * 4096, 4096);
       }
       row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
     }
+    if (lane == 0) bulk_wait_all();
     atomicAdd(p.db2h + f, dbacc);
   }
   PEV_TC2_EPILOGUE()
@@ -850,10 +888,11 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
   const int dbg = DBG ? p.dbg : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem + Smem::W_OFF;
-  uint8_t* sA = smem + Smem::A_OFF;
-  float* sWd = reinterpret_cast<float*>(smem + Smem::VEC_OFF);
-  const Bars B = make_bars(smem);
+  constexpr int NUM_STAGES = SmemN::NSTAGE;
+  uint8_t* sW = smem + SmemN::W_OFF;
+  uint8_t* sA = smem + SmemN::A_OFF;
+  float* sWd = reinterpret_cast<float*>(smem + SmemN::VEC_OFF);
+  const Bars B = make_bars(smem + SmemN::BAR_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < H; k += B1_THREADS) sWd[k] = 0.5f * p.wd[k];
   if (threadIdx.x == 0) {
@@ -1348,6 +1387,92 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int G, fl
   out[i] = scale * ((s0 + s1) + (s2 + s3));
 }
 
+// =================================================================================================== sums
+// Segment sums of ghu = dL/dhu (bf16 [E,256]) over CSR rows and CSC columns, one WARP per node: a lane owns 8
+// features (one 16-byte chunk of the 512-byte edge row, so every load is a fully coalesced row), fp32 accumulation
+// in ascending edge order (deterministic), 4 edge rows in flight.  gA[i] = sum_{row e = i} ghu[e], gB[j] = sum_{col e = j}
+// ghu[e]; the (wd/2)-gradient sum_e d2[e] ghu[e] stays in registers across the nodes a warp visits (one atomic per
+// feature per warp at the end).  HBM-bound: ghu is read twice (1024 B per edge), gAB written once.
+__global__ void __launch_bounds__(256)
+edge_sums_kernel(const uint4* __restrict__ ghu, const float* __restrict__ d2, const int32_t* __restrict__ row_ptr,
+                 const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ csc_perm, int64_t N,
+                 float* __restrict__ gAB, float* __restrict__ gwdh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float wacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wacc[j] = 0.f;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+    {
+      const int64_t e0 = row_ptr[i], e1 = row_ptr[i + 1];
+      int64_t e = e0;
+      for (; e + 4 <= e1; e += 4) {
+        uint4 v[4];
+        float dd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = __ldg(ghu + (e + u) * 32 + lane);
+          dd[u] = __ldg(d2 + e + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float g8[8];
+          unpack8(v[u], g8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a[j] += g8[j];
+            wacc[j] = fmaf(g8[j], dd[u], wacc[j]);
+          }
+        }
+      }
+      for (; e < e1; ++e) {
+        float g8[8];
+        unpack8(__ldg(ghu + e * 32 + lane), g8);
+        const float dd = __ldg(d2 + e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] += g8[j];
+          wacc[j] = fmaf(g8[j], dd, wacc[j]);
+        }
+      }
+    }
+    {
+      const int64_t q0 = col_ptr[i], q1 = col_ptr[i + 1];
+      int64_t q = q0;
+      for (; q + 4 <= q1; q += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(ghu + (int64_t)__ldg(csc_perm + q + u) * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float g8[8];
+          unpack8(v[u], g8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] += g8[j];
+        }
+      }
+      for (; q < q1; ++q) {
+        float g8[8];
+        unpack8(__ldg(ghu + (int64_t)__ldg(csc_perm + q) * 32 + lane), g8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] += g8[j];
+      }
+    }
+    float4* oa = reinterpret_cast<float4*>(gAB + i * 2 * H + lane * 8);
+    float4* ob = reinterpret_cast<float4*>(gAB + i * 2 * H + H + lane * 8);
+    oa[0] = make_float4(a[0], a[1], a[2], a[3]);
+    oa[1] = make_float4(a[4], a[5], a[6], a[7]);
+    ob[0] = make_float4(b[0], b[1], b[2], b[3]);
+    ob[1] = make_float4(b[4], b[5], b[6], b[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(gwdh + lane * 8 + j, wacc[j]);
+}
+
 // d2[e] = |x[row[e]] - x[col[e]]|^2  (models/en_gnn_decoder.py:61-62), one thread per edge
 __global__ void edge_d2_kernel(const float* __restrict__ x, const int32_t* __restrict__ row,
                                const int32_t* __restrict__ col, int64_t E, float* __restrict__ d2) {
@@ -1371,8 +1496,8 @@ __global__ void pack_weight_scaled_kernel(const float* __restrict__ W, int trans
 }
 
 template <typename K>
-static int configure(K kernel, const char* name) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+static int configure(K kernel, const char* name, int smem_bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return set_error(2, "%s: %s", name, cudaGetErrorString(e));
   return 0;
 }
@@ -1441,8 +1566,8 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   PEV_REQUIRE(row && col && hvT && d2, "edge arrays missing");
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd1_kernel<0>, "fwd1_kernel")) return rc;
-    if (int rc = tc2::configure(tc2::fwd1_kernel<1>, "fwd1_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<0>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<1>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
     configured = true;
   }
   tc2::Fwd1Params p = {};
@@ -1450,8 +1575,8 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   p.hvT = reinterpret_cast<uint8_t*>(hvT); p.agg = agg; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::fwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
-  else tc2::fwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  if (p.dbg) tc2::fwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+  else tc2::fwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
   return after_launch("edge2_fwd1_kernel");
 }
 
@@ -1464,8 +1589,8 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd2_kernel<0>, "fwd2_kernel")) return rc;
-    if (int rc = tc2::configure(tc2::fwd2_kernel<1>, "fwd2_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<0>, "fwd2_kernel", tc2::SmemN::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<1>, "fwd2_kernel", tc2::SmemN::BYTES)) return rc;
     configured = true;
   }
   tc2::Fwd2Params p = {};
@@ -1473,8 +1598,8 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   p.hs = reinterpret_cast<bf16_t*>(hs_out); p.w = w_out; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
-  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemN::BYTES, st>>>(p);
+  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemN::BYTES, st>>>(p);
   return after_launch("edge2_fwd2_kernel");
 }
 
@@ -1487,8 +1612,8 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   PEV_REQUIRE(hs && gw && gagg && row && hvT && ghvT, "edge arrays missing");
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::bwd2_kernel<0>, "bwd2_kernel")) return rc;
-    if (int rc = tc2::configure(tc2::bwd2_kernel<1>, "bwd2_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::bwd2_kernel<0>, "bwd2_kernel", tc2::SmemT::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::bwd2_kernel<1>, "bwd2_kernel", tc2::SmemT::BYTES)) return rc;
     configured = true;
   }
   tc2::Bwd2Params p = {};
@@ -1497,8 +1622,8 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::bwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
-  else tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  if (p.dbg) tc2::bwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+  else tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
   return after_launch("edge2_bwd2_kernel");
 }
 
@@ -1511,8 +1636,8 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::bwd1_kernel<0>, "bwd1_kernel")) return rc;
-    if (int rc = tc2::configure(tc2::bwd1_kernel<1>, "bwd1_kernel")) return rc;
+    if (int rc = tc2::configure(tc2::bwd1_kernel<0>, "bwd1_kernel", tc2::SmemN::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::bwd1_kernel<1>, "bwd1_kernel", tc2::SmemN::BYTES)) return rc;
     configured = true;
   }
   tc2::Bwd1Params p = {};
@@ -1521,9 +1646,24 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SMEM_BYTES, st>>>(p);
-  else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SMEM_BYTES, st>>>(p);
+  if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemN::BYTES, st>>>(p);
+  else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemN::BYTES, st>>>(p);
   return after_launch("edge2_bwd1_kernel");
+}
+
+int pev_edge2_sums(const void* ghu, const float* d2, const int32_t* row_ptr, const int32_t* col_ptr,
+                   const int32_t* csc_perm, int64_t num_nodes, int64_t num_edges, float* gAB, float* gwdh, void* stream) {
+  PEV_REQUIRE(row_ptr && col_ptr && gAB && gwdh && num_nodes >= 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(gwdh, 0, sizeof(float) * tc2::H, st);
+  if (num_nodes == 0) return 0;
+  PEV_REQUIRE(num_edges == 0 || (ghu && d2 && csc_perm), "edge arrays missing");
+  int64_t grid = (num_nodes + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  tc2::edge_sums_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(ghu), d2, row_ptr, col_ptr,
+                                                        csc_perm, num_nodes, gAB, gwdh);
+  return after_launch("edge2_sums_kernel");
 }
 
 int64_t pev_edge2_wgrad_workspace_bytes(void) { return (int64_t)sm_count() * tc2::H * tc2::H * (int64_t)sizeof(float); }

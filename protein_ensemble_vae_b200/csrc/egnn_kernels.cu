@@ -237,6 +237,17 @@ int pev_edge_prologue_bwd_bf16(const void* gu, const float* gd2, const float* x,
   return after_launch("edge_prologue_bwd_coord_accum_kernel");
 }
 
+int pev_edge_coord_bwd_accum(const float* gd2, const float* x, const int32_t* row_ptr, const int32_t* row,
+                             const int32_t* col, const int32_t* col_ptr, const int32_t* csc_perm, int64_t N, int64_t E,
+                             float* gx_accum, void* stream) {
+  PEV_REQUIRE(x && row_ptr && col_ptr && gx_accum && N >= 0, "bad argument");
+  if (N == 0 || E == 0) return 0;
+  PEV_REQUIRE(gd2 && row && col && csc_perm, "edge arrays missing");
+  edge_prologue_bwd_coord_accum_kernel<<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(
+      gd2, x, row_ptr, row, col, col_ptr, csc_perm, N, gx_accum);
+  return after_launch("edge_prologue_bwd_coord_accum_kernel");
+}
+
 int pev_scatter_coord_fwd(const float* m, const float* w, const float* x, const float* dinv,
                           const int32_t* row_ptr, const int32_t* col, int64_t N, int32_t H, float* agg,
                           float* x_out, void* stream) {

@@ -176,11 +176,13 @@ class FusedEdgeV2(torch.autograd.Function):
                        ptr(gW2), st)
             del ghvT
             gAB = torch.empty(N, 2 * H, dtype=f32, device=dev)
-            part = torch.empty(N, H, dtype=f32, device=dev)
-            with _lib.profiled("edge_prologue_bwd"):
-                L.call("pev_edge_prologue_bwd_bf16", ptr(ghu), ptr(gd2), ptr(x), ptr(g.row_ptr), ptr(g.row), ptr(g.col),
-                       ptr(g.col_ptr), ptr(g.csc_perm), N, E, ptr(gAB), ptr(gx), ptr(part), st)
-            gwd = 0.5 * part.sum(0)                     # hu = ... + (wd/2) d2
+            gwdh = torch.empty(H, dtype=f32, device=dev)
+            with _lib.profiled("edge2_sums"):
+                L.call("pev_edge2_sums", ptr(ghu), ptr(d2), ptr(g.row_ptr), ptr(g.col_ptr), ptr(g.csc_perm), N, E,
+                       ptr(gAB), ptr(gwdh), st)
+            L.call("pev_edge_coord_bwd_accum", ptr(gd2), ptr(x), ptr(g.row_ptr), ptr(g.row), ptr(g.col), ptr(g.col_ptr),
+                   ptr(g.csc_perm), N, E, ptr(gx), st)
+            gwd = 0.5 * gwdh                            # hu = ... + (wd/2) d2
             gb6 = gw[:E].sum().reshape(1)
         return (gAB, gx, gwd, gW2, 0.5 * db2h, gW5, 0.5 * db5h, gw6.reshape(1, H), gb6, None, None, None, None)
 
