@@ -15,10 +15,12 @@
 //   fwd1  hu = Ah_i + Bh_j + wdh d2 ; a = silu  --GEMM W2h (transposed)-->  hv (+b2h) -> HBM tile image,
 //         m = silu ; agg[row] += m (in-thread segment sums, one RED per segment per feature)
 //   fwd2  m = silu(hv)  --GEMM W5h (A operand MN-major)-->  hs (+b5h) [-> HBM, training], t = silu, w[e] = t.w6 + b6
+#include <cuda.h>          // CUtensorMap types only: the encoder is resolved at run time (no libcuda link dependency)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/pev_b200.h"
 #include "pev_common.cuh"
@@ -66,7 +68,8 @@ struct SmemL {
   static_assert(BYTES <= 232448, "shared memory budget");
 };
 using SmemT = SmemL<2, 256, 8 * 8192>;   // feature-lane epilogues (fwd1, bwd2): 2-stage ring + 8 x 2 x 4 KB image staging
-using SmemN = SmemL<4, 1024, 0>;         // edge-lane epilogues (fwd2, bwd1): 4-stage ring
+using SmemB1 = SmemL<2, 256, 16 * 4096>;  // bwd1: 2-stage ring (TMA-fed) + 16 x 2 x 2 KB row-box staging for the store of ghu
+using SmemF2 = SmemL<3, 512, 8 * 4096>;  // fwd2: 3-stage ring + 8 x 2 x 2 KB row-box staging for the TMA tensor store of hs
 
 struct Bars {
   uint64_t* full;     // [NUM_STAGES] producers -> MMA
@@ -423,9 +426,9 @@ struct Fwd2Params {
 };
 
 template <int DBG>
-__global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p, const __grid_constant__ CUtensorMap hs_map) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(SmemN, NUM_PROD_THREADS)
+  PEV_TC2_PROLOGUE(SmemF2, NUM_PROD_THREADS)
   float* sBias = sVec;
   float* sW6 = sVec + H;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
     const float b6 = half == 0 ? __ldg(p.b6) : 0.f;
+    uint8_t* stg = smem + SmemF2::STG_OFF + warp * 4096;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -553,16 +557,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);
         }
-        if (p.hs && valid && !(dbg & 2)) {
-          uint8_t* dst = reinterpret_cast<uint8_t*>(p.hs + e * H + col0);
+        if (p.hs && !(dbg & 2)) {
+          // hs rows -> HBM through a TMA tensor store: the warp's [32 edges x 32 features] box is staged in shared
+          // memory (64-byte rows, SWIZZLE_64B chunk positions: conflict-free) and written by the TMA engine, which
+          // also clips the rows past E.  Two boxes per warp alternate, so nothing waits on a store just issued.
+          uint8_t* sbuf = stg + (cb & 1) * 2048;
+          if (lane == 0) bulk_wait_read_1();
+          __syncwarp();
 #pragma unroll
-          for (int pr = 0; pr < 2; ++pr) {
-            const float lo8[8] = {val[16 * pr], val[16 * pr + 1], val[16 * pr + 2], val[16 * pr + 3],
-                                  val[16 * pr + 4], val[16 * pr + 5], val[16 * pr + 6], val[16 * pr + 7]};
-            const float hi8[8] = {val[16 * pr + 8], val[16 * pr + 9], val[16 * pr + 10], val[16 * pr + 11],
-                                  val[16 * pr + 12], val[16 * pr + 13], val[16 * pr + 14], val[16 * pr + 15]};
-            st_256(dst + 32 * pr, pack8(lo8), pack8(hi8));
+          for (int k = 0; k < 4; ++k) {
+            const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
+                                 val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
+            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = pack8(o8);
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&hs_map, col0, (int)((int64_t)tile * TILE_M + q * 32), sbuf);
         }
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -575,6 +585,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
       }
       if (valid) atomicAdd(p.w + e, dot + b6);
     }
+    if (lane == 0) bulk_wait_all();
   }
   PEV_TC2_EPILOGUE()
 }
@@ -884,15 +895,15 @@ struct Bwd1Params {
 };
 
 template <int DBG>
-__global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p) {
+__global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p, const __grid_constant__ CUtensorMap ghu_map) {
   const int dbg = DBG ? p.dbg : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int NUM_STAGES = SmemN::NSTAGE;
-  uint8_t* sW = smem + SmemN::W_OFF;
-  uint8_t* sA = smem + SmemN::A_OFF;
-  float* sWd = reinterpret_cast<float*>(smem + SmemN::VEC_OFF);
-  const Bars B = make_bars(smem + SmemN::BAR_OFF);
+  constexpr int NUM_STAGES = SmemB1::NSTAGE;
+  uint8_t* sW = smem + SmemB1::W_OFF;
+  uint8_t* sA = smem + SmemB1::A_OFF;
+  float* sWd = reinterpret_cast<float*>(smem + SmemB1::VEC_OFF);
+  const Bars B = make_bars(smem + SmemB1::BAR_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < H; k += B1_THREADS) sWd[k] = 0.5f * p.wd[k];
   if (threadIdx.x == 0) {
@@ -971,6 +982,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
     int nr, nc, nrn = 0, ncn = 0;
     float dd, ddn = 0.f;
     load_meta(blockIdx.x, nr, nc, dd);
+    uint8_t* stg = smem + SmemB1::STG_OFF + warp * 4096;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -1040,21 +1052,25 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p)
           dot = fmaf(gu[4 * k + 2], w.z, dot);
           dot = fmaf(gu[4 * k + 3], w.w, dot);
         }
-        if (valid && !(dbg & 2)) {
-          uint8_t* dst = reinterpret_cast<uint8_t*>(p.ghu + e * H + col0);
+        if (!(dbg & 2)) {                         // ghu rows -> HBM: staged [32 x 32] box + TMA tensor store (see fwd2)
+          uint8_t* sbuf = stg + b * 2048;
+          if (lane == 0) bulk_wait_read_1();
+          __syncwarp();
 #pragma unroll
-          for (int pr = 0; pr < 2; ++pr) {
-            const float lo8[8] = {gu[16 * pr], gu[16 * pr + 1], gu[16 * pr + 2], gu[16 * pr + 3],
-                                  gu[16 * pr + 4], gu[16 * pr + 5], gu[16 * pr + 6], gu[16 * pr + 7]};
-            const float hi8[8] = {gu[16 * pr + 8], gu[16 * pr + 9], gu[16 * pr + 10], gu[16 * pr + 11],
-                                  gu[16 * pr + 12], gu[16 * pr + 13], gu[16 * pr + 14], gu[16 * pr + 15]};
-            st_256(dst + 32 * pr, pack8(lo8), pack8(hi8));
+          for (int k = 0; k < 4; ++k) {
+            const float o8[8] = {gu[8 * k], gu[8 * k + 1], gu[8 * k + 2], gu[8 * k + 3],
+                                 gu[8 * k + 4], gu[8 * k + 5], gu[8 * k + 6], gu[8 * k + 7]};
+            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = pack8(o8);
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&ghu_map, col0, (int)((int64_t)tile * TILE_M + q * 32), sbuf);
         }
       }
       if (valid) atomicAdd(p.gd2 + e, dot);
       nr = nrn; nc = ncn; dd = ddn;
     }
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -1495,6 +1511,30 @@ __global__ void pack_weight_scaled_kernel(const float* __restrict__ W, int trans
   out[byte >> 1] = __float2bfloat16(v);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library must load without libcuda.so)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// tensor map of a bf16 [rows, 256] row-major matrix with a [32 rows x 32 columns] box (64-byte inner extent, SWIZZLE_64B)
+static int make_rows_map(void* base, int64_t rows, CUtensorMap* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+      return set_error(2, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)H * 2};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(2, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 template <typename K>
 static int configure(K kernel, const char* name, int smem_bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -1589,8 +1629,8 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd2_kernel<0>, "fwd2_kernel", tc2::SmemN::BYTES)) return rc;
-    if (int rc = tc2::configure(tc2::fwd2_kernel<1>, "fwd2_kernel", tc2::SmemN::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<0>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<1>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
     configured = true;
   }
   tc2::Fwd2Params p = {};
@@ -1598,8 +1638,12 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   p.hs = reinterpret_cast<bf16_t*>(hs_out); p.w = w_out; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemN::BYTES, st>>>(p);
-  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemN::BYTES, st>>>(p);
+  alignas(64) CUtensorMap hs_map;
+  memset(&hs_map, 0, sizeof(hs_map));
+  if (hs_out)
+    if (int rc = tc2::make_rows_map(hs_out, num_edges, &hs_map)) return rc;
+  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
   return after_launch("edge2_fwd2_kernel");
 }
 
@@ -1636,8 +1680,8 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::bwd1_kernel<0>, "bwd1_kernel", tc2::SmemN::BYTES)) return rc;
-    if (int rc = tc2::configure(tc2::bwd1_kernel<1>, "bwd1_kernel", tc2::SmemN::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::bwd1_kernel<0>, "bwd1_kernel", tc2::SmemB1::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::bwd1_kernel<1>, "bwd1_kernel", tc2::SmemB1::BYTES)) return rc;
     configured = true;
   }
   tc2::Bwd1Params p = {};
@@ -1646,8 +1690,10 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemN::BYTES, st>>>(p);
-  else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemN::BYTES, st>>>(p);
+  alignas(64) CUtensorMap ghu_map;
+  if (int rc = tc2::make_rows_map(ghu, num_edges, &ghu_map)) return rc;
+  if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemB1::BYTES, st>>>(p, ghu_map);
+  else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemB1::BYTES, st>>>(p, ghu_map);
   return after_launch("edge2_bwd1_kernel");
 }
 

@@ -59,6 +59,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// TMA engine, shared box -> 2-D tensor (tensor map in kernel parameter space); clips rows / columns out of bounds
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+               "r"(smem_u32(src_smem))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recent bulk group have finished reading their source
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
