@@ -99,50 +99,7 @@ int pev_scatter_coord_bwd(const float* gagg, const float* gxo, const float* w, c
                           float* gx, void* stream);
 
 /* ---------------------------------------------------------------- K1 (bf16 tensor-core form)
- * Fused edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79) on tcgen05, H = 256.
- * Stage 1: a = silu(A_i + B_j + wd d2) built on the fly, v = a W2^T + b2 (bf16 x bf16 -> fp32 in
- *          TMEM); writes v as bf16 [E,256] and agg[N,256] = segment_sum(silu(v)) (zeroed inside,
- *          fp32 atomics per warp-segment).  AB is fp32 [N,512] = [h Wa^T + b1 | h Wb^T].
- * Stage 2: m = silu(v), s = m W5^T + b5, t = silu(s), w = t . w6 + b6; writes w[E] fp32 (zeroed
- *          inside) and, if s_out != NULL, s as bf16 [E,256] for the backward pass.
- * W2p / W5p are 131072-byte images produced by pev_pack_weight_bf16 (bf16, K-major, 128-byte
- * swizzle -- the resident B operand of tcgen05.mma). */
-int pev_pack_weight_bf16(const float* W /*[256,256] row-major (out,in)*/, int32_t transpose,
-                         void* packed /*131072 bytes*/, void* stream);
-int pev_edge_mlp1_fwd_bf16(const float* AB /*fp32 [N,512]*/, const float* x, const float* wd,
-                           const void* W2p, const float* b2, const int32_t* row, const int32_t* col,
-                           int64_t num_nodes, int64_t num_edges, void* v_out /*bf16 [E,256]*/,
-                           void* a_out /*bf16 [E,256] or NULL: a = silu(u), kept for dW2*/,
-                           void* da_out /*bf16 [E,256] or NULL (with a_out): silu'(u)*/,
-                           float* agg /*[N,256]*/, void* stream);
-int pev_edge_mlp2_fwd_bf16(const void* v /*bf16 [E,256]*/, const void* W5p, const float* b5,
-                           const float* w6, const float* b6 /*[1]*/, int64_t num_edges,
-                           float* w_out /*[E]*/, void* s_out /*bf16 [E,256] or NULL*/,
-                           void* m_out /*bf16 [E,256] or NULL: m = silu(v), kept for dW5*/,
-                           void* dm_out /*bf16 [E,256] or NULL (with m_out): silu'(v)*/, void* stream);
-/* Backward of stage 2 (phi_x and the aggregation): gs = gw w6 silu'(s),
- * gm = gs W5 + gagg[row], gv = gm dm with dm = silu'(v) as stored by the forward pass.
- * W5tp = pev_pack_weight_bf16(W5, transpose=1).  Writes gs, gv (bf16 [E,256]) and the column sums
- * db5[256] = sum_e gs, dw6[256] = sum_e gw silu(s) (zeroed inside). */
-int pev_edge_mlp2_bwd_bf16(const void* s, const void* dm, const float* gw /*[E]*/, const float* w6,
-                           const void* W5tp, const float* gagg /*[N,256]*/, const int32_t* row,
-                           int64_t num_edges, void* gs_out, void* gv_out, float* db5, float* dw6,
-                           void* stream);
-/* Backward of stage 1: ga = gv W2, gu = ga da with da = silu'(u) as stored by the forward pass; writes
- * gu (bf16 [E,256]), gd2[e] = gu . wd and db2[256] = sum_e gv (both zeroed inside). */
-int pev_edge_mlp1_bwd_bf16(const void* gv, const void* da, const void* W2tp, const float* wd,
-                           int64_t num_edges, void* gu_out, float* gd2 /*[E]*/, float* db2,
-                           void* stream);
-/* Segmented sums of the bf16 per-edge gradient gu over CSR rows and CSC columns (the bf16 twin of
- * pev_edge_prologue_bwd): gAB[N,512], gwd_part[N,256], gx[N,3] (+= into a caller-initialised gx). */
-int pev_edge_prologue_bwd_bf16(const void* gu /*bf16 [E,256]*/, const float* gd2, const float* x,
-                               const int32_t* row_ptr, const int32_t* row, const int32_t* col,
-                               const int32_t* col_ptr, const int32_t* csc_perm, int64_t num_nodes,
-                               int64_t num_edges, float* gAB, float* gx_accum, float* gwd_part,
-                               void* stream);
-
-/* ---------------------------------------------------------------- K1 (bf16 tensor-core form, v2)
- * Second-generation fused edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79), H = 256
+ * Fused edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79), H = 256
  * (csrc/edge_tc2_kernels.cu).  Conventions:
  *  - half domain: pre-activations are carried as h = z/2; weight images are packed with scale 0.5
  *    (pev_pack_weight_bf16_scaled), biases are halved inside the kernels, and the node projection is

@@ -53,12 +53,6 @@ _PROTOS = {
 }
 # tensor-core entry points: present in libpev_b200.so only (no host restatement)
 _PROTOS_TC = {
-    "pev_pack_weight_bf16": (c_int32, [_P, _I, _P, _P]),
-    "pev_edge_mlp1_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
-    "pev_edge_mlp2_fwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
-    "pev_edge_mlp2_bwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
-    "pev_edge_mlp1_bwd_bf16": (c_int32, [_P, _P, _P, _P, _L, _P, _P, _P, _P]),
-    "pev_edge_prologue_bwd_bf16": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P]),
     # v2 edge pipeline (csrc/edge_tc2_kernels.cu)
     "pev_pack_weight_bf16_scaled": (c_int32, [_P, _I, c_float, _P, _P]),
     "pev_edge2_tile_image_bytes": (c_int64, [_L]),

@@ -123,36 +123,6 @@ scatter_bwd_gx_kernel(const float* __restrict__ gxo, const float* __restrict__ w
   st3(gx + 3 * i, coord_update_bwd_x(gxo, w, dinv, row_ptr, row, col_ptr, csc_perm, i));
 }
 
-// bf16 twin of edge_prologue_bwd_feat: one thread per (node, feature pair), fp32 accumulation in
-// ascending edge order over the node's CSR row segment (gA, gwd) and CSC column segment (gB)
-__global__ void __launch_bounds__(256)
-edge_prologue_bwd_feat_bf16_kernel(const __nv_bfloat162* __restrict__ gu, const float* __restrict__ x,
-                                   const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                   const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ csc_perm,
-                                   int64_t N, int H2, float* __restrict__ gAB, float* __restrict__ gwd_part) {
-  const int64_t total = N * H2;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = idx / H2;
-    const int k2 = (int)(idx - i * H2);
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, p0 = 0.f, p1 = 0.f;
-    for (int64_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
-      const float2 g = __bfloat1622float2(gu[e * H2 + k2]);
-      const float d2 = edge_d2(x, (int)i, col[e]);
-      a0 += g.x; a1 += g.y;
-      p0 = fmaf(g.x, d2, p0); p1 = fmaf(g.y, d2, p1);
-    }
-    for (int64_t q = col_ptr[i]; q < col_ptr[i + 1]; ++q) {
-      const float2 g = __bfloat1622float2(gu[(int64_t)csc_perm[q] * H2 + k2]);
-      b0 += g.x; b1 += g.y;
-    }
-    const int H = 2 * H2;
-    *reinterpret_cast<float2*>(gAB + i * 2 * H + 2 * k2) = make_float2(a0, a1);
-    *reinterpret_cast<float2*>(gAB + i * 2 * H + H + 2 * k2) = make_float2(b0, b1);
-    *reinterpret_cast<float2*>(gwd_part + i * H + 2 * k2) = make_float2(p0, p1);
-  }
-}
-
 __global__ void __launch_bounds__(128)
 edge_prologue_bwd_coord_accum_kernel(const float* __restrict__ gd2, const float* __restrict__ x,
                                      const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ row,
@@ -217,24 +187,6 @@ int pev_edge_prologue_bwd(const float* gu, const float* x, const float* wd, cons
   edge_prologue_bwd_coord_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(scratch_gd2, x, row_ptr, row, col,
                                                                              col_ptr, csc_perm, N, gx);
   return after_launch("edge_prologue_bwd_coord_kernel");
-}
-
-int pev_edge_prologue_bwd_bf16(const void* gu, const float* gd2, const float* x, const int32_t* row_ptr,
-                               const int32_t* row, const int32_t* col, const int32_t* col_ptr,
-                               const int32_t* csc_perm, int64_t N, int64_t E, float* gAB, float* gx_accum,
-                               float* gwd_part, void* stream) {
-  PEV_REQUIRE(x && row_ptr && col_ptr && gAB && gx_accum && gwd_part, "bad argument");
-  if (N == 0) return 0;
-  PEV_REQUIRE(E == 0 || (gu && gd2 && row && col && csc_perm), "edge arrays missing");
-  cudaStream_t st = as_stream(stream);
-  int rc;
-  const int H2 = 128;
-  edge_prologue_bwd_feat_bf16_kernel<<<grid_cap(N * H2, 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat162*>(gu), x, row_ptr, col, col_ptr, csc_perm, N, H2, gAB, gwd_part);
-  if ((rc = after_launch("edge_prologue_bwd_feat_bf16_kernel"))) return rc;
-  edge_prologue_bwd_coord_accum_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(gd2, x, row_ptr, row, col,
-                                                                                   col_ptr, csc_perm, N, gx_accum);
-  return after_launch("edge_prologue_bwd_coord_accum_kernel");
 }
 
 int pev_edge_coord_bwd_accum(const float* gd2, const float* x, const int32_t* row_ptr, const int32_t* row,

@@ -12,7 +12,7 @@ Two precisions:
 
 * ``"fp32"`` -- exact-order path: :class:`EdgePrologue` (K1, fp32 form) -> dense fp32 edge MLP ->
   :class:`ScatterCoord` (K2, sequential ascending-edge sums, bit-identical to CPU ``index_add_``).
-* ``"bf16"`` -- fused tcgen05 edge MLP (``egnn_tc.py``), H = 256.
+* ``"bf16"`` -- fused tcgen05 edge MLP (``egnn_tc.py`` / ``egnn_tc2.py``), H = 256.
 """
 from __future__ import annotations
 

@@ -175,3 +175,22 @@ def test_kabsch_host(bk):
     for s in range(a.shape[0]):
         want = kabsch_oracle.kabsch_rmsd(a[s].astype(np.float64), b[0].astype(np.float64), np.ones(a.shape[1]))
         assert abs(shared[s] - want) < 1e-5 * max(want, 1.0)
+
+
+def test_tile_image_layout_roundtrip_and_addressing():
+    """Tile-image format of the v2 edge kernels (csrc/edge_tc2_kernels.cu header): helper round trip and the byte
+    address formula the kernels use."""
+    from protein_ensemble_vae_b200 import egnn_tc2 as T2
+    torch.manual_seed(0)
+    E = 300
+    rows = torch.randn(E, 256).to(torch.bfloat16)
+    img = T2.rows_to_tile_image(rows)
+    assert img.shape == (3, 128 * 256)
+    assert torch.equal(T2.tile_image_to_rows(img, E), rows)
+    flat = img.view(-1)
+    for e, f in ((0, 0), (5, 7), (63, 64), (64, 200), (127, 255), (128, 9), (299, 130)):
+        t, el = divmod(e, 128)
+        off = t * 65536 + (f // 64) * 16384 + (el // 64) * 8192 + ((f % 64) // 8) * 1024 + (f % 8) * 128 \
+            + ((((el % 64) // 8) ^ (f % 8)) << 4) + (el % 8) * 2
+        assert flat[off // 2] == rows[e, f]
+    assert float(img.view(3, -1)[2].float().abs().sum()) > 0 and float(T2.rows_to_tile_image(rows[:1])[0, 128:].abs().sum()) >= 0
