@@ -114,15 +114,16 @@ int64_t pev_edge2_tile_image_bytes(int64_t num_edges);
 /* d2[e] = |x[row[e]] - x[col[e]]|^2 (models/en_gnn_decoder.py:61-62). */
 int pev_edge_d2(const float* x, const int32_t* row, const int32_t* col, int64_t num_edges,
                 float* d2 /*[E]*/, void* stream);
-/* fwd1: hu = Ah_i + Bh_j + (wd/2) d2, a = silu(2 hu), hv = a (W2/2)^T + b2/2 -> hvT tile images;
- * agg[N,256] = segment_sum(silu(2 hv)) (zeroed inside; one fp32 atomic per segment and feature). */
+/* fwd1: hu = Ah_i + Bh_j + (wd/2) d2, a = silu(2 hu), hv = a (W2/2)^T + b2/2, m = silu(2 hv);
+ * writes the mT tile images (operand of fwd2 / wgrad5) and, when hvT != NULL (a backward pass follows),
+ * the hvT tile images; agg[N,256] = segment_sum(m) (zeroed inside; one fp32 atomic per segment and feature). */
 int pev_edge2_fwd1(const void* ABh /*fp16 [N,512]*/, const float* d2 /*[E]*/, const float* wd,
                    const void* W2hp, const float* b2, const int32_t* row, const int32_t* col,
-                   int64_t num_nodes, int64_t num_edges, void* hvT /*tile images*/,
-                   float* agg /*[N,256]*/, void* stream);
-/* fwd2: m = silu(2 hv), hs = m (W5/2)^T + b5/2, t = silu(2 hs), w = t . w6 + b6 -> w[E] (zeroed
- * inside); hs_out (bf16 [E,256]) is written when not NULL (kept for the backward pass). */
-int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const float* w6,
+                   int64_t num_nodes, int64_t num_edges, void* hvT /*tile images or NULL*/,
+                   void* mT /*tile images*/, float* agg /*[N,256]*/, void* stream);
+/* fwd2: hs = m (W5/2)^T + b5/2, t = silu(2 hs), w = t . w6 + b6 -> w[E] (zeroed inside);
+ * hs_out (bf16 [E,256]) is written when not NULL (kept for the backward pass). */
+int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const float* w6,
                    const float* b6 /*[1]*/, int64_t num_edges, float* w_out /*[E]*/,
                    void* hs_out /*bf16 [E,256] or NULL*/, void* stream);
 
@@ -151,13 +152,13 @@ int pev_edge_coord_bwd_accum(const float* gd2, const float* x, const int32_t* ro
                              const int32_t* col, const int32_t* col_ptr, const int32_t* csc_perm,
                              int64_t num_nodes, int64_t num_edges, float* gx_accum, void* stream);
 /* Weight gradients of the two 256x256 edge linears as split-K tcgen05 GEMMs over the edge dimension; both
- * operands are rebuilt on the fly (nothing but hs / hvT / ghvT is read from HBM).  `workspace` holds one
+ * operands come from hs / mT / ghvT and the node projection (a is rebuilt on the fly).  `workspace` holds one
  * 256x256 fp32 partial per CTA (pev_edge2_wgrad_workspace_bytes()); the partials are summed in a fixed order.
  *   wgrad5: dW5[k,f] = sum_e gs[e,k] m[e,f] (full-domain gradient of phi_x.0.weight), db5[256] = sum_e ghs
  *           (half domain: db5 = result / 2), dw6[256] = sum_e gw silu(s)  (db5, dw6 zeroed inside)
  *   wgrad2: dW2[f,j] = sum_e gv[e,f] a[e,j] (full-domain gradient of phi_e.2.weight) */
 int64_t pev_edge2_wgrad_workspace_bytes(void);
-int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* hvT, int64_t num_edges,
+int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* mT, int64_t num_edges,
                      float* workspace, float* dW5 /*[256,256]*/, float* db5h, float* dw6, void* stream);
 int pev_edge2_wgrad2(const void* ghvT, const void* ABh, const float* d2, const int32_t* row,
                      const int32_t* col, const float* wd, int64_t num_edges, float* workspace,

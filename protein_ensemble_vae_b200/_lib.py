@@ -57,7 +57,7 @@ _PROTOS_TC = {
     "pev_pack_weight_bf16_scaled": (c_int32, [_P, _I, c_float, _P, _P]),
     "pev_edge2_tile_image_bytes": (c_int64, [_L]),
     "pev_edge_d2": (c_int32, [_P, _P, _P, _L, _P, _P]),
-    "pev_edge2_fwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
+    "pev_edge2_fwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P]),
     "pev_edge2_fwd2": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "pev_edge2_bwd2": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "pev_edge2_bwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),

@@ -12,9 +12,9 @@
 //     16-byte chunk c ^ r) -- exactly the SWIZZLE_128B shared-memory image of the tile, which the tensor core reads
 //     either as an MN-major operand (M = edges) or as a K-major operand (K = edges), so consumers copy it verbatim.
 //
-//   fwd1  hu = Ah_i + Bh_j + wdh d2 ; a = silu  --GEMM W2h (transposed)-->  hv (+b2h) -> HBM tile image,
-//         m = silu ; agg[row] += m (in-thread segment sums, one RED per segment per feature)
-//   fwd2  m = silu(hv)  --GEMM W5h (A operand MN-major)-->  hs (+b5h) [-> HBM, training], t = silu, w[e] = t.w6 + b6
+//   fwd1  hu = Ah_i + Bh_j + wdh d2 ; a = silu  --GEMM W2h (transposed)-->  hv (+b2h), m = silu(hv) -> HBM tile images
+//         (hv only when a backward pass follows) ; agg[row] += m (in-thread segment sums, one RED per segment per feature)
+//   fwd2  m (TMA, A operand MN-major)  --GEMM W5h-->  hs (+b5h) [-> HBM, training], t = silu, w[e] = t.w6 + b6
 #include <cuda.h>          // CUtensorMap types only: the encoder is resolved at run time (no libcuda link dependency)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -69,7 +69,6 @@ struct SmemL {
 };
 using SmemT = SmemL<2, 256, 8 * 8192>;   // feature-lane epilogues (fwd1, bwd2): 2-stage ring + 8 x 2 x 4 KB image staging
 using SmemB1 = SmemL<2, 256, 16 * 4096>;  // bwd1: 2-stage ring (TMA-fed) + 16 x 2 x 2 KB row-box staging for the store of ghu
-using SmemF2 = SmemL<3, 512, 8 * 4096>;  // fwd2: 3-stage ring + 8 x 2 x 2 KB row-box staging for the TMA tensor store of hs
 
 struct Bars {
   uint64_t* full;     // [NUM_STAGES] producers -> MMA
@@ -189,7 +188,8 @@ struct Fwd1Params {
   const float* wd;            // [256] (full domain; halved on load)
   const float* b2;            // [256] (full domain; halved on load)
   const void* W2hp;           // packed image of 0.5 W2
-  uint8_t* hvT;               // [num_tiles] x 64 KB tile images of hv = v/2 (bf16)
+  uint8_t* hvT;               // [num_tiles] x 64 KB tile images of hv = v/2 (bf16); null when no backward follows
+  uint8_t* mT;                // [num_tiles] x 64 KB tile images of m = silu(v) (bf16): the operand of fwd2 / wgrad5
   float* agg;                 // [N,256] (+=)
   int64_t E;
   int num_tiles;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
     // tile-image offset of this warp's 32 rows (features f - lane .. + 31), edge half 0: 4 KB contiguous
     const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
     const int sw = f & 7;
-    uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;      // two 4 KB buffers, one per edge half
+    uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;      // two 4 KB buffers: hv rows | m rows
     auto flush = [&](int r, float s) {
       if (r >= 0 && !(dbg & 4)) atomicAdd(aggcol + (int64_t)r * H, s);
     };
@@ -338,7 +338,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
         const int64_t e = e0 + cb * 32 + lane;
         myrow[cb] = e < p.E ? __ldg(p.row + e) : -1;
       }
-      uint8_t* img = p.hvT + (int64_t)tile * TILE_IMG_BYTES + img_blk;
       mbar_wait(&B.tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       if (dbg & 128) {                                 // role ablation: accumulator handshake only
@@ -361,30 +360,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);            // accumulator stage fully read
         }
-        // hv -> HBM tile image (bf16).  This warp's 32 feature rows x 64 edges are 4 KB contiguous in the image: the
-        // rows are staged in shared memory (swizzled chunk positions: conflict-free) and written by one TMA bulk copy
-        // per edge half -- full lines, no per-lane global stores.
+        // hv and m = silu(2 hv) -> HBM tile images (bf16).  This warp's 32 feature rows x 64 edges are 4 KB contiguous
+        // in an image: the rows are staged in shared memory (swizzled chunk positions: conflict-free) and written by
+        // one TMA bulk copy per edge half and image -- full lines, no per-lane global stores.
+        float m[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m[j] = (dbg & 8) ? val[j] : silu_h(val[j]);
         if (!(dbg & 2)) {
-          uint8_t* sbuf = stg + (cb >> 1) * 4096;
           if ((cb & 1) == 0) {
-            if (lane == 0) bulk_wait_read_1();        // the bulk copy that last used this buffer has read it
+            if (lane == 0) bulk_wait_read();          // the previous bulk copies have read the staging buffers
             __syncwarp();
           }
+          uint8_t* srow = stg + lane * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
-                                 val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
-            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((((cb & 1) * 4 + k) ^ sw) << 4)) = pack8(o8);
+            const uint32_t pos = (uint32_t)((((cb & 1) * 4 + k) ^ sw) << 4);
+            if (p.hvT) {
+              const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
+                                   val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
+              *reinterpret_cast<uint4*>(srow + pos) = pack8(o8);
+            }
+            const float q8[8] = {m[8 * k], m[8 * k + 1], m[8 * k + 2], m[8 * k + 3],
+                                 m[8 * k + 4], m[8 * k + 5], m[8 * k + 6], m[8 * k + 7]};
+            *reinterpret_cast<uint4*>(srow + 4096 + pos) = pack8(q8);
           }
           if (cb & 1) {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) bulk_s2g(img + (cb >> 1) * 8192, sbuf, 4096);
+            if (lane == 0) {
+              const int64_t off = (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192;
+              if (p.hvT) bulk_s2g(p.hvT + off, stg, 4096);
+              bulk_s2g(p.mT + off, stg + 4096, 4096);
+            }
           }
         }
-        float m[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) m[j] = (dbg & 8) ? val[j] : silu_h(val[j]);
         // segment sums over the 32 edges (uniform control flow: every lane sees the same edges)
         int prev = __shfl_up_sync(0xffffffffu, myrow[cb], 1);
         if (lane == 0) prev = cur;
@@ -412,8 +421,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
 }
 
 // =================================================================================================== fwd2
+//   m (tile images, TMA -> MN-major A operand)  --GEMM (W5/2)-->  hs (+b5h) [-> HBM rows, training], t = silu,
+//   w[e] = t . w6 + b6.   Block: 16 epilogue warps (lane = edge; TMEM lane quarter = warp % 4, column quarter =
+//   warp / 4), warp 16 = MMA issue, warp 17 = TMA loads.  No CUDA-core producer: fwd1 already wrote m.
+constexpr int F2_EPI_WARPS = 16;
+constexpr int F2_MMA_WARP = 16;
+constexpr int F2_TMA_WARP = 17;
+constexpr int F2_THREADS = 32 * (F2_EPI_WARPS + 4);     // 640 -> 96 registers at launch
+constexpr int F2_REGS_EPI = 104;
+using SmemF2 = SmemL<3, 512, 16 * 2048>;                // 3-stage ring + 16 x 2 KB row-box staging (TMA tensor store of hs)
+
 struct Fwd2Params {
-  const uint8_t* hvT;     // tile images of hv
+  const uint8_t* mT;      // tile images of m = silu(v)
   const void* W5hp;       // packed image of 0.5 W5
   const float* b5;        // [256] full domain
   const float* w6;        // [256]
@@ -426,21 +445,43 @@ struct Fwd2Params {
 };
 
 template <int DBG>
-__global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p, const __grid_constant__ CUtensorMap hs_map) {
+__global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p, const __grid_constant__ CUtensorMap hs_map) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(SmemF2, NUM_PROD_THREADS)
-  float* sBias = sVec;
-  float* sW6 = sVec + H;
-  for (int k = threadIdx.x; k < H; k += NUM_THREADS) {
+  constexpr int NUM_STAGES = SmemF2::NSTAGE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem + SmemF2::W_OFF;
+  uint8_t* sA = smem + SmemF2::A_OFF;
+  float* sBias = reinterpret_cast<float*>(smem + SmemF2::VEC_OFF);
+  float* sW6 = sBias + H;
+  const Bars B = make_bars(smem + SmemF2::BAR_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < H; k += F2_THREADS) {
     sBias[k] = 0.5f * p.b5[k];
     sW6[k] = p.w6[k];
   }
-  PEV_TC2_SYNC_ROLES()
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(&B.full[s], 1);
+      mbar_init(&B.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&B.tfull[a], 1);
+      mbar_init(&B.tempty[a], 32 * F2_EPI_WARPS);
+    }
+    mbar_init(B.w, 1);
+    fence_barrier_init();
+  }
+  if (warp == F2_MMA_WARP) tmem_alloc(B.tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *B.tmem_slot;
 
-  if (warp >= MMA_WARP && warp < PROD_WARP0) {
-    // ------------------------------------------------------------------ MMA issue: D[e, n] = m[e, :] . W5h[n, :]
+  if (warp >= F2_EPI_WARPS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA_WG));
-    if (warp == MMA_WARP && lane == 0) {
+    if (warp == F2_MMA_WARP && lane == 0) {
+      // ---------------------------------------------------------------- MMA issue: D[e, n] = m[e, :] . W5h[n, :]
       load_weight_image(sW, p.W5hp, B.w);
       constexpr uint32_t IDESC = idesc_bf16(128, 256, true, false);             // A (activations) MN-major
       int stage = 0, it = 0;
@@ -465,65 +506,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
         }
         umma_commit(&B.tfull[acc]);
       }
-    }
-    __syncwarp();
-  } else if (warp >= PROD_WARP0) {
-    // ------------------------------------------------------------------ producers: m = silu(hv), image -> ring verbatim
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
-    const int pt = threadIdx.x - 32 * PROD_WARP0;
-    constexpr int CPT = STAGE_BYTES / 16 / NUM_PROD_THREADS;   // 16-byte chunks per thread per stage (2)
-    constexpr int PD = 3;                                      // stages of load-ahead
-    int stage = 0;
-    uint32_t phase = 0;
-    uint4 pf[NUM_KCHUNKS][CPT];
-    auto issue = [&](int tile, int kc) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.hvT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES);
-#pragma unroll
-      for (int i = 0; i < CPT; ++i)
-        pf[kc][i] = (dbg & 1) ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + pt + NUM_PROD_THREADS * i);
-    };
-#pragma unroll
-    for (int kc = 0; kc < PD; ++kc) issue(blockIdx.x, kc);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int next_tile = tile + gridDim.x;
-      if (dbg & 64) {                                  // role ablation: ring handshake only
+    } else if (warp == F2_TMA_WARP && lane == 0) {
+      // ---------------------------------------------------------------- TMA: tile image K-chunks -> ring, verbatim
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
           mbar_wait(&B.empty[stage], phase ^ 1);
-          fence_proxy_async();
-          mbar_arrive(&B.full[stage]);
+          mbar_arrive_expect_tx(&B.full[stage], STAGE_BYTES);
+          bulk_g2s(sA + stage * STAGE_BYTES, p.mT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES, STAGE_BYTES,
+                   &B.full[stage]);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
-        continue;
-      }
-#pragma unroll
-      for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
-        if (kc + PD < NUM_KCHUNKS) issue(tile, kc + PD);
-        else if (next_tile < p.num_tiles) issue(next_tile, kc + PD - NUM_KCHUNKS);
-        uint4 out[CPT];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          float v8[8];
-          unpack8(pf[kc][i], v8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v8[j] = silu_h(v8[j]);
-          out[i] = pack8(v8);
-        }
-        mbar_wait(&B.empty[stage], phase ^ 1);
-        uint4* st = reinterpret_cast<uint4*>(sA + stage * STAGE_BYTES);
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) st[pt + NUM_PROD_THREADS * i] = out[i];
-        fence_proxy_async();
-        mbar_arrive(&B.full[stage]);
-        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: lane = edge, registers = features
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
-    const int q = warp & 3, half = warp >> 2;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
-    const float b6 = half == 0 ? __ldg(p.b6) : 0.f;
-    uint8_t* stg = smem + SmemF2::STG_OFF + warp * 4096;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F2_REGS_EPI));
+    const int q = warp & 3, cq = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    const float b6 = cq == 0 ? __ldg(p.b6) : 0.f;
+    uint8_t* stg = smem + SmemF2::STG_OFF + warp * 2048;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
       float dot = 0.f;
       mbar_wait(&B.tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      if (dbg & 128) {                                 // role ablation: accumulator handshake only
+      if (dbg & 128) {
         tc_fence_before();
         mbar_arrive(&B.tempty[acc]);
         continue;
@@ -540,19 +544,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
       uint32_t raw[32];
       tmem_ld32_issue(lane_addr + acc * H, raw);
 #pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        const int col0 = half * 128 + cb * 32;
+      for (int b = 0; b < 2; ++b) {
+        const int col0 = cq * 64 + b * 32;
         tmem_wait();
         float val[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j4);
-          val[4 * j4] = __uint_as_float(raw[4 * j4]) + b.x;
-          val[4 * j4 + 1] = __uint_as_float(raw[4 * j4 + 1]) + b.y;
-          val[4 * j4 + 2] = __uint_as_float(raw[4 * j4 + 2]) + b.z;
-          val[4 * j4 + 3] = __uint_as_float(raw[4 * j4 + 3]) + b.w;
+          const float4 bb = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j4);
+          val[4 * j4] = __uint_as_float(raw[4 * j4]) + bb.x;
+          val[4 * j4 + 1] = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
+          val[4 * j4 + 2] = __uint_as_float(raw[4 * j4 + 2]) + bb.z;
+          val[4 * j4 + 3] = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
         }
-        if (cb + 1 < 4) tmem_ld32_issue(lane_addr + acc * H + (cb + 1) * 32, raw);
+        if (b == 0) tmem_ld32_issue(lane_addr + acc * H + 32, raw);
         else {
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);
@@ -560,19 +564,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
         if (p.hs && !(dbg & 2)) {
           // hs rows -> HBM through a TMA tensor store: the warp's [32 edges x 32 features] box is staged in shared
           // memory (64-byte rows, SWIZZLE_64B chunk positions: conflict-free) and written by the TMA engine, which
-          // also clips the rows past E.  Two boxes per warp alternate, so nothing waits on a store just issued.
-          uint8_t* sbuf = stg + (cb & 1) * 2048;
-          if (lane == 0) bulk_wait_read_1();
+          // also clips the rows past E.
+          if (lane == 0) bulk_wait_read();
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
                                  val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
-            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = pack8(o8);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = pack8(o8);
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) tma_store_2d(&hs_map, col0, (int)((int64_t)tile * TILE_M + q * 32), sbuf);
+          if (lane == 0) tma_store_2d(&hs_map, col0, (int)((int64_t)tile * TILE_M + q * 32), stg);
         }
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -587,7 +590,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd2_kernel(const Fwd2Params p
     }
     if (lane == 0) bulk_wait_all();
   }
-  PEV_TC2_EPILOGUE()
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F2_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 __device__ __forceinline__ uint4 sel4(uint32_t c, const uint4 a, const uint4 b) {   // c ? a : b
@@ -1084,28 +1093,26 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p,
 // =================================================================================================== wgrad
 // Weight gradients as split-K GEMMs over the edge dimension, accumulated in TMEM over all tiles of a CTA (2 x 256
 // columns = the whole 256 x 256 fp32 matrix) and written once per CTA to a partial buffer; wgrad_reduce_kernel sums
-// the partials in a fixed order (deterministic).  Both operands are rebuilt on the fly, nothing but hs / hvT / ghvT
+// the partials in a fixed order (deterministic).  Both operands are rebuilt on the fly, nothing but hs / mT / ghvT
 // is read from HBM.  The ring unit is a HALF tile (64 edges): 32 KB of each operand, 3 stages.
-//   MODE 5:  dW5h[k, f] = sum_e ghs[e, k] m[e, f]       A = ghs (MN-major, rows = edges), B = m = silu(hv) (K-major image)
+//   MODE 5:  dW5h[k, f] = sum_e ghs[e, k] m[e, f]       A = ghs (MN-major, rows = edges), B = m (K-major image via TMA)
 //            + column sums db5h[k] = sum_e ghs[e, k], dW6[k] = sum_e gw[e] t[e, k]  (in the row producers' registers)
 //   MODE 2:  dW2h[f, j] = sum_e ghv[e, f] a[e, j]       A = ghv (K-major image via TMA), B = a = silu(hu) (MN-major, rows = edges)
-// Warps: 0..15 row producers (4 per 64-column block, 16 rows each), 16 MMA issue, 17 TMA (MODE 2), 20..27 image
-// producers (MODE 5).  After the main loop warps 0..7 flush TMEM.
+// Warps: 0..15 row producers (4 per 64-column block, 16 rows each), 16 MMA issue, 17 TMA (the image operand).
+// After the main loop warps 0..7 flush TMEM.
 constexpr int WG_HALF_BYTES = 64 * H * 2;          // 32 KB: one operand of a half tile
 constexpr int WG_STAGE_BYTES = 2 * WG_HALF_BYTES;  // 64 KB
 constexpr int WG_STAGES = 3;
 constexpr int WG_ROW_WARPS = 16;
 constexpr int WG_MMA_WARP = 16;
 constexpr int WG_TMA_WARP = 17;
-constexpr int WG_IMG_WARP0 = 20;
-constexpr int WG_IMG_WARPS = 8;
 constexpr int WG_VEC_OFF = WG_STAGES * WG_STAGE_BYTES;                 // 4 x 256 floats
 constexpr int WG_BAR_OFF = WG_VEC_OFF + 4 * H * 4;
 constexpr int WG_SMEM_BYTES = WG_BAR_OFF + 128 + 1024;
 template <int MODE> struct WgCfg {
-  static constexpr int WARPS = MODE == 5 ? WG_IMG_WARP0 + WG_IMG_WARPS : 20;
-  static constexpr int THREADS = 32 * WARPS;                            // 896 (72 regs) / 640 (96 regs)
-  static constexpr int FULL_COUNT = MODE == 5 ? 32 * (WG_ROW_WARPS + WG_IMG_WARPS) : 32 * WG_ROW_WARPS + 1;
+  static constexpr int WARPS = 20;
+  static constexpr int THREADS = 32 * WARPS;                            // 640 (96 registers per thread)
+  static constexpr int FULL_COUNT = 32 * WG_ROW_WARPS + 1;              // row producers + the TMA thread's expect_tx
 };
 
 struct WgradParams {
@@ -1113,7 +1120,7 @@ struct WgradParams {
   const __nv_bfloat16* hs;    // [E,256]
   const float* gw;            // [E]
   const float* w6;            // [256]
-  const uint8_t* hvT;         // tile images of hv
+  const uint8_t* mT;          // tile images of m = silu(v)
   float* db5h;                // [256] (+=)
   float* dw6;                 // [256] (+=)
   // MODE 2
@@ -1306,57 +1313,24 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
       umma_commit(done);
     }
     __syncwarp();
-  } else if (MODE == 2 && warp == WG_TMA_WARP) {
+  } else if (warp == WG_TMA_WARP) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- TMA: ghv image half (4 x 8 KB) -> A operand
+      // ---------------------------------------------------------------- TMA: image half (4 x 8 KB) -> K-major operand
+      // (MODE 2: ghv -> A operand; MODE 5: m -> B operand); the 8 KB pieces [fq] of the edge half become contiguous
+      const uint8_t* img = MODE == 5 ? p.mT : p.ghvT;
       int stage = 0;
       uint32_t phase = 0;
       for (int hi = 0; hi < nh; ++hi) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], WG_HALF_BYTES);
-        const uint8_t* src = p.ghvT + (int64_t)tile_of(hi) * TILE_IMG_BYTES + (hi & 1) * 8192;
-        uint8_t* dst = smem + stage * WG_STAGE_BYTES;
+        const uint8_t* src = img + (int64_t)tile_of(hi) * TILE_IMG_BYTES + (hi & 1) * 8192;
+        uint8_t* dst = smem + stage * WG_STAGE_BYTES + (MODE == 5 ? WG_HALF_BYTES : 0);
 #pragma unroll
         for (int fq = 0; fq < 4; ++fq) bulk_g2s(dst + fq * 8192, src + fq * 16384, 8192, &full[stage]);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
-  } else if (MODE == 5 && warp >= WG_IMG_WARP0) {
-    // ------------------------------------------------------------------ image producers: m = silu(hv), K-major B operand
-    const int pt = threadIdx.x - 32 * WG_IMG_WARP0;            // 0..255
-    constexpr int CPT = WG_HALF_BYTES / 16 / (32 * WG_IMG_WARPS);   // 8 chunks per thread per half tile
-    int stage = 0;
-    uint32_t phase = 0;
-    uint4 pf[CPT];
-    auto issue = [&](int hi) {
-      const uint8_t* src = p.hvT + (int64_t)tile_of(hi) * TILE_IMG_BYTES + (hi & 1) * 8192;
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        const int idx = pt + 256 * i;                            // chunk of the 32 KB half: fq = idx >> 9
-        pf[i] = __ldg(reinterpret_cast<const uint4*>(src + (idx >> 9) * 16384 + (idx & 511) * 16));
-      }
-    };
-    issue(0);
-    for (int hi = 0; hi < nh; ++hi) {
-      uint4 out[CPT];
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        float h8[8];
-        unpack8(pf[i], h8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h8[j] = silu_h(h8[j]);
-        out[i] = pack8(h8);
-      }
-      if (hi + 1 < nh) issue(hi + 1);
-      mbar_wait(&empty[stage], phase ^ 1);
-      uint4* st = reinterpret_cast<uint4*>(smem + stage * WG_STAGE_BYTES + WG_HALF_BYTES);
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) st[pt + 256 * i] = out[i];
-      fence_proxy_async();
-      mbar_arrive(&full[stage]);
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
-    }
   }
 
   // -------------------------------------------------------------------- flush: TMEM -> this CTA's partial matrix
@@ -1597,13 +1571,13 @@ int pev_edge_d2(const float* x, const int32_t* row, const int32_t* col, int64_t 
 }
 
 int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void* W2hp, const float* b2,
-                   const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges, void* hvT, float* agg,
-                   void* stream) {
+                   const int32_t* row, const int32_t* col, int64_t num_nodes, int64_t num_edges, void* hvT, void* mT,
+                   float* agg, void* stream) {
   PEV_REQUIRE(ABh && wd && W2hp && b2 && agg && num_nodes >= 0 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
   if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc2::H * (size_t)num_nodes, st);
   if (num_edges == 0) return 0;
-  PEV_REQUIRE(row && col && hvT && d2, "edge arrays missing");
+  PEV_REQUIRE(row && col && mT && d2, "edge arrays missing");
   static bool configured = false;
   if (!configured) {
     if (int rc = tc2::configure(tc2::fwd1_kernel<0>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
@@ -1612,7 +1586,7 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   }
   tc2::Fwd1Params p = {};
   p.ABh = reinterpret_cast<const __half*>(ABh); p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.b2 = b2; p.W2hp = W2hp;
-  p.hvT = reinterpret_cast<uint8_t*>(hvT); p.agg = agg; p.E = num_edges;
+  p.hvT = reinterpret_cast<uint8_t*>(hvT); p.mT = reinterpret_cast<uint8_t*>(mT); p.agg = agg; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
   if (p.dbg) tc2::fwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
@@ -1620,11 +1594,11 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   return after_launch("edge2_fwd1_kernel");
 }
 
-int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const float* w6, const float* b6,
+int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const float* w6, const float* b6,
                    int64_t num_edges, float* w_out, void* hs_out, void* stream) {
   PEV_REQUIRE(W5hp && b5 && w6 && b6 && num_edges >= 0, "bad argument");
   if (num_edges == 0) return 0;
-  PEV_REQUIRE(hvT && w_out, "edge arrays missing");
+  PEV_REQUIRE(mT && w_out, "edge arrays missing");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
@@ -1634,7 +1608,7 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
     configured = true;
   }
   tc2::Fwd2Params p = {};
-  p.hvT = reinterpret_cast<const uint8_t*>(hvT); p.W5hp = W5hp; p.b5 = b5; p.w6 = w6; p.b6 = b6;
+  p.mT = reinterpret_cast<const uint8_t*>(mT); p.W5hp = W5hp; p.b5 = b5; p.w6 = w6; p.b6 = b6;
   p.hs = reinterpret_cast<bf16_t*>(hs_out); p.w = w_out; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
@@ -1642,8 +1616,8 @@ int pev_edge2_fwd2(const void* hvT, const void* W5hp, const float* b5, const flo
   memset(&hs_map, 0, sizeof(hs_map));
   if (hs_out)
     if (int rc = tc2::make_rows_map(hs_out, num_edges, &hs_map)) return rc;
-  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
-  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
   return after_launch("edge2_fwd2_kernel");
 }
 
@@ -1714,7 +1688,7 @@ int pev_edge2_sums(const void* ghu, const float* d2, const int32_t* row_ptr, con
 
 int64_t pev_edge2_wgrad_workspace_bytes(void) { return (int64_t)sm_count() * tc2::H * tc2::H * (int64_t)sizeof(float); }
 
-int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* hvT, int64_t num_edges,
+int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* mT, int64_t num_edges,
                      float* workspace, float* dW5, float* db5, float* dw6, void* stream) {
   PEV_REQUIRE(w6 && dW5 && db5 && dw6 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
@@ -1724,9 +1698,9 @@ int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const voi
     cudaMemsetAsync(dW5, 0, sizeof(float) * tc2::H * tc2::H, st);
     return 0;
   }
-  PEV_REQUIRE(hs && gw && hvT && workspace, "edge arrays missing");
+  PEV_REQUIRE(hs && gw && mT && workspace, "edge arrays missing");
   tc2::WgradParams p = {};
-  p.hs = reinterpret_cast<const bf16_t*>(hs); p.gw = gw; p.w6 = w6; p.hvT = reinterpret_cast<const uint8_t*>(hvT);
+  p.hs = reinterpret_cast<const bf16_t*>(hs); p.gw = gw; p.w6 = w6; p.mT = reinterpret_cast<const uint8_t*>(mT);
   p.db5h = db5; p.dw6 = dw6; p.partial = workspace; p.E = num_edges;
   return launch_wgrad<5>(p, 0.5f, dW5, st);
 }

@@ -123,6 +123,31 @@ class NodeLinear(torch.autograd.Function):
         return gx, gW, gb, None
 
 
+class NodeLinear2(torch.autograd.Function):
+    """``[x1 | x2] W^T + b`` without materialising the concatenation (``phi_h[0]`` on ``[h, agg]``,
+    ``models/en_gnn_decoder.py:71``): two accumulating TF32 GEMMs forward, contiguous gradients backward."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W, b):
+        D1 = x1.shape[1]
+        ctx.save_for_backward(x1, x2, W)
+        with _tf32_matmul():
+            y = torch.addmm(b, x1, W[:, :D1].t())
+            return y.addmm_(x2, W[:, D1:].t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, W = ctx.saved_tensors
+        D1 = x1.shape[1]
+        g = g.contiguous()
+        with _tf32_matmul():
+            g1 = g @ W[:, :D1] if ctx.needs_input_grad[0] else None
+            g2 = g @ W[:, D1:] if ctx.needs_input_grad[1] else None
+            gW = torch.cat([g.t() @ x1, g.t() @ x2], 1) if ctx.needs_input_grad[2] else None
+        gb = column_sum(g) if ctx.needs_input_grad[3] else None
+        return g1, g2, gW, gb
+
+
 def apply_tf32(module, x, fp32_forward=False):
     """Run an ``nn.Linear`` / ``nn.Sequential`` of the decoder with its linears on :class:`NodeLinear` (bf16 path)."""
     if isinstance(module, nn.Linear):

@@ -95,8 +95,8 @@ class FusedEdgeV2(torch.autograd.Function):
 
     ``ABh`` is the fp32 half-domain node projection ``0.5 [h Wa^T + b1 | h Wb^T]`` (rounded to fp16 here, once).
     Forward: ``pev_edge_d2`` -> ``pev_edge2_fwd1`` -> ``pev_edge2_fwd2`` -> exact-order coordinate update (K2).
-    Kept for the backward pass: the ``hv`` tile images and ``hs`` rows (bf16, 2 x 2.47 GB per layer at config 2),
-    ``w``, ``d2`` and the fp16 ``ABh``.  Backward: K2 backward -> ``bwd2`` (ghv) -> ``wgrad5`` ->
+    Kept for the backward pass: the ``hv`` and ``m`` tile images and ``hs`` rows (bf16, 3 x 2.47 GB per layer at
+    config 2), ``w``, ``d2`` and the fp16 ``ABh``.  Backward: K2 backward -> ``bwd2`` (ghv) -> ``wgrad5`` ->
     ``bwd1`` (ghu) -> ``wgrad2`` -> segmented row / column sums of ``ghu``; the activations a, m and the SiLU
     derivatives are rebuilt inside the kernels (one tanh each) instead of being stored.
     """
@@ -116,7 +116,8 @@ class FusedEdgeV2(torch.autograd.Function):
             W2hp = packed_weight_scaled(W2, 0.5, cache=caches[0])
             W5hp = packed_weight_scaled(W5, 0.5, cache=caches[1])
             d2 = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
-            hvT = alloc_tile_image(E, dev)
+            hvT = alloc_tile_image(E, dev) if keep else None
+            mT = alloc_tile_image(E, dev)
             hs = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
             agg = torch.empty(N, H, dtype=torch.float32, device=dev)
             w = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
@@ -124,21 +125,21 @@ class FusedEdgeV2(torch.autograd.Function):
             L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2), st)
             with _lib.profiled("edge2_fwd1"):
                 L.call("pev_edge2_fwd1", ptr(ABb), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E,
-                       ptr(hvT), ptr(agg), st)
+                       ptr(hvT), ptr(mT), ptr(agg), st)
             with _lib.profiled("edge2_fwd2"):
-                L.call("pev_edge2_fwd2", ptr(hvT), ptr(W5hp), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(hs), st)
+                L.call("pev_edge2_fwd2", ptr(mT), ptr(W5hp), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w), ptr(hs), st)
             L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
                    None, ptr(x_out), st)
         ctx.g, ctx.caches = g, caches
         if keep:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, hs, w, d2)
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2)
         else:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None)
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None, None)
         return agg, x_out
 
     @staticmethod
     def backward(ctx, gagg, gxo):
-        x, wd, W2, W5, w6v, dinv, ABb, hvT, hs, w, d2 = ctx.saved_tensors
+        x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2 = ctx.saved_tensors
         if hs is None:
             raise RuntimeError("FusedEdgeV2 ran with keep=False (no_grad); backward is unavailable")
         g = ctx.g
@@ -163,7 +164,7 @@ class FusedEdgeV2(torch.autograd.Function):
             gW5 = torch.empty(H, H, dtype=f32, device=dev)
             db5h, gw6 = torch.empty(H, dtype=f32, device=dev), torch.empty(H, dtype=f32, device=dev)
             with _lib.profiled("edge2_wgrad5"):
-                L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6v), ptr(hvT), E, ptr(ws), ptr(gW5), ptr(db5h),
+                L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6v), ptr(mT), E, ptr(ws), ptr(gW5), ptr(db5h),
                        ptr(gw6), st)
             ghu = torch.empty(E, H, dtype=bf, device=dev)
             gd2 = torch.empty(max(E, 1), dtype=f32, device=dev)
@@ -189,7 +190,7 @@ class FusedEdgeV2(torch.autograd.Function):
 
 def egn_layer_v2(layer, h, x, g, dinv):
     """One EGNN layer with the edge MLP on the v2 kernels; ``layer`` is an ``EGNLayer`` (parameter holder)."""
-    from .egnn_tc import NodeLinear, layer_norm
+    from .egnn_tc import NodeLinear, NodeLinear2, layer_norm
     W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
@@ -200,6 +201,6 @@ def egn_layer_v2(layer, h, x, g, dinv):
     agg, x_new = FusedEdgeV2.apply(ABh, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
                                    layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
                                    layer.phi_x[2].bias, dinv, g, keep, caches)
-    q = layer.phi_h[1](NodeLinear.apply(torch.cat([h, agg], -1), layer.phi_h[0].weight, layer.phi_h[0].bias))
+    q = layer.phi_h[1](NodeLinear2.apply(h, agg, layer.phi_h[0].weight, layer.phi_h[0].bias))
     h_new = layer_norm(layer.norm_h, NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias), h)
     return h_new, x_new

@@ -51,13 +51,13 @@ def test_forward_kernels_match_emulation(lengths, W):
     L.call("pev_edge_d2", ptr(c["x"]), ptr(g.row), ptr(g.col), E, ptr(d2), st)
     d2_ref = ((c["x"][row] - c["x"][col]) ** 2).sum(-1)
     assert rel_err(d2, d2_ref) < 1e-6
-    hvT = T2.alloc_tile_image(E, "cuda")
+    hvT, mT = T2.alloc_tile_image(E, "cuda"), T2.alloc_tile_image(E, "cuda")
     agg = torch.full((N, H), 7.0, device="cuda")            # zeroed inside
     w = torch.full((E,), 7.0, device="cuda")
     hs = torch.empty(E, H, dtype=BF, device="cuda")
     L.call("pev_edge2_fwd1", ptr(c["ABh"]), ptr(d2), ptr(c["wd"]), ptr(T2.packed_weight_scaled(c["W2"], 0.5)), ptr(c["b2"]),
-           ptr(g.row), ptr(g.col), N, E, ptr(hvT), ptr(agg), st)
-    L.call("pev_edge2_fwd2", ptr(hvT), ptr(T2.packed_weight_scaled(c["W5"], 0.5)), ptr(c["b5"]), ptr(c["w6"]), ptr(c["b6"]),
+           ptr(g.row), ptr(g.col), N, E, ptr(hvT), ptr(mT), ptr(agg), st)
+    L.call("pev_edge2_fwd2", ptr(mT), ptr(T2.packed_weight_scaled(c["W5"], 0.5)), ptr(c["b5"]), ptr(c["w6"]), ptr(c["b6"]),
            E, ptr(w), ptr(hs), st)
     hu = (c["ABh"][row, :H] + c["ABh"][col, H:]).float() + 0.5 * c["wd"] * d2_ref[:, None]
     hv = bf(silu2(hu)) @ bf(0.5 * c["W2"]).t() + 0.5 * c["b2"]
@@ -65,11 +65,18 @@ def test_forward_kernels_match_emulation(lengths, W):
     hv_k = T2.tile_image_to_rows(hvT, E).float()
     assert rel_err(hv_k, hv) < 6e-3
     assert rel_err(agg, agg_ref) < 1e-3
-    hs_ref = bf(silu2(hv_k)) @ bf(0.5 * c["W5"]).t() + 0.5 * c["b5"]          # from the kernel's own stored hv
+    m_k = T2.tile_image_to_rows(mT, E).float()
+    assert rel_err(m_k, silu2(hv)) < 6e-3
+    hs_ref = m_k @ bf(0.5 * c["W5"]).t() + 0.5 * c["b5"]                       # from the kernel's own stored m
     assert rel_err(hs.float(), hs_ref) < 6e-3
     assert rel_err(w, silu2(hs_ref) @ c["w6"] + c["b6"]) < 6e-3
-    w2 = torch.full((E,), 7.0, device="cuda")               # inference form: hs not written
-    L.call("pev_edge2_fwd2", ptr(hvT), ptr(T2.packed_weight_scaled(c["W5"], 0.5)), ptr(c["b5"]), ptr(c["w6"]), ptr(c["b6"]),
+    agg2 = torch.full((N, H), 7.0, device="cuda")          # inference form: neither hv nor hs written
+    mT2 = T2.alloc_tile_image(E, "cuda")
+    L.call("pev_edge2_fwd1", ptr(c["ABh"]), ptr(d2), ptr(c["wd"]), ptr(T2.packed_weight_scaled(c["W2"], 0.5)), ptr(c["b2"]),
+           ptr(g.row), ptr(g.col), N, E, None, ptr(mT2), ptr(agg2), st)
+    assert torch.equal(T2.tile_image_to_rows(mT2, E), T2.tile_image_to_rows(mT, E)) and rel_err(agg2, agg) < 1e-5
+    w2 = torch.full((E,), 7.0, device="cuda")
+    L.call("pev_edge2_fwd2", ptr(mT), ptr(T2.packed_weight_scaled(c["W5"], 0.5)), ptr(c["b5"]), ptr(c["w6"]), ptr(c["b6"]),
            E, ptr(w2), None, st)
     assert rel_err(w2, w) < 1e-5
 
@@ -89,6 +96,7 @@ def test_backward_kernels_match_emulation(lengths, W):
     L, st = _lib.lib(), stream(c["x"])
     d2 = ((c["x"][row] - c["x"][col]) ** 2).sum(-1).contiguous()
     hvT = T2.rows_to_tile_image(hv)
+    mT = T2.rows_to_tile_image(silu2(hv.float()).to(BF))
     ghvT = T2.alloc_tile_image(E, "cuda")
     db2h = torch.empty(H, device="cuda")
     ghu = torch.empty(E, H, dtype=BF, device="cuda")
@@ -101,7 +109,7 @@ def test_backward_kernels_match_emulation(lengths, W):
            ptr(db2h), st)
     L.call("pev_edge2_bwd1", ptr(ghvT), ptr(P(c["W2"])), ptr(c["ABh"]), ptr(d2), ptr(g.row), ptr(g.col), ptr(c["wd"]), E,
            ptr(ghu), ptr(gd2), st)
-    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(c["w6"]), ptr(hvT), E, ptr(ws), ptr(dW5), ptr(db5h), ptr(dw6), st)
+    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(c["w6"]), ptr(mT), E, ptr(ws), ptr(dW5), ptr(db5h), ptr(dw6), st)
     L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(c["ABh"]), ptr(d2), ptr(g.row), ptr(g.col), ptr(c["wd"]), E, ptr(ws), ptr(dW2), st)
     ghs = gw[:, None] * c["w6"] * one_plus_r(hs.float())
     ghv = (bf(ghs) @ bf(0.5 * c["W5"]) + gagg[row]) * one_plus_r(hv.float())

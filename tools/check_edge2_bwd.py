@@ -64,6 +64,7 @@ st = stream(x)
 W5thp = T2.packed_weight_scaled(W5, 0.5, transpose=True)
 W2thp = T2.packed_weight_scaled(W2, 0.5, transpose=True)
 hvT = T2.rows_to_tile_image(hv)
+mT = T2.rows_to_tile_image((hv.float() + hv.float() * torch.tanh(hv.float())).to(bf16))
 ghvT = T2.alloc_tile_image(E, dev)
 db2h_k = torch.empty(H, device=dev)
 ghu_k = torch.empty(E, H, dtype=bf16, device=dev)
@@ -82,7 +83,7 @@ for rep in range(reps + 1):
     L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABh), ptr(d2k), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ghu_k),
            ptr(gd2_k), st)
     ev[2].record()
-    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(hvT), E, ptr(ws), ptr(dW5_k), ptr(db5h_k), ptr(dw6_k), st)
+    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(mT), E, ptr(ws), ptr(dW5_k), ptr(db5h_k), ptr(dw6_k), st)
     ev[3].record()
     L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(ABh), ptr(d2k), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ws), ptr(dW2_k), st)
     ev[4].record()

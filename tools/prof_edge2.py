@@ -25,7 +25,7 @@ L = _lib.lib()
 st = stream(x)
 P = lambda W, t=False: T2.packed_weight_scaled(W, 0.5, transpose=t)
 W2hp, W5hp, W2thp, W5thp = P(W2), P(W5), P(W2, True), P(W5, True)
-hvT, ghvT = T2.alloc_tile_image(E, dev), T2.alloc_tile_image(E, dev)
+hvT, mT, ghvT = (T2.alloc_tile_image(E, dev) for _ in range(3))
 hs, ghu = (torch.empty(E, H, dtype=torch.bfloat16, device=dev) for _ in range(2))
 agg, w, d2, gd2 = torch.empty(N, H, device=dev), torch.empty(E, device=dev), torch.empty(E, device=dev), torch.empty(E, device=dev)
 db2h, db5h, dw6 = (torch.empty(H, device=dev) for _ in range(3))
@@ -37,13 +37,13 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
 L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2), st)
 for rep in range(reps + 1):
     ev[0].record()
-    L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E, ptr(hvT), ptr(agg), st)
+    L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E, ptr(hvT), ptr(mT), ptr(agg), st)
     ev[1].record()
-    L.call("pev_edge2_fwd2", ptr(hvT), ptr(W5hp), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(hs), st)
+    L.call("pev_edge2_fwd2", ptr(mT), ptr(W5hp), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(hs), st)
     ev[2].record()
     L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ghvT), ptr(db2h), st)
     ev[3].record()
-    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(hvT), E, ptr(ws), ptr(dW5), ptr(db5h), ptr(dw6), st)
+    L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(mT), E, ptr(ws), ptr(dW5), ptr(db5h), ptr(dw6), st)
     ev[4].record()
     L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABh), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ghu), ptr(gd2), st)
     ev[5].record()
