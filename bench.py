@@ -147,7 +147,7 @@ def workload_config(n_gpus):
                         "decoder fwd+bwd + compute_total_loss fwd+bwd + Adam step, bf16 edge MLP",
             "L": CFG["L"], "layers": CFG["layers"], "batch_per_gpu": CFG["batch_per_gpu"],
             "global_batch": CFG["batch_per_gpu"] * n_gpus, "parallelism": f"dp{n_gpus}",
-            "cache": "inputs_larger_than_l2 (603 MB of latents/posteriors + 5 GB of per-edge activations per layer)"}
+            "cache": "inputs_larger_than_l2 (603 MB of latents/posteriors + 7.4 GB of per-edge bf16 streams per layer)"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -258,11 +258,11 @@ def run_gpu(args):
         # "traffic" of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the
         # ncu --set full capture in profiles/ (scaled from its B=32 launch by the edge count).
         KSPEC = {  # tag: (kernel, streams read+written, extra bytes per edge, tcgen05 GEMMs, tanh per edge-feature)
-            "edge2_fwd1": ("fwd1_kernel", 1, 16, 1, 2),
-            "edge2_fwd2": ("fwd2_kernel", 2, 4, 1, 2),
+            "edge2_fwd1": ("fwd1_kernel", 2, 16, 1, 2),
+            "edge2_fwd2": ("fwd2_kernel", 2, 4, 1, 1),
             "edge2_bwd2": ("bwd2_kernel", 3, 8, 1, 2),
             "edge2_bwd1": ("bwd1_kernel", 2, 20, 1, 1),
-            "edge2_wgrad5": ("wgrad_kernel<5>", 2, 4, 1, 2),
+            "edge2_wgrad5": ("wgrad_kernel<5>", 2, 4, 1, 1),
             "edge2_wgrad2": ("wgrad_kernel<2>", 1, 12, 1, 1),
             "edge2_sums": ("edge_sums_kernel", 2, 8, 0, 0),
         }
@@ -321,7 +321,8 @@ def run_gpu(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per edge of each v2 edge kernel (ncu --set full, profiles/)
-NCU_TRAFFIC_PER_EDGE = {}
+NCU_TRAFFIC_PER_EDGE = {"edge2_fwd1": 987.9, "edge2_fwd2": 961.2, "edge2_bwd2": 1504.9, "edge2_wgrad5": 1035.8,
+                        "edge2_bwd1": 987.6, "edge2_wgrad2": 546.6, "edge2_sums": 847.6}
 
 
 def lib_edges(L, W=40):

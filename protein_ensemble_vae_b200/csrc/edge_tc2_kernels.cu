@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[8 + j] = silu_grad_r(h8[j]);
         }
-        if (bi + 1 < nb)                            // the same pair of the next batch (two 16-edge steps ahead)
+        if (bi + 1 < nb && !(dbg & 4))              // the same pair of the next batch (two 16-edge steps ahead)
           ld_256(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES + pair_off((bi + 1) & 3, pr), hvq[pr][0], hvq[pr][1]);
         tmem_wait();
         if (cb == 3 && pr == 1) {
