@@ -752,11 +752,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 128);
     const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
     const int sw = f & 7;
-    const uint32_t swap = (uint32_t)(sw & 1);
     float dbacc = 0.f;
-    // byte offset inside a tile image of the 32-byte pair `pr` of batch `cb` for this thread's feature row
-    auto pair_off = [&](int cb, int pr) -> uint32_t {
-      return img_row + (uint32_t)((cb >> 1) * 8192) + (uint32_t)(((((cb & 1) * 4 + 2 * pr) ^ sw) & 6) << 4);
+    // byte offsets inside a tile image of the two 16-byte chunks (8 edges each) of step `pr` of batch `cb` for this
+    // thread's feature row
+    auto chunk_off = [&](int cb, int pr, int k) -> uint32_t {
+      return img_row + (uint32_t)((cb >> 1) * 8192) + (uint32_t)((((cb & 1) * 4 + 2 * pr + k) ^ sw) << 4);
+    };
+    auto load_hv = [&](const uint8_t* img, int cb, int pr, uint4 (&q)[2]) {
+      q[0] = __ldg(reinterpret_cast<const uint4*>(img + chunk_off(cb, pr, 0)));
+      q[1] = __ldg(reinterpret_cast<const uint4*>(img + chunk_off(cb, pr, 1)));
     };
     // The CTA's tiles are walked as a flat sequence of 32-edge batches (4 per tile), each in two steps of 16 edges
     // (one 32-byte pair of the thread's image row, 16 TMEM columns).  Row ids are fetched two batches ahead, the
@@ -776,8 +780,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     float gaF, gaL, gaFn = 0.f, gaLn = 0.f;
     batch_ga(row_c, gaF, gaL);
     uint4 hvq[2][2];                               // hv pair `pr` of the batch in flight: loaded one batch ahead
-    ld_256(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES + pair_off(0, 0), hvq[0][0], hvq[0][1]);
-    ld_256(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES + pair_off(0, 1), hvq[1][0], hvq[1][1]);
+    load_hv(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES, 0, 0, hvq[0]);
+    load_hv(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES, 0, 1, hvq[1]);
     uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;       // staging of this warp's 32 rows x 64 edges: 2 x 4 KB
     const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
 #pragma unroll 1
@@ -801,8 +805,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       // segments of the 32-edge batch (uniform control flow: every lane sees the same edges)
       const int prev = __shfl_up_sync(0xffffffffu, row_c, 1);
       const uint32_t bm = __ballot_sync(0xffffffffu, lane != 0 && row_c != prev);
-      const bool one = bm != 0u && (bm & (bm - 1u)) == 0u;
-      const uint32_t low = bm - 1u;                // one boundary: edges before it
+      const bool simple = (bm & (bm - 1u)) == 0u;  // at most one boundary in the batch
+      const uint32_t low = bm - 1u;                // edges before the boundary (all 32 when there is none)
       float ga_run = gaF;                          // several boundaries: running value / row
       int r_run = __shfl_sync(0xffffffffu, row_c, 0);
       uint8_t* stg_row = stg + (cb >> 1) * 4096 + lane * 128;
@@ -817,28 +821,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         // r(hv) of the 16 edges while the TMEM load is in flight
         float r[16];
         {
-          // the two 16-byte chunks of the pair sit in swizzled order: pick them at use time (selecting right
-          // after the load would expose its latency)
           float h8[8];
-          unpack8(sel4(swap, hvq[pr][1], hvq[pr][0]), h8);
+          unpack8(hvq[pr][0], h8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = silu_grad_r(h8[j]);
-          unpack8(sel4(swap, hvq[pr][0], hvq[pr][1]), h8);
+          unpack8(hvq[pr][1], h8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[8 + j] = silu_grad_r(h8[j]);
         }
-        if (bi + 1 < nb && !(dbg & 4))              // the same pair of the next batch (two 16-edge steps ahead)
-          ld_256(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES + pair_off((bi + 1) & 3, pr), hvq[pr][0], hvq[pr][1]);
+        if (bi + 1 < nb && !(dbg & 4))              // the same step of the next batch (two 16-edge steps ahead)
+          load_hv(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES, (bi + 1) & 3, pr, hvq[pr]);
         tmem_wait();
         if (cb == 3 && pr == 1) {
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);
         }
         float gv[16];
-        if (bm == 0u) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) gv[j] = __uint_as_float(raw[j]) + gaF;
-        } else if (one) {
+        if (simple) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) gv[j] = __uint_as_float(raw[j]) + (((low >> (16 * pr + j)) & 1u) ? gaF : gaL);
         } else {                                   // several short segments (not a banded graph): edge by edge

@@ -157,9 +157,17 @@ class EGNNDecoder(nn.Module):
         B, L, _ = z_l.shape
         device = z_l.device
         if mask is not None:
-            mb = mask.bool()
-            lengths = mb.sum(1).tolist()                        # one host sync per forward
-            flat_idx = torch.nonzero(mb.reshape(-1)).squeeze(-1) if sum(lengths) != B * L else None
+            # The packed size needs the valid lengths on the host: one sync per forward -- unless this very mask
+            # tensor (same object, same in-place version; the cache keeps it alive so its storage cannot be recycled)
+            # was resolved on the previous call, as in a training loop over one resident batch.
+            c = self.__dict__.get("_pev_mask_cache")
+            if c is not None and c[0] is mask and c[1] == mask._version:
+                lengths, flat_idx = c[2], c[3]
+            else:
+                mb = mask.bool()
+                lengths = mb.sum(1).tolist()
+                flat_idx = torch.nonzero(mb.reshape(-1)).squeeze(-1) if sum(lengths) != B * L else None
+                self.__dict__["_pev_mask_cache"] = (mask, mask._version, lengths, flat_idx)
         else:
             lengths, flat_idx = [L] * B, None
         N = int(sum(lengths))
