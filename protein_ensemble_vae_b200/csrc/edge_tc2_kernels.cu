@@ -137,21 +137,6 @@ __device__ __forceinline__ float masked_sum32(const float (&m)[32], uint32_t msk
   for (int j = 0; j < 32; ++j) s[j & 3] += ((msk >> j) & 1u) ? m[j] : 0.f;
   return (s[0] + s[1]) + (s[2] + s[3]);
 }
-// 32-byte global store of two 16-byte chunks, in the order (lo, hi) or swapped (one full sector either way)
-__device__ __forceinline__ void st_pair_256(void* addr, const uint4 a, const uint4 b, uint32_t swap) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-      "@!q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
-      "@q st.global.v8.b32 [%0], {%5, %6, %7, %8, %1, %2, %3, %4};\n\t}" ::"l"(addr),
-      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(swap)
-      : "memory");
-}
-__device__ __forceinline__ void st_256(void* addr, const uint4 a, const uint4 b) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(addr), "r"(a.x), "r"(a.y), "r"(a.z),
-               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
-}
-
 // Common prologue: barriers, TMEM, role register budgets.  Returns the TMEM base address.
 #define PEV_TC2_PROLOGUE(SM, FULL_COUNT)                                                      \
   constexpr int NUM_STAGES = SM::NSTAGE;                                                      \
@@ -599,18 +584,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p,
   }
 }
 
-__device__ __forceinline__ uint4 sel4(uint32_t c, const uint4 a, const uint4 b) {   // c ? a : b
-  return make_uint4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
-}
-// 32-byte global load of two 16-byte chunks stored in the order (lo, hi) or swapped (see st_pair_256)
-__device__ __forceinline__ void ld_pair_256(const void* addr, uint32_t swap, uint4& a, uint4& b) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-      "@!q ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
-      "@q ld.global.v8.b32 {%4, %5, %6, %7, %0, %1, %2, %3}, [%8];\n\t}"
-      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-      : "l"(addr), "r"(swap));
-}
+// 32-byte global load (LDG.256): two 16-byte chunks
 __device__ __forceinline__ void ld_256(const void* addr, uint4& a, uint4& b) {
   asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)

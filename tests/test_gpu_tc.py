@@ -107,3 +107,33 @@ def test_edge2_sums_match_index_add():
         gB = torch.zeros(N, H, device="cuda").index_add_(0, g.col.long(), gf)
         assert rel_err(gAB[:, :H], gA) < 1e-5 and rel_err(gAB[:, H:], gB) < 1e-5
         assert rel_err(gwdh, (gf * d2[:, None]).sum(0)) < 1e-4
+
+
+def test_node_linear2_matches_cat_linear_and_mask_cache_invalidates():
+    """phi_h[0] on [h, agg] without the concatenation (TF32: 2e-3), and the decoder's mask cache: an in-place edit of
+    the same mask tensor must be seen."""
+    from protein_ensemble_vae_b200 import EGNNDecoder
+    from protein_ensemble_vae_b200.egnn_tc import NodeLinear2
+    torch.manual_seed(2)
+    x1, x2 = (torch.randn(500, 256, device="cuda", requires_grad=True) for _ in range(2))
+    lin = torch.nn.Linear(512, 256).cuda()
+    coef = torch.randn(500, 256, device="cuda")
+    y = NodeLinear2.apply(x1, x2, lin.weight, lin.bias)
+    (y * coef).sum().backward()
+    got = (y.detach(), x1.grad.clone(), x2.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x1.grad = x2.grad = lin.weight.grad = lin.bias.grad = None
+    y2 = lin(torch.cat([x1, x2], -1))
+    (y2 * coef).sum().backward()
+    for a, b in zip(got, (y2.detach(), x1.grad, x2.grad, lin.weight.grad, lin.bias.grad)):
+        assert rel_err(a, b) < 2e-3
+    dec = EGNNDecoder(32, 16, hidden_dim=256, num_layers=1, max_neighbors=40, dropout=0.0, precision="bf16").cuda().eval()
+    zg, zl = torch.randn(2, 32, device="cuda"), torch.randn(2, 50, 16, device="cuda")
+    mask = torch.ones(2, 50, device="cuda")
+    with torch.no_grad():
+        a1 = dec(zg, zl, mask)[1]
+        a2 = dec(zg, zl, mask)[1]                      # cache hit: same tensor, same version
+        assert rel_err(a1, a2) < 1e-4                  # (agg is accumulated with fp32 atomics: not bit-reproducible)
+        mask[1, 30:] = 0                               # in-place edit bumps the version
+        a3 = dec(zg, zl, mask)[1]
+        ref = dec(zg, zl, mask.clone())[1]
+    assert float(a3[1, 30:].abs().max()) == 0.0 and rel_err(a3, ref) < 1e-4
