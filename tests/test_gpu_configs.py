@@ -170,3 +170,18 @@ def test_single_residue_and_empty_conformers():
         n, ca, c, lg = dec(torch.randn(3, 64, device=DEV), torch.randn(3, 9, 32, device=DEV), mask)
     assert torch.isfinite(ca).all() and float(ca[1].abs().max()) == 0.0 and float(lg[1].abs().max()) == 0.0
     assert float(ca[0, 4].abs().max()) > 0 and float(ca[0, :4].abs().max()) == 0.0
+
+
+def test_device_prefetcher_yields_batches_in_order():
+    """Double-buffered H2D staging (protein_ensemble_vae_b200/data.py): every batch arrives intact and in order,
+    also when the consumer is slow or the iterable is empty / a single batch."""
+    from protein_ensemble_vae_b200 import DevicePrefetcher
+    host = [{"a": torch.full((1000, 64), float(i)).pin_memory(), "b": torch.arange(5) + i} for i in range(7)]
+    seen = []
+    for d in DevicePrefetcher(host, DEV):
+        junk = torch.randn(2048, 2048, device=DEV) @ torch.randn(2048, 2048, device=DEV)   # keep the stream busy
+        seen.append((float(d["a"].mean()), int(d["b"][0]), float(d["a"].min()), float(junk.sum() * 0)))
+    assert [(s[0], s[1], s[2]) for s in seen] == [(float(i), i, float(i)) for i in range(7)]
+    assert list(DevicePrefetcher([], DEV)) == []
+    one = list(DevicePrefetcher(host[:1], DEV))
+    assert len(one) == 1 and float(one[0]["a"].max()) == 0.0
