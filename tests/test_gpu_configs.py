@@ -180,7 +180,7 @@ def test_device_prefetcher_yields_batches_in_order():
     seen = []
     for d in DevicePrefetcher(host, DEV):
         junk = torch.randn(2048, 2048, device=DEV) @ torch.randn(2048, 2048, device=DEV)   # keep the stream busy
-        seen.append((float(d["a"].mean()), int(d["b"][0]), float(d["a"].min()), float(junk.sum() * 0)))
+        seen.append((float(d["a"].max()), int(d["b"][0]), float(d["a"].min()), float(junk.sum() * 0)))
     assert [(s[0], s[1], s[2]) for s in seen] == [(float(i), i, float(i)) for i in range(7)]
     assert list(DevicePrefetcher([], DEV)) == []
     one = list(DevicePrefetcher(host[:1], DEV))
