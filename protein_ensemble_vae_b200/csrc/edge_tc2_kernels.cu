@@ -67,7 +67,8 @@ struct SmemL {
   static constexpr int BYTES = TOTAL + 1024;                            // slack for manual 1024-byte alignment
   static_assert(BYTES <= 232448, "shared memory budget");
 };
-using SmemT = SmemL<2, 256, 8 * 8192>;   // feature-lane epilogues (fwd1, bwd2): 2-stage ring + 8 x 2 x 4 KB image staging
+using SmemT = SmemL<2, 256, 8 * 8192>;   // fwd1: 2-stage ring + 8 x (4 KB hv rows | 4 KB m rows) image staging
+using SmemB2 = SmemL<4, 256, 8 * 4096>;  // bwd2: 4-stage ring + 8 x 4 KB image staging (ghv rows)
 using SmemB1 = SmemL<2, 256, 16 * 4096>;  // bwd1: 2-stage ring (TMA-fed) + 16 x 2 x 2 KB row-box staging for the store of ghu
 
 struct Bars {
@@ -612,7 +613,7 @@ struct Bwd2Params {
 template <int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(SmemT, NUM_PROD_THREADS)
+  PEV_TC2_PROLOGUE(SmemB2, NUM_PROD_THREADS)
   float* sW6 = sVec;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) sW6[k] = p.w6[k];
   PEV_TC2_SYNC_ROLES()
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     uint4 hvq[2][2];                               // hv pair `pr` of the batch in flight: loaded one batch ahead
     load_hv(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES, 0, 0, hvq[0]);
     load_hv(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES, 0, 1, hvq[1]);
-    uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;       // staging of this warp's 32 rows x 64 edges: 2 x 4 KB
+    uint8_t* stg = smem + SmemB2::STG_OFF + warp * 4096;      // staging of this warp's 32 rows x 64 edges (4 KB)
     const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
 #pragma unroll 1
     for (int bi = 0; bi < nb; ++bi) {
@@ -783,9 +784,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       const uint32_t low = bm - 1u;                // edges before the boundary (all 32 when there is none)
       float ga_run = gaF;                          // several boundaries: running value / row
       int r_run = __shfl_sync(0xffffffffu, row_c, 0);
-      uint8_t* stg_row = stg + (cb >> 1) * 4096 + lane * 128;
+      uint8_t* stg_row = stg + lane * 128;
       if (!(dbg & 2) && (cb & 1) == 0) {
-        if (lane == 0) bulk_wait_read_1();         // the bulk copy that last used this buffer has read it
+        if (lane == 0) bulk_wait_read();           // the previous bulk copy has read the staging buffer
         __syncwarp();
       }
 #pragma unroll
@@ -841,7 +842,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         fence_proxy_async();
         __syncwarp();
         if (lane == 0)
-          bulk_s2g(p.ghvT + (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192, stg + (cb >> 1) * 4096, 4096);
+          bulk_s2g(p.ghvT + (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192, stg, 4096);
       }
       row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
     }
@@ -1360,6 +1361,7 @@ __global__ void __launch_bounds__(256)
 edge_sums_kernel(const uint4* __restrict__ ghu, const float* __restrict__ d2, const int32_t* __restrict__ row_ptr,
                  const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ csc_perm, int64_t N,
                  float* __restrict__ gAB, float* __restrict__ gwdh) {
+  constexpr int UNR = 8;                        // edge rows in flight per warp
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1373,16 +1375,16 @@ edge_sums_kernel(const uint4* __restrict__ ghu, const float* __restrict__ d2, co
     {
       const int64_t e0 = row_ptr[i], e1 = row_ptr[i + 1];
       int64_t e = e0;
-      for (; e + 4 <= e1; e += 4) {
-        uint4 v[4];
-        float dd[4];
+      for (; e + UNR <= e1; e += UNR) {
+        uint4 v[UNR];
+        float dd[UNR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
           v[u] = __ldg(ghu + (e + u) * 32 + lane);
           dd[u] = __ldg(d2 + e + u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
           float g8[8];
           unpack8(v[u], g8);
 #pragma unroll
@@ -1406,12 +1408,12 @@ edge_sums_kernel(const uint4* __restrict__ ghu, const float* __restrict__ d2, co
     {
       const int64_t q0 = col_ptr[i], q1 = col_ptr[i + 1];
       int64_t q = q0;
-      for (; q + 4 <= q1; q += 4) {
-        uint4 v[4];
+      for (; q + UNR <= q1; q += UNR) {
+        uint4 v[UNR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(ghu + (int64_t)__ldg(csc_perm + q + u) * 32 + lane);
+        for (int u = 0; u < UNR; ++u) v[u] = __ldg(ghu + (int64_t)__ldg(csc_perm + q + u) * 32 + lane);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
           float g8[8];
           unpack8(v[u], g8);
 #pragma unroll
@@ -1603,8 +1605,8 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   PEV_REQUIRE(hs && gw && gagg && row && hvT && ghvT, "edge arrays missing");
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::bwd2_kernel<0>, "bwd2_kernel", tc2::SmemT::BYTES)) return rc;
-    if (int rc = tc2::configure(tc2::bwd2_kernel<1>, "bwd2_kernel", tc2::SmemT::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::bwd2_kernel<0>, "bwd2_kernel", tc2::SmemB2::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::bwd2_kernel<1>, "bwd2_kernel", tc2::SmemB2::BYTES)) return rc;
     configured = true;
   }
   tc2::Bwd2Params p = {};
@@ -1613,8 +1615,8 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::bwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
-  else tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+  if (p.dbg) tc2::bwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemB2::BYTES, st>>>(p);
+  else tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemB2::BYTES, st>>>(p);
   return after_launch("edge2_bwd2_kernel");
 }
 
