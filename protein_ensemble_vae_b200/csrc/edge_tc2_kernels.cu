@@ -21,6 +21,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "../../include/pev_b200.h"
 #include "pev_common.cuh"
@@ -67,7 +68,8 @@ struct SmemL {
   static constexpr int BYTES = TOTAL + 1024;                            // slack for manual 1024-byte alignment
   static_assert(BYTES <= 232448, "shared memory budget");
 };
-using SmemT = SmemL<2, 256, 8 * 8192>;   // fwd1: 2-stage ring + 8 x (4 KB hv rows | 4 KB m rows) image staging
+using SmemT = SmemL<2, 256, 8 * 8192>;   // fwd1 (training): 2-stage ring + 8 x (4 KB hv rows | 4 KB m rows) image staging
+using SmemTI = SmemL<4, 256, 8 * 4096>;  // fwd1 (inference, hv not written): 4-stage ring + 8 x 4 KB m rows
 using SmemB2 = SmemL<4, 256, 8 * 4096>;  // bwd2: 4-stage ring + 8 x 4 KB image staging (ghv rows)
 using SmemB1 = SmemL<2, 256, 16 * 4096>;  // bwd1: 2-stage ring (TMA-fed) + 16 x 2 x 2 KB row-box staging for the store of ghu
 
@@ -182,10 +184,13 @@ struct Fwd1Params {
   int dbg;                    // PEV_TC2_DEBUG bit mask (profiling experiments only; 0 in production)
 };
 
-template <int DBG>
+template <int DBG, bool TRAIN>   // TRAIN: hv is written too (p.hvT != null)
 __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p) {
   const int dbg = DBG ? p.dbg : 0;
-  PEV_TC2_PROLOGUE(SmemT, NUM_PROD_THREADS)
+  using SM = std::conditional_t<TRAIN, SmemT, SmemTI>;
+  constexpr int STG_PER_WARP = TRAIN ? 8192 : 4096;
+  constexpr int M_STG_OFF = TRAIN ? 4096 : 0;
+  PEV_TC2_PROLOGUE(SM, NUM_PROD_THREADS)
   float* sWd = sVec;
   for (int k = threadIdx.x; k < H; k += NUM_THREADS) sWd[k] = 0.5f * p.wd[k];
   PEV_TC2_SYNC_ROLES()
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
     // tile-image offset of this warp's 32 rows (features f - lane .. + 31), edge half 0: 4 KB contiguous
     const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
     const int sw = f & 7;
-    uint8_t* stg = smem + SmemT::STG_OFF + warp * 8192;      // two 4 KB buffers: hv rows | m rows
+    uint8_t* stg = smem + SM::STG_OFF + warp * STG_PER_WARP; // 4 KB buffers: [hv rows |] m rows
     auto flush = [&](int r, float s) {
       if (r >= 0 && !(dbg & 4)) atomicAdd(aggcol + (int64_t)r * H, s);
     };
@@ -361,22 +366,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t pos = (uint32_t)((((cb & 1) * 4 + k) ^ sw) << 4);
-            if (p.hvT) {
+            if (TRAIN) {
               const float o8[8] = {val[8 * k], val[8 * k + 1], val[8 * k + 2], val[8 * k + 3],
                                    val[8 * k + 4], val[8 * k + 5], val[8 * k + 6], val[8 * k + 7]};
               *reinterpret_cast<uint4*>(srow + pos) = pack8(o8);
             }
             const float q8[8] = {m[8 * k], m[8 * k + 1], m[8 * k + 2], m[8 * k + 3],
                                  m[8 * k + 4], m[8 * k + 5], m[8 * k + 6], m[8 * k + 7]};
-            *reinterpret_cast<uint4*>(srow + 4096 + pos) = pack8(q8);
+            *reinterpret_cast<uint4*>(srow + M_STG_OFF + pos) = pack8(q8);
           }
           if (cb & 1) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
               const int64_t off = (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192;
-              if (p.hvT) bulk_s2g(p.hvT + off, stg, 4096);
-              bulk_s2g(p.mT + off, stg + 4096, 4096);
+              if (TRAIN) bulk_s2g(p.hvT + off, stg, 4096);
+              bulk_s2g(p.mT + off, stg + M_STG_OFF, 4096);
             }
           }
         }
@@ -430,7 +435,7 @@ struct Fwd2Params {
   int dbg;
 };
 
-template <int DBG>
+template <int DBG, bool TRAIN>   // TRAIN: hs is written (p.hs != null)
 __global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p, const __grid_constant__ CUtensorMap hs_map) {
   const int dbg = DBG ? p.dbg : 0;
   constexpr int NUM_STAGES = SmemF2::NSTAGE;
@@ -547,7 +552,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p,
           tc_fence_before();
           mbar_arrive(&B.tempty[acc]);
         }
-        if (p.hs && !(dbg & 2)) {
+        if (TRAIN && !(dbg & 2)) {
           // hs rows -> HBM through a TMA tensor store: the warp's [32 edges x 32 features] box is staged in shared
           // memory (64-byte rows, SWIZZLE_64B chunk positions: conflict-free) and written by the TMA engine, which
           // also clips the rows past E.
@@ -1555,8 +1560,10 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   PEV_REQUIRE(row && col && mT && d2, "edge arrays missing");
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd1_kernel<0>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
-    if (int rc = tc2::configure(tc2::fwd1_kernel<1>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<0, true>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<1, true>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<0, false>, "fwd1_kernel", tc2::SmemTI::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd1_kernel<1, false>, "fwd1_kernel", tc2::SmemTI::BYTES)) return rc;
     configured = true;
   }
   tc2::Fwd1Params p = {};
@@ -1564,8 +1571,14 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   p.hvT = reinterpret_cast<uint8_t*>(hvT); p.mT = reinterpret_cast<uint8_t*>(mT); p.agg = agg; p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
-  if (p.dbg) tc2::fwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
-  else tc2::fwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+  const int grid = tc2::grid_for(p.num_tiles);
+  if (hvT) {
+    if (p.dbg) tc2::fwd1_kernel<1, true><<<grid, tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+    else tc2::fwd1_kernel<0, true><<<grid, tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+  } else {
+    if (p.dbg) tc2::fwd1_kernel<1, false><<<grid, tc2::NUM_THREADS, tc2::SmemTI::BYTES, st>>>(p);
+    else tc2::fwd1_kernel<0, false><<<grid, tc2::NUM_THREADS, tc2::SmemTI::BYTES, st>>>(p);
+  }
   return after_launch("edge2_fwd1_kernel");
 }
 
@@ -1578,8 +1591,10 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured = false;
   if (!configured) {
-    if (int rc = tc2::configure(tc2::fwd2_kernel<0>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
-    if (int rc = tc2::configure(tc2::fwd2_kernel<1>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<0, true>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<1, true>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<0, false>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+    if (int rc = tc2::configure(tc2::fwd2_kernel<1, false>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
     configured = true;
   }
   tc2::Fwd2Params p = {};
@@ -1591,8 +1606,14 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
   memset(&hs_map, 0, sizeof(hs_map));
   if (hs_out)
     if (int rc = tc2::make_rows_map(hs_out, num_edges, &hs_map)) return rc;
-  if (p.dbg) tc2::fwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
-  else tc2::fwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+  const int grid = tc2::grid_for(p.num_tiles);
+  if (hs_out) {
+    if (p.dbg) tc2::fwd2_kernel<1, true><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+    else tc2::fwd2_kernel<0, true><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+  } else {
+    if (p.dbg) tc2::fwd2_kernel<1, false><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+    else tc2::fwd2_kernel<0, false><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+  }
   return after_launch("edge2_fwd2_kernel");
 }
 

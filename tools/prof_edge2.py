@@ -32,7 +32,7 @@ db2h, db5h, dw6 = (torch.empty(H, device=dev) for _ in range(3))
 dW5, dW2 = torch.empty(H, H, device=dev), torch.empty(H, H, device=dev)
 ws = torch.empty(L.cdll.pev_edge2_wgrad_workspace_bytes() // 4, device=dev)
 gAB, part, gx = torch.empty(N, 2 * H, device=dev), torch.empty(N, H, device=dev), torch.zeros(N, 3, device=dev)
-names = ["fwd1", "fwd2", "bwd2", "wgrad5", "bwd1", "wgrad2", "sums"]
+names = ["fwd1", "fwd2", "bwd2", "wgrad5", "bwd1", "wgrad2", "sums", "fwd1_infer", "fwd2_infer"]
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
 L.call("pev_edge_d2", ptr(x), ptr(g.row), ptr(g.col), E, ptr(d2), st)
 for rep in range(reps + 1):
@@ -51,6 +51,10 @@ for rep in range(reps + 1):
     ev[6].record()
     L.call("pev_edge2_sums", ptr(ghu), ptr(d2), ptr(g.row_ptr), ptr(g.col_ptr), ptr(g.csc_perm), N, E, ptr(gAB), ptr(db2h), st)
     ev[7].record()
+    L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E, None, ptr(mT), ptr(agg), st)
+    ev[8].record()
+    L.call("pev_edge2_fwd2", ptr(mT), ptr(W5hp), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), None, st)
+    ev[9].record()
     torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))]
 print(f"B={B} E={E} tiles={(E + 127) // 128} " + " ".join(f"{n}={t:.3f}" for n, t in zip(names, ms)) + f" total={sum(ms):.3f} ms")
