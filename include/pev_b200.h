@@ -240,6 +240,10 @@ int pev_dihedral_terms_bwd(const float* dih, const float* target, const float* m
  * out[S]; 0.0 for an empty selection as in the reference (:350-351). */
 int pev_kabsch_rmsd(const float* a, const float* b, const float* mask, int32_t S, int32_t L,
                     int32_t b_batch, int32_t mask_batch, int32_t mode, float* out, void* stream);
+/* All pairs of one ensemble: out[S,S] (symmetric, zero diagonal) = Kabsch RMSD of a[i] vs a[j] for i < j -- the
+ * diversity loop of generate_ensemble_pdbs.py:591-595 (S(S-1)/2 host calls there) in one launch; mask[L] or NULL. */
+int pev_kabsch_rmsd_pairs(const float* a, const float* mask, int32_t S, int32_t L, int32_t mode,
+                          float* out /*[S,S]*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,8 +8,8 @@ kernels reached through the C ABI of ``include/pev_b200.h``.  CUDA-only, no CPU 
 from . import data, en_gnn_decoder, graph, kabsch, losses  # noqa: F401
 from .data import DevicePrefetcher  # noqa: F401
 from .en_gnn_decoder import EGNLayer, EGNNDecoder, ResidueDecoder, SE3EquivariantDecoder  # noqa: F401
-from .kabsch import kabsch_rmsd, kabsch_rmsd_batch  # noqa: F401
+from .kabsch import ensemble_diversity, kabsch_rmsd, kabsch_rmsd_batch, kabsch_rmsd_pairs  # noqa: F401
 from .losses import compute_total_loss  # noqa: F401
 
 __all__ = ["EGNLayer", "EGNNDecoder", "SE3EquivariantDecoder", "ResidueDecoder", "compute_total_loss",
-           "kabsch_rmsd", "kabsch_rmsd_batch", "DevicePrefetcher", "data", "losses", "en_gnn_decoder", "graph", "kabsch"]
+           "kabsch_rmsd", "kabsch_rmsd_batch", "kabsch_rmsd_pairs", "ensemble_diversity", "DevicePrefetcher", "data", "losses", "en_gnn_decoder", "graph", "kabsch"]

@@ -61,6 +61,7 @@ _PROTOS_TC = {
     "pev_edge2_fwd2": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "pev_edge2_bwd2": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "pev_edge2_bwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "pev_kabsch_rmsd_pairs": (c_int32, [_P, _P, _I, _I, _I, _P, _P]),
     # node-level kernels (csrc/node_kernels.cu)
     "pev_add_layernorm_fwd": (c_int32, [_P, _P, _P, _P, c_float, _L, _I, _P, _P, _P, _P, _P]),
     "pev_layernorm_bwd": (c_int32, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),

@@ -9,15 +9,9 @@
 
 namespace pev {
 
-__global__ void __launch_bounds__(128)
-kabsch_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask, int S,
-              int L, int b_batch, int mask_batch, int mode, float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= S) return;
-  const float* pa = a + (int64_t)s * L * 3;
-  const float* pb = b + (b_batch ? (int64_t)s * L * 3 : 0);
-  const float* pm = mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr;
+// RMSD of one pair of structures after Kabsch superposition, computed by one warp; returns the value in every lane
+__device__ __forceinline__ float kabsch_pair(const float* __restrict__ pa, const float* __restrict__ pb,
+                                             const float* __restrict__ pm, int L, int mode, int lane) {
   // pass 1: centroids
   double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
   int n = 0;
@@ -28,10 +22,7 @@ kabsch_kernel(const float* __restrict__ a, const float* __restrict__ b, const fl
     for (int k = 0; k < 3; ++k) { ca[k] += pa[3 * l + k]; cb[k] += pb[3 * l + k]; }
   }
   n = warp_sum(n);
-  if (n == 0) {
-    if (lane == 0) out[s] = 0.f;
-    return;
-  }
+  if (n == 0) return 0.f;
 #pragma unroll
   for (int k = 0; k < 3; ++k) { ca[k] = warp_sum(ca[k]) / n; cb[k] = warp_sum(cb[k]) / n; }
   // pass 2: covariance of the centred sets
@@ -73,7 +64,43 @@ kabsch_kernel(const float* __restrict__ a, const float* __restrict__ b, const fl
     }
   }
   e = warp_sum(e);
-  if (lane == 0) out[s] = (float)sqrt(e / n);
+  return (float)sqrt(e / n);
+}
+
+__global__ void __launch_bounds__(128)
+kabsch_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask, int S,
+              int L, int b_batch, int mask_batch, int mode, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const float* pa = a + (int64_t)s * L * 3;
+  const float* pb = b + (b_batch ? (int64_t)s * L * 3 : 0);
+  const float* pm = mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr;
+  const float r = kabsch_pair(pa, pb, pm, L, mode, lane);
+  if (lane == 0) out[s] = r;
+}
+
+// all pairs i < j of one ensemble (the diversity loop of generate_ensemble_pdbs.py:591-595): one warp per pair;
+// out[S,S] gets the value at (i,j) and (j,i), zeros on the diagonal
+__global__ void __launch_bounds__(128)
+kabsch_pairs_kernel(const float* __restrict__ a, const float* __restrict__ mask, int S, int L, int mode,
+                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pidx = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t npairs = (int64_t)S * (S - 1) / 2;
+  if (pidx >= npairs) {
+    return;
+  }
+  // pair index -> (i, j), i < j, rows of the strict upper triangle in order
+  int64_t i = (int64_t)((2.0 * S - 1.0 - sqrt((2.0 * S - 1.0) * (2.0 * S - 1.0) - 8.0 * (double)pidx)) * 0.5);
+  while (i > 0 && i * (2 * S - i - 1) / 2 > pidx) --i;
+  while ((i + 1) * (2 * S - i - 2) / 2 <= pidx) ++i;
+  const int64_t j = pidx - i * (2 * S - i - 1) / 2 + i + 1;
+  const float r = kabsch_pair(a + i * L * 3, a + j * L * 3, mask, L, mode, lane);
+  if (lane == 0) {
+    out[i * S + j] = r;
+    out[j * S + i] = r;
+  }
 }
 
 }  // namespace pev
@@ -85,4 +112,17 @@ extern "C" int pev_kabsch_rmsd(const float* a, const float* b, const float* mask
   if (S == 0) return 0;
   kabsch_kernel<<<(S + 3) / 4, 128, 0, as_stream(stream)>>>(a, b, mask, S, L, b_batch, mask_batch, mode, out);
   return after_launch("kabsch_kernel");
+}
+
+extern "C" int pev_kabsch_rmsd_pairs(const float* a, const float* mask, int32_t S, int32_t L, int32_t mode, float* out,
+                                     void* stream) {
+  using namespace pev;
+  PEV_REQUIRE(a && out && S >= 0 && L > 0 && (mode == 0 || mode == 1), "bad argument");
+  if (S == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(out, 0, sizeof(float) * (size_t)S * S, st);
+  const int64_t npairs = (int64_t)S * (S - 1) / 2;
+  if (npairs == 0) return 0;
+  kabsch_pairs_kernel<<<(unsigned)((npairs + 3) / 4), 128, 0, st>>>(a, mask, S, L, mode, out);
+  return after_launch("kabsch_pairs_kernel");
 }

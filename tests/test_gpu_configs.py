@@ -185,3 +185,31 @@ def test_device_prefetcher_yields_batches_in_order():
     assert list(DevicePrefetcher([], DEV)) == []
     one = list(DevicePrefetcher(host[:1], DEV))
     assert len(one) == 1 and float(one[0]["a"].max()) == 0.0
+
+
+@pytest.mark.parametrize("S,L", [(1, 20), (2, 33), (7, 100), (40, 64)])
+def test_kabsch_rmsd_pairs_matches_oracle_pair_by_pair(S, L):
+    """All-pairs RMSD matrix of one ensemble (generate_ensemble_pdbs.py:591-595 in one launch) against the numpy oracle
+    for every pair, in both conventions; symmetric, zero diagonal; the mean is the reference's avg_diversity."""
+    from protein_ensemble_vae_b200 import ensemble_diversity, kabsch_rmsd_pairs
+    rng = np.random.default_rng(S * 131 + L)
+    base = np.cumsum(rng.standard_normal((L, 3)) * 2.0, 0)
+    ens = np.stack([base + 0.7 * rng.standard_normal((L, 3)) for _ in range(S)]).astype(np.float32)
+    mask = np.ones(L, dtype=np.float32)
+    mask[rng.integers(0, L, 3)] = 0
+    c, m = torch.tensor(ens, device=DEV), torch.tensor(mask, device=DEV)
+    for compat, fn in ((False, kabsch_oracle.kabsch_rmsd), (True, kabsch_oracle.kabsch_rmsd_ref_compat)):
+        M = kabsch_rmsd_pairs(c, m, ref_compat=compat).cpu().numpy()
+        assert M.shape == (S, S) and np.all(np.diag(M) == 0) and np.array_equal(M, M.T)
+        vals = []
+        for i in range(S):
+            for j in range(i + 1, S):
+                want = fn(ens[i].astype(np.float64), ens[j].astype(np.float64), mask)
+                assert abs(M[i, j] - want) <= 1e-5 * max(want, 1e-3) + 2e-6, (i, j, M[i, j], want)
+                vals.append(want)
+        div = float(ensemble_diversity(c, m, ref_compat=compat))
+        assert abs(div - (np.mean(vals) if vals else 0.0)) <= 1e-5 * max(np.mean(vals) if vals else 0.0, 1e-3) + 2e-6
+    M0 = kabsch_rmsd_pairs(c, None).cpu().numpy()                           # no mask
+    if S >= 2:
+        want = kabsch_oracle.kabsch_rmsd(ens[0].astype(np.float64), ens[S - 1].astype(np.float64), np.ones(L))
+        assert abs(M0[0, S - 1] - want) <= 1e-5 * want + 2e-6
