@@ -239,24 +239,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
     const int r0 = pw * 8 + (lane >> 3);
     int stage = 0;
     uint32_t phase = 0;
-    struct Meta { int nr[RPT], nc[RPT]; float d2[RPT]; };
+    // Row metadata is kept lane-distributed (lane l: edge 8 pw + (l & 7) of the current / the next tile, three registers
+    // each) and handed to its users by shuffles at every use: kept per user lane it was spilled right after the loads,
+    // which parked every producer warp for a full global-load latency once per tile.
+    struct Meta { int r, c; float d; };
     auto load_meta = [&](int tile, Meta& m) {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        int64_t e = (int64_t)tile * TILE_M + r0 + 4 * i;
-        e = e < p.E ? e : p.E - 1;                 // tail rows recompute the last edge; the epilogue drops them
-        m.nr[i] = __ldg(p.row + e);
-        m.nc[i] = __ldg(p.col + e);
-        m.d2[i] = __ldg(p.d2 + e);
-      }
+      int64_t e = (int64_t)tile * TILE_M + pw * 8 + (lane & 7);
+      e = e < p.E ? e : p.E - 1;                   // tail rows recompute the last edge; the epilogue drops them
+      m.r = __ldg(p.row + e);
+      m.c = __ldg(p.col + e);
+      m.d = __ldg(p.d2 + e);
     };
     uint4 pfA[2][RPT], pfB[2][RPT];
     auto issue = [&](const Meta& m, int kc, int slot) {
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
+        const int nr = __shfl_sync(0xffffffffu, m.r, (lane >> 3) + 4 * i);
+        const int nc = __shfl_sync(0xffffffffu, m.c, (lane >> 3) + 4 * i);
         if (dbg & 1) { pfA[slot][i] = pfB[slot][i] = make_uint4(0u, 0u, 0u, 0u); continue; }
-        pfA[slot][i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)m.nr[i] * 2 * H + kc * KCHUNK + chunk * 8));
-        pfB[slot][i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)m.nc[i] * 2 * H + H + kc * KCHUNK + chunk * 8));
+        pfA[slot][i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)nr * 2 * H + kc * KCHUNK + chunk * 8));
+        pfB[slot][i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)nc * 2 * H + H + kc * KCHUNK + chunk * 8));
       }
     };
     Meta mc, mn;
@@ -275,6 +277,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
         continue;
       }
       if (next_tile < p.num_tiles) load_meta(next_tile, mn);
+      float d2r[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) d2r[i] = __shfl_sync(0xffffffffu, mc.d, (lane >> 3) + 4 * i);
 #pragma unroll
       for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
         if (kc + 1 < NUM_KCHUNKS) issue(mc, kc + 1, (kc + 1) & 1);
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
           add_f16x8_to_f32(pfA[kc & 1][i], pfB[kc & 1][i], s8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float hu = fmaf(wd8[j], mc.d2[i], s8[j]);
+            const float hu = fmaf(wd8[j], d2r[i], s8[j]);
             o8[j] = (dbg & 16) ? hu : silu_h(hu);
           }
           out[i] = pack8(o8);
