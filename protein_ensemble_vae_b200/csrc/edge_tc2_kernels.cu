@@ -70,7 +70,7 @@ struct SmemL {
 };
 using SmemT = SmemL<2, 256, 8 * 8192>;   // fwd1 (training): 2-stage ring + 8 x (4 KB hv rows | 4 KB m rows) image staging
 using SmemTI = SmemL<4, 256, 8 * 4096>;  // fwd1 (inference, hv not written): 4-stage ring + 8 x 4 KB m rows
-using SmemB2 = SmemL<4, 256, 8 * 4096>;  // bwd2: 4-stage ring + 8 x 4 KB image staging (ghv rows)
+using SmemB2 = SmemL<2, 256, 8 * 8192>;  // bwd2: 2-stage ring + 8 x 2 x 4 KB image buffers (hv in by TMA, ghv out in place)
 using SmemB1 = SmemL<2, 256, 16 * 4096>;  // bwd1: 2-stage ring (TMA-fed) + 16 x 2 x 2 KB row-box staging for the store of ghu
 
 struct Bars {
@@ -738,19 +738,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
     const int sw = f & 7;
     float dbacc = 0.f;
-    // byte offsets inside a tile image of the two 16-byte chunks (8 edges each) of step `pr` of batch `cb` for this
-    // thread's feature row
-    auto chunk_off = [&](int cb, int pr, int k) -> uint32_t {
-      return img_row + (uint32_t)((cb >> 1) * 8192) + (uint32_t)((((cb & 1) * 4 + 2 * pr + k) ^ sw) << 4);
-    };
-    auto load_hv = [&](const uint8_t* img, int cb, int pr, uint4 (&q)[2]) {
-      q[0] = __ldg(reinterpret_cast<const uint4*>(img + chunk_off(cb, pr, 0)));
-      q[1] = __ldg(reinterpret_cast<const uint4*>(img + chunk_off(cb, pr, 1)));
-    };
     // The CTA's tiles are walked as a flat sequence of 32-edge batches (4 per tile), each in two steps of 16 edges
     // (one 32-byte pair of the thread's image row, 16 TMEM columns).  Row ids are fetched two batches ahead, the
-    // gagg values of a batch's first / last row one batch ahead, hv one batch (two steps) ahead.
+    // gagg values of a batch's first / last row one batch ahead.
+    // hv arrives by TMA: this warp's 32 feature rows x 64 edges ("half" h of the flat sequence: tile h / 2, edge half
+    // h & 1) are 4 KB contiguous in the image and land in one of the warp's two 4 KB buffers; ghv overwrites them in
+    // place (every thread rewrites exactly the chunks it read) and leaves by one TMA bulk store per half.  A buffer is
+    // refilled one and a half batches before it is needed, after its store has been read out.  No per-lane global
+    // loads of hv, no registers held across the prefetch distance.
     const int nb = 4 * ((p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+    const int nh = nb >> 1;
     auto tile_of = [&](int bi) { return (int)blockIdx.x + (bi >> 2) * (int)gridDim.x; };
     auto batch_row = [&](int bi) -> int {
       const int64_t e = (int64_t)tile_of(bi) * TILE_M + (bi & 3) * 32 + lane;
@@ -761,17 +758,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       gF = rF >= 0 ? __ldg(gaggcol + (int64_t)rF * H) : 0.f;
       gL = rL >= 0 ? __ldg(gaggcol + (int64_t)rL * H) : 0.f;
     };
+    uint8_t* buf0 = smem + SmemB2::STG_OFF + warp * 8192;
+    uint64_t* hvbar = reinterpret_cast<uint64_t*>(smem + SmemB2::BAR_OFF + 128) + warp * 2;
+    const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
+    auto arm = [&](int h) {                        // lane 0: fetch half h into buffer h & 1
+      uint64_t* bar = hvbar + (h & 1);
+      mbar_arrive_expect_tx(bar, 4096);
+      bulk_g2s(buf0 + (h & 1) * 4096, p.hvT + (int64_t)tile_of(2 * h) * TILE_IMG_BYTES + img_blk + (h & 1) * 8192, 4096, bar);
+    };
+    if (lane == 0) {
+      mbar_init(hvbar, 1);
+      mbar_init(hvbar + 1, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+      if (!(dbg & 4)) {
+        if (nh > 0) arm(0);
+        if (nh > 1) arm(1);
+      }
+    }
+    __syncwarp();
     int row_c = batch_row(0), row_n = nb > 1 ? batch_row(1) : -1;
     float gaF, gaL, gaFn = 0.f, gaLn = 0.f;
     batch_ga(row_c, gaF, gaL);
-    uint4 hvq[2][2];                               // hv pair `pr` of the batch in flight: loaded one batch ahead
-    load_hv(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES, 0, 0, hvq[0]);
-    load_hv(p.hvT + (int64_t)blockIdx.x * TILE_IMG_BYTES, 0, 1, hvq[1]);
-    uint8_t* stg = smem + SmemB2::STG_OFF + warp * 4096;      // staging of this warp's 32 rows x 64 edges (4 KB)
-    const uint32_t img_blk = (uint32_t)((f >> 6) * 16384 + (q & 1) * 4096);
 #pragma unroll 1
     for (int bi = 0; bi < nb; ++bi) {
-      const int cb = bi & 3, it = bi >> 2, acc = it & 1;
+      const int cb = bi & 3, it = bi >> 2, acc = it & 1, h = bi >> 1;
       const int tile = tile_of(bi);
       const int row_nn = bi + 2 < nb ? batch_row(bi + 2) : -1;
       if (bi + 1 < nb) batch_ga(row_n, gaFn, gaLn);
@@ -794,28 +805,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       const uint32_t low = bm - 1u;                // edges before the boundary (all 32 when there is none)
       float ga_run = gaF;                          // several boundaries: running value / row
       int r_run = __shfl_sync(0xffffffffu, row_c, 0);
-      uint8_t* stg_row = stg + lane * 128;
-      if (!(dbg & 2) && (cb & 1) == 0) {
-        if (lane == 0) bulk_wait_read();           // the previous bulk copy has read the staging buffer
-        __syncwarp();
+      uint8_t* my = buf0 + (h & 1) * 4096 + lane * 128;
+      if ((cb & 1) == 0) {
+        if (!(dbg & 4)) {
+          mbar_wait(hvbar + (h & 1), (h >> 1) & 1);   // this half of hv has landed
+        } else if (!(dbg & 2)) {
+          if (lane == 0) bulk_wait_read();
+          __syncwarp();
+        }
       }
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr) {
         uint32_t raw[16];
         tmem_ld16_issue(lane_addr + acc * H + cb * 32 + pr * 16, raw);
+        const int c = (cb & 1) * 4 + 2 * pr;
+        uint4* p0 = reinterpret_cast<uint4*>(my + ((c ^ sw) << 4));
+        uint4* p1 = reinterpret_cast<uint4*>(my + (((c + 1) ^ sw) << 4));
         // r(hv) of the 16 edges while the TMEM load is in flight
         float r[16];
         {
           float h8[8];
-          unpack8(hvq[pr][0], h8);
+          unpack8(*p0, h8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = silu_grad_r(h8[j]);
-          unpack8(hvq[pr][1], h8);
+          unpack8(*p1, h8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[8 + j] = silu_grad_r(h8[j]);
         }
-        if (bi + 1 < nb && !(dbg & 4))              // the same step of the next batch (two 16-edge steps ahead)
-          load_hv(p.hvT + (int64_t)tile_of(bi + 1) * TILE_IMG_BYTES, (bi + 1) & 3, pr, hvq[pr]);
         tmem_wait();
         if (cb == 3 && pr == 1) {
           tc_fence_before();
@@ -840,19 +856,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         for (int j = 0; j < 16; ++j) gv[j] = fmaf(gv[j], r[j], gv[j]);
         dbacc += ((gv[0] + gv[1]) + (gv[2] + gv[3])) + ((gv[4] + gv[5]) + (gv[6] + gv[7])) +
                  (((gv[8] + gv[9]) + (gv[10] + gv[11])) + ((gv[12] + gv[13]) + (gv[14] + gv[15])));
-        if (!(dbg & 2)) {                           // ghv -> staging (swizzled chunk positions of the image row)
+        {                                           // ghv over hv, same chunks
           const float lo8[8] = {gv[0], gv[1], gv[2], gv[3], gv[4], gv[5], gv[6], gv[7]};
           const float hi8[8] = {gv[8], gv[9], gv[10], gv[11], gv[12], gv[13], gv[14], gv[15]};
-          const int c = (cb & 1) * 4 + 2 * pr;
-          *reinterpret_cast<uint4*>(stg_row + ((c ^ sw) << 4)) = pack8(lo8);
-          *reinterpret_cast<uint4*>(stg_row + (((c + 1) ^ sw) << 4)) = pack8(hi8);
+          *p0 = pack8(lo8);
+          *p1 = pack8(hi8);
+        }
+        if (pr == 0 && (cb & 1) == 0 && h >= 1 && h + 1 < nh && !(dbg & 4)) {
+          // the other buffer (half h - 1) was handed to its store one batch step ago: refill it with half h + 1
+          if (lane == 0) {
+            bulk_wait_read();
+            arm(h + 1);
+          }
         }
       }
-      if (!(dbg & 2) && (cb & 1)) {                 // 32 rows x 64 edges complete: one 4 KB TMA bulk store
+      if (cb & 1) {                                 // 32 rows x 64 edges complete: one 4 KB TMA bulk store
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0)
-          bulk_s2g(p.ghvT + (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192, stg, 4096);
+        if (lane == 0 && !(dbg & 2))
+          bulk_s2g(p.ghvT + (int64_t)tile * TILE_IMG_BYTES + img_blk + (cb >> 1) * 8192, buf0 + (h & 1) * 4096, 4096);
       }
       row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
     }
