@@ -1191,33 +1191,38 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
       for (int j = 0; j < 8; ++j) cs0[j] = cs1[j] = 0.f;
       uint4 pf[4];
       float gwv[4];
-      auto issue = [&](int hi) {
+      auto issue = [&](int hi, int g) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 2 * g; i < 2 * g + 2; ++i) {
           const int64_t e = (int64_t)tile_of(hi) * TILE_M + (hi & 1) * 64 + rl0 + 4 * i;
           const int64_t ec = e < p.E ? e : p.E - 1;
           pf[i] = __ldg(reinterpret_cast<const uint4*>(p.hs + ec * H + c0));
           gwv[i] = e < p.E ? __ldg(p.gw + e) : 0.f;
         }
       };
-      issue(0);
+      issue(0, 0);
+      issue(0, 1);
       for (int hi = 0; hi < nh; ++hi) {
         uint4 out[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float h8[8], o8[8];
-          unpack8(pf[i], h8);
+        for (int g = 0; g < 2; ++g) {                // rows {0,1} then {2,3}: each pair is re-issued for half tile hi + 1
+#pragma unroll                                       // as soon as it has been consumed
+          for (int i = 2 * g; i < 2 * g + 2; ++i) {
+            float h8[8], o8[8];
+            unpack8(pf[i], h8);
+            const float gwi = gwv[i];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t;
-            const float r = silu_grad_r(h8[j], t);
-            o8[j] = gwv[i] * fmaf(v8[j], r, v8[j]);
-            cs0[j] += o8[j];
-            cs1[j] = fmaf(gwv[i], t, cs1[j]);
+            for (int j = 0; j < 8; ++j) {
+              float t;
+              const float r = silu_grad_r(h8[j], t);
+              o8[j] = gwi * fmaf(v8[j], r, v8[j]);
+              cs0[j] += o8[j];
+              cs1[j] = fmaf(gwi, t, cs1[j]);
+            }
+            out[i] = pack8(o8);
           }
-          out[i] = pack8(o8);
+          if (hi + 1 < nh) issue(hi + 1, g);
         }
-        if (hi + 1 < nh) issue(hi + 1);
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* st = smem + stage * WG_STAGE_BYTES + cq * 8192;
 #pragma unroll
@@ -1253,30 +1258,34 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
           ddn[i] = __ldg(p.d2 + e);
         }
       };
-      auto issue = [&]() {
+      auto issue = [&](int g) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 2 * g; i < 2 * g + 2; ++i) {
           pfA[i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)nr[i] * 2 * H + c0));
           pfB[i] = __ldg(reinterpret_cast<const uint4*>(p.ABh + (int64_t)nc[i] * 2 * H + H + c0));
         }
       };
       load_meta(0);
-      issue();
+      issue(0);
+      issue(1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dd[i] = ddn[i];
       if (nh > 1) load_meta(1);
       for (int hi = 0; hi < nh; ++hi) {
         uint4 out[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float s8[8], o8[8];
-          add_f16x8_to_f32(pfA[i], pfB[i], s8);
+        for (int g = 0; g < 2; ++g) {                // rows {0,1} then {2,3}: each pair is re-issued for half tile hi + 1
+#pragma unroll                                       // (metadata in nr / nc / ddn) as soon as it has been consumed
+          for (int i = 2 * g; i < 2 * g + 2; ++i) {
+            float s8[8], o8[8];
+            add_f16x8_to_f32(pfA[i], pfB[i], s8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o8[j] = silu_h(fmaf(v8[j], dd[i], s8[j]));
-          out[i] = pack8(o8);
+            for (int j = 0; j < 8; ++j) o8[j] = silu_h(fmaf(v8[j], dd[i], s8[j]));
+            out[i] = pack8(o8);
+          }
+          if (hi + 1 < nh) issue(g);
         }
         if (hi + 1 < nh) {
-          issue();                                   // operands of half tile hi + 1 (its metadata is in nr / nc / ddn)
 #pragma unroll
           for (int i = 0; i < 4; ++i) dd[i] = ddn[i];
           if (hi + 2 < nh) load_meta(hi + 2);
