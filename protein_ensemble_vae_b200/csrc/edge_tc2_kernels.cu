@@ -714,7 +714,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
           float h8[8], o8[8];
           unpack8(pf[kc & 1][i], h8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o8[j] = gwc[i] * fmaf(w8[j], silu_grad_r(h8[j]), w8[j]);
+          for (int j = 0; j < 8; j += 2) {
+            const float2 w2 = make_float2(w8[j], w8[j + 1]);
+            const float2 o = fmul2(splat2(gwc[i]), ffma2(w2, silu_grad_r2(make_float2(h8[j], h8[j + 1])), w2));
+            o8[j] = o.x;
+            o8[j + 1] = o.y;
+          }
           out[i] = pack8(o8);
         }
         mbar_wait(&B.empty[stage], phase ^ 1);
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 128);
     const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
     const int sw = f & 7;
-    float dbacc = 0.f;
+    float2 dbacc2 = make_float2(0.f, 0.f);
     // The CTA's tiles are walked as a flat sequence of 32-edge batches (4 per tile), each in two steps of 16 edges
     // (one 32-byte pair of the thread's image row, 16 TMEM columns).  Row ids are fetched two batches ahead, the
     // gagg values of a batch's first / last row one batch ahead.
@@ -822,15 +827,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         uint4* p0 = reinterpret_cast<uint4*>(my + ((c ^ sw) << 4));
         uint4* p1 = reinterpret_cast<uint4*>(my + (((c + 1) ^ sw) << 4));
         // r(hv) of the 16 edges while the TMEM load is in flight
-        float r[16];
+        float2 r[8];
         {
           float h8[8];
           unpack8(*p0, h8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = silu_grad_r(h8[j]);
+          for (int j = 0; j < 4; ++j) r[j] = silu_grad_r2(make_float2(h8[2 * j], h8[2 * j + 1]));
           unpack8(*p1, h8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[8 + j] = silu_grad_r(h8[j]);
+          for (int j = 0; j < 4; ++j) r[4 + j] = silu_grad_r2(make_float2(h8[2 * j], h8[2 * j + 1]));
         }
         tmem_wait();
         if (cb == 3 && pr == 1) {
@@ -840,7 +845,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         float gv[16];
         if (simple) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) gv[j] = __uint_as_float(raw[j]) + (((low >> (16 * pr + j)) & 1u) ? gaF : gaL);
+          for (int j = 0; j < 16; j += 2) {
+            const float2 g = fadd2(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])),
+                                   make_float2(((low >> (16 * pr + j)) & 1u) ? gaF : gaL,
+                                               ((low >> (16 * pr + j + 1)) & 1u) ? gaF : gaL));
+            gv[j] = g.x;
+            gv[j + 1] = g.y;
+          }
         } else {                                   // several short segments (not a banded graph): edge by edge
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -852,10 +863,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
             gv[j] = __uint_as_float(raw[j]) + ga_run;
           }
         }
+        {
+          float2 g2[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gv[j] = fmaf(gv[j], r[j], gv[j]);
-        dbacc += ((gv[0] + gv[1]) + (gv[2] + gv[3])) + ((gv[4] + gv[5]) + (gv[6] + gv[7])) +
-                 (((gv[8] + gv[9]) + (gv[10] + gv[11])) + ((gv[12] + gv[13]) + (gv[14] + gv[15])));
+          for (int j = 0; j < 8; ++j) {
+            const float2 g = make_float2(gv[2 * j], gv[2 * j + 1]);
+            g2[j] = ffma2(g, r[j], g);
+            gv[2 * j] = g2[j].x;
+            gv[2 * j + 1] = g2[j].y;
+          }
+          const float2 s = fadd2(fadd2(fadd2(g2[0], g2[1]), fadd2(g2[2], g2[3])), fadd2(fadd2(g2[4], g2[5]), fadd2(g2[6], g2[7])));
+          dbacc2 = fadd2(dbacc2, s);
+        }
         {                                           // ghv over hv, same chunks
           const float lo8[8] = {gv[0], gv[1], gv[2], gv[3], gv[4], gv[5], gv[6], gv[7]};
           const float hi8[8] = {gv[8], gv[9], gv[10], gv[11], gv[12], gv[13], gv[14], gv[15]};
@@ -879,7 +898,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
     }
     if (lane == 0) bulk_wait_all();
-    atomicAdd(p.db2h + f, dbacc);
+    atomicAdd(p.db2h + f, dbacc2.x + dbacc2.y);
   }
   PEV_TC2_EPILOGUE()
 }

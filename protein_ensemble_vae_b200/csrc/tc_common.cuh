@@ -163,6 +163,47 @@ __device__ __forceinline__ float silu_grad_r(float h, float& f) {
   return fmaf(h, fmaf(-t, t, 1.0f), t);
 }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 -- two lanes of fp32 math per issue slot).  The CUDA-core roles
+// of these kernels are bound by issue slots, not by the FMA pipe, so the element-wise epilogue / producer math is
+// written on pairs.  Same rounding as the scalar forms (fma.rn / add.rn / mul.rn per component).
+__device__ __forceinline__ uint64_t f2_pack(float2 a) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 tanh_fast2(float2 h) { return make_float2(tanh_fast(h.x), tanh_fast(h.y)); }
+__device__ __forceinline__ float2 silu_h2(float2 h) { return ffma2(h, tanh_fast2(h), h); }
+__device__ __forceinline__ float2 silu_grad_r2(float2 h) {
+  const float2 t = tanh_fast2(h);
+  return ffma2(h, ffma2(make_float2(-t.x, -t.y), t, splat2(1.0f)), t);
+}
+__device__ __forceinline__ float2 silu_grad_r2(float2 h, float2& f) {
+  const float2 t = tanh_fast2(h);
+  f = ffma2(h, t, h);
+  return ffma2(h, ffma2(make_float2(-t.x, -t.y), t, splat2(1.0f)), t);
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of 128-byte row `r` inside a SWIZZLE_128B tile whose 8-row groups are
 // 1024 B apart
 __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
