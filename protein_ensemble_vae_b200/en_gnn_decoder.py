@@ -179,12 +179,14 @@ class EGNNDecoder(nn.Module):
         # pack valid residues: z = [z_g (replicated) | z_l]   (:233-234)
         zl_flat = z_l.reshape(B * L, -1)
         zl_p = zl_flat if flat_idx is None else zl_flat.index_select(0, flat_idx)
-        conf_of = torch.repeat_interleave(torch.arange(B, device=device),
-                                          torch.tensor(lengths, device=device), output_size=N)
+        g, dinv = self._graph(lengths, device)
+        conf_of = g.conf_of                                     # cached with the band graph: no per-step H2D copy
+        if conf_of is None:
+            conf_of = torch.repeat_interleave(torch.arange(B, device=device),
+                                              torch.tensor(lengths, device=device), output_size=N)
         z = torch.cat([z_g.index_select(0, conf_of), zl_p], -1)
         x = self._run(self.latent_to_coords, z)                 # :237
         h = self._run(self.input_embedding, z)                  # :240
-        g, dinv = self._graph(lengths, device)
         for layer in self.layers:                               # :248-250
             h, x = _layer_forward(layer, h, x, g, dinv, self.precision)
             h = self.dropout(h)

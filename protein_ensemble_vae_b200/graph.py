@@ -42,6 +42,7 @@ class PackedGraph:
     lengths: tuple | None = None
     sort_perm: torch.Tensor | None = None   # generic graphs: positions of the sorted edges in the caller's order
     starts: torch.Tensor | None = None      # [N] bool, True at the first node of each conformer
+    conf_of: torch.Tensor | None = None     # [N] int64, conformer of each packed node (band graphs; cached with them)
 
     def edge_index(self) -> torch.Tensor:
         """int64 ``[2, E]`` in the reference's layout."""
@@ -82,7 +83,8 @@ def band_graph(lengths, max_neighbors: int, device, cache: bool = True) -> Packe
         first = [int(c) for c, v in zip(cu[:-1], lengths) if v > 0]
         if first:
             starts[torch.tensor(first, device=dev)] = True
-    g = PackedGraph(N, E, row_ptr, row, col, row_ptr, csc, dinv, cu_d, lengths, starts=starts)
+        conf_of = torch.repeat_interleave(torch.arange(B, device=dev), torch.tensor(lengths, device=dev), output_size=N)
+    g = PackedGraph(N, E, row_ptr, row, col, row_ptr, csc, dinv, cu_d, lengths, starts=starts, conf_of=conf_of)
     if cache:
         if len(_BAND_CACHE) > 64:
             _BAND_CACHE.clear()
