@@ -55,7 +55,9 @@ def synth_batch(B, L, z_g, z_l, seed, device="cpu", pin=False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms 200`
+    process started before the warm-up (its start-up cost stays outside the timed region; re-spawning nvidia-smi for
+    every sample stalls kernel launches for milliseconds), rows kept only if they arrive inside [mark_start, mark_stop]."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -63,17 +65,29 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.all_rows, self.rows, self.proc = index, [], [], None
+        self.t0 = self.t1 = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.all_rows.append((time.time(), [c.strip() for c in line.strip().split(",")]))
+        except Exception:
+            pass
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
+        time.sleep(0.25)                           # let the sample in flight arrive
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for t, r in self.all_rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.25]
+        self.rows = rows or [r for _, r in self.all_rows[-2:]]
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
@@ -207,17 +221,19 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(args.warmup):
-        step(resident)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(resident)
+    torch.cuda.synchronize()
+    sampler.mark_start()
     _lib.PROFILE = {}
     n0 = lib.launch_count()
     ms = timed(lambda: step(resident), args.steps)
     launches = lib.launch_count() - n0
     prof, _lib.PROFILE = _lib.PROFILE, None
-    sampler.stop_flag = True
+    sampler.mark_stop()
     value = B * world * args.steps / (ms / 1e3)
 
     # end to end: pinned host buffers -> device every step (DevicePrefetcher: the copy of step i+1 runs on a side
