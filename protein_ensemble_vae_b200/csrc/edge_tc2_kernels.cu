@@ -15,6 +15,13 @@
 //   fwd1  hu = Ah_i + Bh_j + wdh d2 ; a = silu  --GEMM W2h (transposed)-->  hv (+b2h), m = silu(hv) -> HBM tile images
 //         (hv only when a backward pass follows) ; agg[row] += m (in-thread segment sums, one RED per segment per feature)
 //   fwd2  m (TMA, A operand MN-major)  --GEMM W5h-->  hs (+b5h) [-> HBM, training], t = silu, w[e] = t.w6 + b6
+//   bwd2  ghs = gw w6 (1 + r(hs))  --GEMM W5h^T (transposed)-->  ghv = (. + gagg[row]) (1 + r(hv)) -> HBM tile image
+//         (hv arrives by TMA into the warp's staging buffer and is overwritten in place) ; db2 += sum_e ghv
+//   bwd1  ghv (TMA, A operand MN-major)  --GEMM W2h^T-->  ghu = . (1 + r(hu)), hu rebuilt from ABh / d2 -> HBM rows,
+//         gd2[e] = ghu . wdh
+//   wgrad5 / wgrad2  dW5 = ghs^T m, dW2 = ghv^T a : split-K over edges, the whole 256 x 256 fp32 matrix accumulated
+//         in TMEM over a CTA's tiles, per-CTA partials + fixed-order reduction
+//   sums  row / column segment sums of ghu (gA | gB) and sum_e d2 ghu (gwd), one warp per node
 #include <cuda.h>          // CUtensorMap types only: the encoder is resolved at run time (no libcuda link dependency)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
