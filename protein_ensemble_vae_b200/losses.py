@@ -241,6 +241,21 @@ def clash_loss(pred_N, pred_CA, pred_C, mask, clash_dist=3.2, soft_margin=0.5):
     return _terms(cfg, mask, pred_N=pred_N, pred_CA=pred_CA, pred_C=pred_C)[T_CLASH]
 
 
+_COEF_CACHE: dict = {}
+
+
+def _coef_vector(values: tuple, device):
+    """Device copy of a coefficient vector and the mask of its non-zero entries, cached per (values, device)."""
+    key = (values, str(device))
+    hit = _COEF_CACHE.get(key)
+    if hit is None:
+        if len(_COEF_CACHE) > 256:
+            _COEF_CACHE.clear()
+        coef = torch.tensor(values, dtype=torch.float32, device=device)
+        hit = _COEF_CACHE[key] = (coef, coef != 0)
+    return hit
+
+
 def compute_total_loss(pred_N, pred_CA, pred_C, pred_seq, target_N, target_CA, target_C, target_seq_labels,
                        mask, mu_g, lv_g, mu_l, lv_l,
                        target_dihedrals, klw_g, klw_l, w_pair, pair_stride,
@@ -256,9 +271,29 @@ def compute_total_loss(pred_N, pred_CA, pred_C, pred_seq, target_N, target_CA, t
     loss_dihedral = cons + t[T_OMEGA]
     loss_bond = t[T_BOND_NCA] + t[T_BOND_CAC] + (2 * t[T_BOND_CN] if multi else 0.0)
     loss_angle = t[T_ANG_NCAC] + (2.0 * (t[T_ANG_CNCA] + t[T_ANG_CACN]) if multi else 0.0)
-    loss = (w_rec * loss_rec + w_pair * t[T_PAIR] + klw_g * t[T_KL_G] + klw_l * t[T_KL_L]
-            + w_dihedral * loss_dihedral + w_rama * t[T_RAMA] + w_bond * loss_bond
-            + w_angle * loss_angle + w_seq * t[T_SEQ] + w_clash * t[T_CLASH])
+    ws = (w_rec, w_pair, klw_g, klw_l, w_dihedral, w_rama, w_bond, w_angle, w_seq, w_clash)
+    if all(isinstance(w, (int, float)) for w in ws):
+        # Scalar weights: the same weighted sum as one dot product with a cached coefficient vector.  The component
+        # expressions above stay available in the dict, but `total.backward()` no longer walks ~20 select / mul / add
+        # nodes (each a zero-fill + copy + add of a [NUM_TERMS] tensor: ~100 launch-bound kernels per step).
+        c = [0.0] * NUM_TERMS
+        c[T_REC_CA], c[T_REC_N], c[T_REC_C] = w_rec, 0.5 * w_rec, 0.5 * w_rec
+        c[T_PAIR], c[T_KL_G], c[T_KL_L] = w_pair, klw_g, klw_l
+        c[T_OMEGA] = w_dihedral
+        if target_dihedrals is not None:
+            c[T_DIH_CONS] = w_dihedral
+        c[T_RAMA], c[T_SEQ], c[T_CLASH] = w_rama, w_seq, w_clash
+        c[T_BOND_NCA] = c[T_BOND_CAC] = w_bond
+        c[T_ANG_NCAC] = w_angle
+        if multi:
+            c[T_BOND_CN] = 2 * w_bond
+            c[T_ANG_CNCA] = c[T_ANG_CACN] = 2.0 * w_angle
+        coef, used = _coef_vector(tuple(float(v) for v in c), t.device)
+        loss = torch.dot(torch.where(used, t, t.new_zeros(())), coef)     # unused terms may be undefined (0/0)
+    else:
+        loss = (w_rec * loss_rec + w_pair * t[T_PAIR] + klw_g * t[T_KL_G] + klw_l * t[T_KL_L]
+                + w_dihedral * loss_dihedral + w_rama * t[T_RAMA] + w_bond * loss_bond
+                + w_angle * loss_angle + w_seq * t[T_SEQ] + w_clash * t[T_CLASH])
     return {
         "total": loss,
         "reconstruction": loss_rec,
