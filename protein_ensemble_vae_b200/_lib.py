@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpev_b200.so")
+LIB_PATH = os.environ.get("PEV_B200_LIB") or os.path.join(HERE, "libpev_b200.so")   # override: A/B builds of csrc/
 NUM_TERMS = 17
 
 # enum pev_term

@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
           }
           out[i] = pack8(o8);
         }
-        mbar_wait(&B.empty[stage], phase ^ 1);
+        mbar_wait_backoff<64>(&B.empty[stage], phase ^ 1);
         uint8_t* st = sA + stage * STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) *reinterpret_cast<uint4*>(st + sw128_offset(r0 + 4 * i, chunk)) = out[i];
@@ -747,7 +747,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     const int f = mh * 128 + q * 32 + lane;
     const float* gaggcol = p.gagg + f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 128);
-    const uint32_t img_row = (uint32_t)((f >> 6) * 16384 + ((f & 63) >> 3) * 1024 + (f & 7) * 128);
     const int sw = f & 7;
     float2 dbacc2 = make_float2(0.f, 0.f);
     // The CTA's tiles are walked as a flat sequence of 32-edge batches (4 per tile), each in two steps of 16 edges

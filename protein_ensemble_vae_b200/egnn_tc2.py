@@ -29,13 +29,14 @@ def packed_weight_scaled(W: torch.Tensor, scale: float, transpose: bool = False,
     """
     tag = ("T" if transpose else "N") + repr(float(scale))
     key = (W.data_ptr(), W._version)
-    if cache is not None and cache.get("key" + tag) == key:
+    capturing = W.is_cuda and torch.cuda.is_current_stream_capturing()   # a CUDA graph must contain the pack kernel
+    if cache is not None and cache.get("key" + tag) == key and not capturing:
         return cache["img" + tag]
     Wc = f32c(W.detach())
     with torch.cuda.device_of(Wc):
         out = torch.empty(H * H, dtype=torch.bfloat16, device=W.device)
         _lib.lib().call("pev_pack_weight_bf16_scaled", ptr(Wc), int(transpose), float(scale), ptr(out), stream(Wc))
-    if cache is not None:
+    if cache is not None and not capturing:
         cache["key" + tag], cache["img" + tag] = key, out
     return out
 
