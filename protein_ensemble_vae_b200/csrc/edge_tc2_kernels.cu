@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
     auto arm = [&](int h) {                        // lane 0: fetch half h into buffer h & 1
       uint64_t* bar = hvbar + (h & 1);
       mbar_arrive_expect_tx(bar, 4096);
-      bulk_g2s(buf0 + (h & 1) * 4096, p.hvT + (int64_t)tile_of(2 * h) * TILE_IMG_BYTES + img_blk + (h & 1) * 8192, 4096, bar);
+      bulk_g2s_stream(buf0 + (h & 1) * 4096, p.hvT + (int64_t)tile_of(2 * h) * TILE_IMG_BYTES + img_blk + (h & 1) * 8192, 4096, bar);
     };
     if (lane == 0) {
       mbar_init(hvbar, 1);
@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p,
         for (int kc = 0; kc < NUM_KCHUNKS; ++kc) {
           mbar_wait_backoff<32>(&B.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&B.full[stage], STAGE_BYTES);
-          bulk_g2s(sA + stage * STAGE_BYTES, p.ghvT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES, STAGE_BYTES,
+          bulk_g2s_stream(sA + stage * STAGE_BYTES, p.ghvT + (int64_t)tile * TILE_IMG_BYTES + kc * STAGE_BYTES, STAGE_BYTES,
                    &B.full[stage]);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -1368,7 +1368,7 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
         const uint8_t* src = img + (int64_t)tile_of(hi) * TILE_IMG_BYTES + (hi & 1) * 8192;
         uint8_t* dst = smem + stage * WG_STAGE_BYTES + (MODE == 5 ? WG_HALF_BYTES : 0);
 #pragma unroll
-        for (int fq = 0; fq < 4; ++fq) bulk_g2s(dst + fq * 8192, src + fq * 16384, 8192, &full[stage]);
+        for (int fq = 0; fq < 4; ++fq) bulk_g2s_stream(dst + fq * 8192, src + fq * 16384, 8192, &full[stage]);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
