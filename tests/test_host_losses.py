@@ -128,3 +128,33 @@ def test_cuda_required_without_test_seam():
     x = torch.zeros(1, 4, 3)
     with pytest.raises(RuntimeError):
         pl.rmsd_loss(x, x, torch.ones(1, 4))
+
+
+def test_total_loss_scalar_and_tensor_weights_agree(bk):
+    """compute_total_loss takes the weighted sum as one dot product when every weight is a Python number and as the
+    reference's expression otherwise (tensor-valued weights, e.g. an annealed KL weight kept on the device); both forms
+    give the same total and the same gradients, including L = 1 (no peptide terms) and a missing dihedral target."""
+    T32 = bk.t32
+    from protein_ensemble_vae_b200 import losses as pl
+    for tag, use_target in (("walk", True), ("compact", False)):
+        case = cases.LOSS_CASES[tag]
+        d = cases.loss_inputs(case)
+        with bk.ctx():
+            tdih = pl.compute_dihedrals_from_coords(T32(d["target_N"]), T32(d["target_CA"]), T32(d["target_C"]),
+                                                    T32(d["mask"])) if use_target else None
+            out = []
+            for tensor_weights in (False, True):
+                w = dict(cases.LOSS_WEIGHTS)
+                if tensor_weights:
+                    w["klw_l"] = torch.tensor(w["klw_l"], device=bk.dev)
+                leaves = {k: T32(d[k]).requires_grad_() for k in cases.GRAD_INPUTS}
+                res = pl.compute_total_loss(
+                    leaves["pred_N"], leaves["pred_CA"], leaves["pred_C"], leaves["pred_seq"], T32(d["target_N"]),
+                    T32(d["target_CA"]), T32(d["target_C"]), torch.tensor(d["labels"]).to(bk.dev), T32(d["mask"]),
+                    leaves["mu_g"], leaves["lv_g"], leaves["mu_l"], leaves["lv_l"], tdih, pair_stride=4, **w)
+                res["total"].backward()
+                out.append((float(res["total"].detach()), {k: v.grad.clone() for k, v in leaves.items()}))
+        (t0, g0), (t1, g1) = out
+        assert abs(t0 - t1) <= 2e-6 * abs(t1), (tag, t0, t1)
+        for k in g0:
+            assert rel_err(g0[k], g1[k]) < 1e-5, (tag, k)
