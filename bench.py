@@ -355,8 +355,8 @@ def run_gpu(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per edge of each v2 edge kernel (ncu --set full, profiles/)
-NCU_TRAFFIC_PER_EDGE = {"edge2_fwd1": 979.7, "edge2_fwd2": 955.2, "edge2_bwd2": 1502.1, "edge2_wgrad5": 1037.8,
-                        "edge2_bwd1": 984.5, "edge2_wgrad2": 547.7, "edge2_sums": 775.1}
+NCU_TRAFFIC_PER_EDGE = {"edge2_fwd1": 980.4, "edge2_fwd2": 956.6, "edge2_bwd2": 1470.9, "edge2_wgrad5": 1035.8,
+                        "edge2_bwd1": 974.9, "edge2_wgrad2": 544.8, "edge2_sums": 774.0}
 
 
 def lib_edges(L, W=40):
