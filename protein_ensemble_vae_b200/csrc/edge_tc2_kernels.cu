@@ -147,6 +147,10 @@ __device__ __forceinline__ float masked_sum32(const float (&m)[32], uint32_t msk
   for (int j = 0; j < 32; ++j) s[j & 3] += ((msk >> j) & 1u) ? m[j] : 0.f;
   return (s[0] + s[1]) + (s[2] + s[3]);
 }
+// Layout of a per-feature vector that the producers read as two float4 per (K-chunk, 16-byte column chunk): the first
+// (second) halves of the eight column chunks of a K-chunk are contiguous, so a quarter-warp's eight 16-byte reads cover
+// 128 contiguous bytes (conflict-free) instead of eight 16-byte pieces 32 bytes apart (2-way bank conflict).
+__device__ __forceinline__ int vec_slot(int k) { return ((k >> 6) * 2 + ((k >> 2) & 1)) * 32 + ((k >> 3) & 7) * 4 + (k & 3); }
 // Common prologue: barriers, TMEM, role register budgets.  Returns the TMEM base address.
 #define PEV_TC2_PROLOGUE(SM, FULL_COUNT)                                                      \
   constexpr int NUM_STAGES = SM::NSTAGE;                                                      \
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
   constexpr int M_STG_OFF = TRAIN ? 4096 : 0;
   PEV_TC2_PROLOGUE(SM, NUM_PROD_THREADS)
   float* sWd = sVec;
-  for (int k = threadIdx.x; k < H; k += NUM_THREADS) sWd[k] = 0.5f * p.wd[k];
+  for (int k = threadIdx.x; k < H; k += NUM_THREADS) sWd[vec_slot(k)] = 0.5f * p.wd[k];
   PEV_TC2_SYNC_ROLES()
 
   if (warp >= MMA_WARP && warp < PROD_WARP0) {
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fwd1_kernel(const Fwd1Params p
         if (kc + 1 < NUM_KCHUNKS) issue(mc, kc + 1, (kc + 1) & 1);
         else if (next_tile < p.num_tiles) issue(mn, 0, 0);
         const int k0 = kc * KCHUNK + chunk * 8;
-        const float4 w0 = *reinterpret_cast<const float4*>(sWd + k0), w1 = *reinterpret_cast<const float4*>(sWd + k0 + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(sWd + vec_slot(k0)), w1 = *reinterpret_cast<const float4*>(sWd + vec_slot(k0 + 4));
         const float wd8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         uint4 out[RPT];
 #pragma unroll
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
   const int dbg = DBG ? p.dbg : 0;
   PEV_TC2_PROLOGUE(SmemB2, NUM_PROD_THREADS)
   float* sW6 = sVec;
-  for (int k = threadIdx.x; k < H; k += NUM_THREADS) sW6[k] = p.w6[k];
+  for (int k = threadIdx.x; k < H; k += NUM_THREADS) sW6[vec_slot(k)] = p.w6[k];
   PEV_TC2_SYNC_ROLES()
 
   if (warp >= MMA_WARP && warp < PROD_WARP0) {
@@ -713,7 +717,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
         if (kc + 1 < NUM_KCHUNKS) issue(tile, kc + 1, (kc + 1) & 1);
         else if (next_tile < p.num_tiles) issue(next_tile, 0, 0);
         const int k0 = kc * KCHUNK + chunk * 8;
-        const float4 w0 = *reinterpret_cast<const float4*>(sW6 + k0), w1 = *reinterpret_cast<const float4*>(sW6 + k0 + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(sW6 + vec_slot(k0)), w1 = *reinterpret_cast<const float4*>(sW6 + vec_slot(k0 + 4));
         const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         uint4 out[RPT];
 #pragma unroll
