@@ -6,7 +6,6 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch
-import torch.nn.functional as F
 from protein_ensemble_vae_b200 import EGNNDecoder
 from bf16_yardstick import emulate_autocast_edge_mlp
 
