@@ -13,4 +13,5 @@ from .kabsch import ensemble_diversity, kabsch_rmsd, kabsch_rmsd_batch, kabsch_r
 from .losses import compute_total_loss  # noqa: F401
 
 __all__ = ["EGNLayer", "EGNNDecoder", "SE3EquivariantDecoder", "ResidueDecoder", "compute_total_loss",
-           "kabsch_rmsd", "kabsch_rmsd_batch", "kabsch_rmsd_pairs", "ensemble_diversity", "DevicePrefetcher", "GraphedStep", "data", "losses", "en_gnn_decoder", "graph", "kabsch"]
+           "kabsch_rmsd", "kabsch_rmsd_batch", "kabsch_rmsd_pairs", "ensemble_diversity", "DevicePrefetcher",
+           "GraphedStep", "data", "losses", "en_gnn_decoder", "graph", "graphs", "kabsch"]
