@@ -222,7 +222,7 @@ def run_gpu(args):
         return float(ms)
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("PEV_BENCH_NO_CLOCKS"):   # set under ncu: it would follow the child process
         sampler.start()
     for _ in range(args.warmup):
         step(resident)
