@@ -50,23 +50,29 @@ def egn_layer(sd, prefix, h, x, edge_index, degree_inv=None):
     return h_new, x + delta                                           # :86
 
 
-def _latent_to_coords(sd, z):
-    # models/en_gnn_decoder.py:124-132 (dropout is identity in eval)
+def _latent_to_coords(sd, z, drop=None):
+    # models/en_gnn_decoder.py:124-132 (dropout :128 is identity in eval; `drop` injects a train-mode mask)
     y = _lin(sd, "latent_to_coords.0", z)
     y = F.relu(F.layer_norm(y, (y.shape[-1],), sd["latent_to_coords.1.weight"],
                             sd["latent_to_coords.1.bias"], 1e-5))
+    if drop is not None:
+        y = drop(y, 0.5)
     y = F.relu(_lin(sd, "latent_to_coords.4", y))
     return _lin(sd, "latent_to_coords.6", y)
 
 
-def _sequence_head(sd, h):
-    # models/en_gnn_decoder.py:162-172
+def _sequence_head(sd, h, drop=None):
+    # models/en_gnn_decoder.py:162-172 (dropouts :166, :170)
     y = _lin(sd, "sequence_head.0", h)
     y = F.relu(F.layer_norm(y, (y.shape[-1],), sd["sequence_head.1.weight"],
                             sd["sequence_head.1.bias"], 1e-5))
+    if drop is not None:
+        y = drop(y, 0.5)
     y = _lin(sd, "sequence_head.4", y)
     y = F.relu(F.layer_norm(y, (y.shape[-1],), sd["sequence_head.5.weight"],
                             sd["sequence_head.5.bias"], 1e-5))
+    if drop is not None:
+        y = drop(y, 0.5)
     return _lin(sd, "sequence_head.8", y)
 
 
@@ -98,12 +104,17 @@ def num_layers_of(sd) -> int:
 
 
 def egnn_decoder(sd, z_g, z_l, mask=None, max_neighbors=20, degree_normalize=True,
-                 edge_cache=None):
+                 edge_cache=None, dropout=None):
     """Decoder forward in eval mode.  Reference: ``EGNNDecoder.forward`` (``:200-333``).
 
     Keeps the reference's per-conformer loop (F2).  ``edge_cache`` (dict) lets a
     caller reuse the banded edge list between conformers of equal length -- the
     reference rebuilds it with a Python double loop on every call.
+
+    ``dropout=(p, keep)`` restates train mode with injected masks: ``keep(site, b, rows, dim, p_site)``
+    returns the 0/1 keep mask of the ``site``-th dropout call of conformer ``b`` (call order :128, :250 per
+    layer, :166, :170); a kept value is scaled by ``1 / (1 - p_site)`` as ``nn.Dropout`` does, with
+    ``p_site = p`` after a layer (:114) and ``p / 2`` inside the heads (:128, :166, :170).
     """
     B, L, _ = z_l.shape
     dt = z_l.dtype
@@ -118,7 +129,17 @@ def egnn_decoder(sd, z_g, z_l, mask=None, max_neighbors=20, degree_normalize=Tru
         full = [torch.zeros(L, 3, dtype=dt) for _ in range(3)] + [torch.zeros(L, 20, dtype=dt)]
         if Lb > 0:
             z = torch.cat([z_g[b].unsqueeze(0).expand(Lb, -1), z_l[b, idx]], -1)   # :233-234
-            x = _latent_to_coords(sd, z)                              # :237
+            drop = None
+            if dropout is not None:
+                p_drop, keep_fn = dropout
+                site = [0]
+
+                def drop(y, frac, _b=b, _site=site):
+                    ps = p_drop * frac
+                    k = keep_fn(_site[0], _b, y.shape[0], y.shape[1], ps)
+                    _site[0] += 1
+                    return y * torch.as_tensor(k, dtype=y.dtype) / (1.0 - ps)
+            x = _latent_to_coords(sd, z, drop)                        # :237
             h = _lin(sd, "input_embedding", z)                        # :240
             key = (Lb, max_neighbors)
             if edge_cache is not None and key in edge_cache:
@@ -133,7 +154,9 @@ def egnn_decoder(sd, z_g, z_l, mask=None, max_neighbors=20, degree_normalize=Tru
                 dinv = (1.0 / deg.float()).to(dt)                     # :245 (float32 reciprocal)
             for l in range(nl):                                       # :248-250
                 h, x = egn_layer(sd, f"layers.{l}.", h, x, ei, dinv)
-            logits = _sequence_head(sd, h)                            # :253
+                if drop is not None:
+                    h = drop(h, 1.0)                                  # :250
+            logits = _sequence_head(sd, h, drop)                      # :253
             x_n, x_c = backbone_from_ca(sd, h, x)
             full[0] = full[0].index_put((idx,), x_n)                  # :313-328
             full[1] = full[1].index_put((idx,), x)

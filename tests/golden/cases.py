@@ -42,6 +42,52 @@ def decoder_inputs(case):
     return zg, zl, mask, coef
 
 
+# ------------------------------------------------------------------ BASELINE-config shapes (round 2)
+# The shapes BASELINE.json's configs name, at a batch the float64 reference finishes in a minute on CPU.
+BIG_DECODER_CASES = {
+    # tag: (z_g, z_l, hidden, layers, W, B, L, mask kind, param seed, data seed, dropout p)
+    "config2": (512, 256, 256, 6, 40, 2, 256, "ragged", 51, 52, 0.0),   # configs[1]: L=256, 6 layers
+    "config14": (512, 256, 256, 8, 40, 2, 100, "full", 53, 54, 0.0),    # configs[0]/[3]: ResidueDecoder (8 layers), L=100
+    "ragged3": (64, 32, 256, 3, 40, 3, 512, "mixed", 55, 56, 0.0),      # configs[2]: L in {512, 64, 300 with a gap}
+    "dropout": (64, 32, 256, 2, 40, 3, 60, "ragged", 57, 60, 0.1),      # train mode, injected dropout masks (data seed chosen so that no ReLU argument is within float32 rounding of 0)
+}
+BIG_WRAPPED = ("config14",)        # generated through the reference's ResidueDecoder wrapper (F1)
+
+
+def big_mask(case):
+    z_g, z_l, H, nl, W, B, L, mkind, pseed, dseed, p = case
+    if mkind == "mixed":
+        m = np.zeros((B, L), np.float32)
+        for b, n in enumerate((512, 64, 300)[:B]):
+            m[b, :n] = 1
+        m[2, 100:105] = 0                                                # interior gap (bridged by the graph)
+        return m
+    return synth.make_masks(B, L, dseed + 1, mkind)
+
+
+def big_decoder_inputs(case):
+    z_g, z_l, H, nl, W, B, L, mkind, pseed, dseed, p = case
+    rng = np.random.default_rng(dseed)
+    zg = synth.f32(rng.standard_normal((B, z_g)))
+    zl = synth.f32(rng.standard_normal((B, L, z_l)))
+    mask = big_mask(case)
+    coef = [synth.f32(rng.standard_normal((B, L, 3))) for _ in range(3)]
+    coef.append(synth.f32(rng.standard_normal((B, L, 20))))
+    return zg, zl, mask, coef
+
+
+def dropout_keep(dseed, site, b, rows, dim, p):
+    """float32 0/1 keep mask of dropout site `site` (call order inside one conformer's forward: latent_to_coords,
+    one per EGNN layer, two in sequence_head) for conformer `b`: [rows, dim]."""
+    rng = np.random.default_rng(dseed * 1000 + site * 17 + b)
+    return (rng.random((rows, dim)) >= p).astype(np.float32)
+
+
+def flat2d(g):
+    """Gradients with more than two axes are projected as [prod(leading), last]."""
+    g = np.asarray(g)
+    return g.reshape(-1, g.shape[-1]) if g.ndim > 2 else g
+
 
 LOSS_WEIGHTS = dict(klw_g=1.0, klw_l=0.5, w_pair=10.0, w_dihedral=20.0, w_rama=400.0, w_bond=500.0,
                     w_angle=500.0, w_rec=10.0, w_seq=50.0, w_clash=300.0)   # models/vae.py:39-50

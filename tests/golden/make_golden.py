@@ -141,6 +141,76 @@ def gen_decoders():
     np.savez_compressed(os.path.join(HERE, "decoders.npz"), **out)
 
 
+
+# --------------------------------------------------------------------------- decoder, BASELINE-config shapes
+class InjectedDropout:
+    """Replaces ``nn.Dropout.forward`` while the reference runs in train mode: the k-th call inside one forward is
+    site ``k % sites`` of conformer ``k // sites`` (the reference loops over conformers, models/en_gnn_decoder.py:216,
+    and every conformer visits the same dropout modules in the same order: latent_to_coords :128, one per layer :250,
+    two in sequence_head :166/:170); the keep mask comes from ``cases.dropout_keep`` instead of torch's generator."""
+
+    def __init__(self, dseed, sites):
+        self.dseed, self.sites, self.k = dseed, sites, 0
+
+    def __enter__(self):
+        self.orig = torch.nn.Dropout.forward
+        me = self
+
+        def forward(mod, x):
+            if not mod.training or mod.p == 0.0:
+                return x
+            b, site = divmod(me.k, me.sites)
+            me.k += 1
+            keep = T(cases.dropout_keep(me.dseed, site, b, x.shape[0], x.shape[1], mod.p))
+            return x * keep / (1.0 - mod.p)
+
+        torch.nn.Dropout.forward = forward
+        return self
+
+    def __exit__(self, *exc):
+        torch.nn.Dropout.forward = self.orig
+        return False
+
+
+def pack_grads_big(named_grads, out, tag, seed=4321):
+    for i, (name, g) in enumerate(sorted(named_grads.items())):
+        g = cases.flat2d(g.detach().numpy())
+        if g.ndim == 2 and g.size > 4096:
+            r1, r2 = proj_vectors(g.shape, seed + i)
+            out[f"{tag}.gproj1.{name}"] = g @ r1
+            out[f"{tag}.gproj2.{name}"] = r2 @ g
+        else:
+            out[f"{tag}.grad.{name}"] = g
+
+
+def gen_big_decoders():
+    out = {}
+    for tag, case in cases.BIG_DECODER_CASES.items():
+        z_g, z_l, H, nl, W, B, L, mkind, pseed, dseed, pdrop = case
+        params = synth.make_params(synth.decoder_param_shapes(z_g, z_l, H, nl), pseed)
+        if tag in cases.BIG_WRAPPED:       # the wrapper hard-codes hidden 256 / 8 layers / W 40 (F1)
+            assert (H, nl, W) == (256, 8, 40)
+            top = ref_dec.ResidueDecoder(z_g, z_l, hidden=64, dropout=pdrop).double()
+            dec = top.decoder.decoder
+        else:
+            top = dec = ref_dec.EGNNDecoder(z_g, z_l, hidden_dim=H, num_layers=nl, max_neighbors=W,
+                                            dropout=pdrop).double()
+        dec.load_state_dict({k: T(v) for k, v in params.items()})
+        top.train(pdrop > 0.0)
+        zg, zl, mask, coef = cases.big_decoder_inputs(case)
+        zg_t, zl_t = T(zg).requires_grad_(), T(zl).requires_grad_()
+        with InjectedDropout(dseed, nl + 3):
+            outs = top(zg_t, zl_t, mask=T(mask))
+        loss = sum((o * T(c)).sum() for o, c in zip(outs, coef))
+        loss.backward()
+        for name, o in zip(("N", "CA", "C", "logits"), outs):
+            out[f"{tag}.{name}"] = o.detach().numpy()
+        grads = {"z_g": zg_t.grad, "z_l": zl_t.grad}
+        grads.update({k: p.grad for k, p in dec.named_parameters() if p.grad is not None})
+        pack_grads_big(grads, out, tag)
+        print("big decoder case", tag, "done", flush=True)
+    np.savez_compressed(os.path.join(HERE, "decoders_big.npz"), **out)
+
 # --------------------------------------------------------------------------- losses
 def gen_losses():
     out = {}
@@ -204,6 +274,7 @@ if __name__ == "__main__":
     gen_edges()
     gen_layers()
     gen_decoders()
+    gen_big_decoders()
     gen_losses()
     gen_kabsch()
     for f in sorted(os.listdir(HERE)):

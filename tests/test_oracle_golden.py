@@ -120,6 +120,32 @@ def test_decoder_matches_reference(tag):
     check_grads(grads, gold, tag, 1e-9)
 
 
+@pytest.mark.parametrize("tag", list(mg_cases.BIG_DECODER_CASES))
+def test_big_decoder_matches_reference(tag):
+    """BASELINE-config shapes (configs[1]: 6 layers x L=256; configs[0]/[3]: 8 layers x L=100 through the reference's
+    ResidueDecoder; configs[2]: ragged 512/64/300) and the train-mode path with injected dropout masks."""
+    gold = load("decoders_big.npz")
+    case = mg_cases.BIG_DECODER_CASES[tag]
+    z_g, z_l, H, nl, W, B, L, mkind, pseed, dseed, pdrop = case
+    sd = {k: T(v).requires_grad_() for k, v in
+          synth.make_params(synth.decoder_param_shapes(z_g, z_l, H, nl), pseed).items()}
+    zg, zl, mask, coef = mg_cases.big_decoder_inputs(case)
+    zg_t, zl_t = T(zg).requires_grad_(), T(zl).requires_grad_()
+    dropout = None
+    if pdrop > 0:
+        dropout = (pdrop, lambda site, b, rows, dim, p: mg_cases.dropout_keep(dseed, site, b, rows, dim, p))
+    outs = egnn_oracle.egnn_decoder(sd, zg_t, zl_t, T(mask), max_neighbors=W, dropout=dropout)
+    for name, o in zip(("N", "CA", "C", "logits"), outs):
+        assert rel_err(o.detach(), gold[f"{tag}.{name}"]) < 1e-11, name
+    sum((o * T(c)).sum() for o, c in zip(outs, coef)).backward()
+    grads = {"z_g": zg_t.grad, "z_l": zl_t.grad}
+    grads.update({k: v.grad for k, v in sd.items() if v.grad is not None})
+    gold_names = {k.split(".", 2)[2] for k in gold.files if k.startswith(tag + ".g")}
+    assert gold_names == set(grads), gold_names ^ set(grads)
+    check_grads({k: torch.as_tensor(mg_cases.flat2d(v.detach().numpy())) for k, v in grads.items()}, gold, tag, 1e-9,
+                seed=4321)
+
+
 # ------------------------------------------------------------------ losses
 @pytest.mark.parametrize("tag", list(mg_cases.LOSS_CASES))
 def test_losses_match_reference(tag):
