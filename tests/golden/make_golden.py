@@ -201,6 +201,14 @@ def gen_big_decoders():
         zg_t, zl_t = T(zg).requires_grad_(), T(zl).requires_grad_()
         with InjectedDropout(dseed, nl + 3):
             outs = top(zg_t, zl_t, mask=T(mask))
+        # second gradient set, "smooth": the CA term alone -- between this loss and the EGNN layers there is no ReLU,
+        # so the gradients of the layer parameters are differentiable functions of the forward activations
+        (outs[1] * T(coef[1])).sum().backward(retain_graph=True)
+        grads = {"z_g": zg_t.grad, "z_l": zl_t.grad}
+        grads.update({k: p.grad for k, p in dec.named_parameters() if p.grad is not None})
+        pack_grads_big(grads, out, tag + ".sm")
+        zg_t.grad = zl_t.grad = None
+        dec.zero_grad(set_to_none=True)
         loss = sum((o * T(c)).sum() for o, c in zip(outs, coef))
         loss.backward()
         for name, o in zip(("N", "CA", "C", "logits"), outs):
