@@ -245,6 +245,19 @@ int pev_kabsch_rmsd(const float* a, const float* b, const float* mask, int32_t S
 int pev_kabsch_rmsd_pairs(const float* a, const float* mask, int32_t S, int32_t L, int32_t mode,
                           float* out /*[S,S]*/, void* stream);
 
+/* ---------------------------------------------------------------- K1, fused CTA-pair form (csrc/edge_tc3_kernels.cu)
+ * One kernel for the whole forward edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79): phi_e[1..3] ->
+ * agg = index_add_(m) (:68-69) and phi_x (:76), with m kept on chip between the two 256 x 256 GEMMs.  Run by CTA
+ * pairs (tcgen05 cta_group::2, each CTA holds one half of both weights).  Inputs as pev_edge2_fwd1 / fwd2 (ABh fp16
+ * half-domain node projection, d2, packed 0.5 W2 / 0.5 W5 images from pev_pack_weight_bf16_scaled).  Outputs:
+ * agg[N,256] (zeroed inside), w[E]; when hv_rows / hs_rows != NULL (a backward pass follows; both or neither) the
+ * half-domain pre-activations hv = v/2 and hs = s/2 as plain bf16 rows [E,256]. */
+int pev_edge3_fwd(const void* ABh /*fp16 [N,512]*/, const float* d2 /*[E]*/, const float* wd /*[256]*/,
+                  const void* W2hp, const float* b2 /*[256]*/, const void* W5hp, const float* b5 /*[256]*/,
+                  const float* w6 /*[256]*/, const float* b6 /*[1]*/, const int32_t* row, const int32_t* col,
+                  int64_t num_nodes, int64_t num_edges, void* hv_rows /*bf16 [E,256] or NULL*/,
+                  void* hs_rows /*bf16 [E,256] or NULL*/, float* agg /*[N,256]*/, float* w /*[E]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

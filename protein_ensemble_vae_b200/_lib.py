@@ -71,6 +71,8 @@ _PROTOS_TC = {
     "pev_edge2_wgrad_workspace_bytes": (c_int64, []),
     "pev_edge2_wgrad5": (c_int32, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
     "pev_edge2_wgrad2": (c_int32, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    # fused CTA-pair edge kernels (csrc/edge_tc3_kernels.cu)
+    "pev_edge3_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
 }
 
 
