@@ -103,8 +103,14 @@ PEV_HD void residue_fwd(const pev_loss_args& A, int b, int i, float* acc) {
     for (int k = 1; k < A.C; ++k) mx = fmaxf(mx, lg[k]);
     float se = 0.f;
     for (int k = 0; k < A.C; ++k) se += expf(lg[k] - mx);
-    float ce = logf(se) + mx - lg[A.labels[bi]];
-    acc[RA_CE] += ce * m;                                              // :431-434
+    // A label outside [0, C) is IGNORED: zero loss and zero gradient for that residue, as F.cross_entropy does for
+    // its default ignore_index = -100 (which the reference's call at models/losses.py:431 inherits).  Other
+    // out-of-range labels make PyTorch raise a device assert; here they are ignored too rather than read out of bounds.
+    const int64_t lab = A.labels[bi];
+    if (lab >= 0 && lab < A.C) {
+      float ce = logf(se) + mx - lg[lab];
+      acc[RA_CE] += ce * m;                                            // :431-434
+    }
   }
 }
 
@@ -225,9 +231,10 @@ PEV_HD void ce_row_bwd(const pev_loss_args& A, float cfs, int64_t bi, float* g) 
   for (int k = 1; k < A.C; ++k) mx = fmaxf(mx, lg[k]);
   float se = 0.f;
   for (int k = 0; k < A.C; ++k) se += expf(lg[k] - mx);
-  float s = cfs * A.mask[bi] / se;
   int64_t lab = A.labels[bi];
-  for (int k = 0; k < A.C; ++k) g[k] = s * expf(lg[k] - mx) - (k == lab ? cfs * A.mask[bi] : 0.f);
+  const bool used = lab >= 0 && lab < A.C;                             // ignored label: zero gradient row
+  float s = used ? cfs * A.mask[bi] / se : 0.f;
+  for (int k = 0; k < A.C; ++k) g[k] = s * expf(lg[k] - mx) - ((used && k == lab) ? cfs * A.mask[bi] : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -91,19 +91,39 @@ def _wgrad_workspace(device) -> torch.Tensor:
     return ws
 
 
+_SCRATCH: dict = {}
+
+
+def _scratch(device, E: int, N: int = 0):
+    """One set of per-edge buffers (hv / m tile images, hs rows) + agg / w dummies for the recompute mode, shared by
+    every layer of every decoder on ``device`` and grown on demand."""
+    key = str(device)
+    cur = _SCRATCH.get(key)
+    if cur is None or cur[0].shape[0] < num_tiles(E) or cur[3].shape[0] < N:
+        Ea, Na = max(E, cur[2].shape[0] if cur else 0), max(N, cur[3].shape[0] if cur else 0)
+        cur = (alloc_tile_image(Ea, device), alloc_tile_image(Ea, device),
+               torch.empty(max(Ea, 1), H, dtype=torch.bfloat16, device=device),
+               torch.empty(max(Na, 1), H, dtype=torch.float32, device=device),
+               torch.empty(max(Ea, 1), dtype=torch.float32, device=device))
+        _SCRATCH[key] = cur
+    return cur
+
+
 class FusedEdgeV2(torch.autograd.Function):
     """(ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3]) on the v2 kernels.
 
     ``ABh`` is the fp32 half-domain node projection ``0.5 [h Wa^T + b1 | h Wb^T]`` (rounded to fp16 here, once).
     Forward: ``pev_edge_d2`` -> ``pev_edge2_fwd1`` -> ``pev_edge2_fwd2`` -> exact-order coordinate update (K2).
     Kept for the backward pass: the ``hv`` and ``m`` tile images and ``hs`` rows (bf16, 3 x 2.47 GB per layer at
-    config 2), ``w``, ``d2`` and the fp16 ``ABh``.  Backward: K2 backward -> ``bwd2`` (ghv) -> ``wgrad5`` ->
+    config 2), ``w``, ``d2`` and the fp16 ``ABh``.  With ``recompute`` the three per-edge streams are NOT kept: the
+    backward pass re-runs ``fwd1`` / ``fwd2`` of the layer into one scratch set shared by all layers (+1 forward of
+    edge work, 1/num_layers of the activation memory: what lets L=1024 dense graphs train).  Backward: K2 backward -> ``bwd2`` (ghv) -> ``wgrad5`` ->
     ``bwd1`` (ghu) -> ``wgrad2`` -> segmented row / column sums of ``ghu``; the activations a, m and the SiLU
     derivatives are rebuilt inside the kernels (one tanh each) instead of being stored.
     """
 
     @staticmethod
-    def forward(ctx, ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches):
+    def forward(ctx, ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches, recompute: bool = False):
         L = _lib.lib()
         N, E = g.num_nodes, g.num_edges
         dev = x.device
@@ -117,9 +137,10 @@ class FusedEdgeV2(torch.autograd.Function):
             W2hp = packed_weight_scaled(W2, 0.5, cache=caches[0])
             W5hp = packed_weight_scaled(W5, 0.5, cache=caches[1])
             d2 = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
-            hvT = alloc_tile_image(E, dev) if keep else None
-            mT = alloc_tile_image(E, dev)
-            hs = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if keep else None
+            store = keep and not recompute
+            hvT = alloc_tile_image(E, dev) if store else None
+            mT = alloc_tile_image(E, dev) if not (keep and recompute) else _scratch(dev, E)[1]
+            hs = torch.empty(E, H, dtype=torch.bfloat16, device=dev) if store else None
             agg = torch.empty(N, H, dtype=torch.float32, device=dev)
             w = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
             x_out = torch.empty_like(x)
@@ -132,19 +153,34 @@ class FusedEdgeV2(torch.autograd.Function):
             L.call("pev_scatter_coord_fwd", None, ptr(w), ptr(x), ptr(dinv), ptr(g.row_ptr), ptr(g.col), N, H,
                    None, ptr(x_out), st)
         ctx.g, ctx.caches = g, caches
-        if keep:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2)
+        ctx.recompute = bool(keep and recompute)
+        if ctx.recompute:
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, None, None, None, w, d2, b2, b5, b6v)
+        elif keep:
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2, None, None, None)
         else:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None, None)
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None, None, None, None, None)
         return agg, x_out
 
     @staticmethod
     def backward(ctx, gagg, gxo):
-        x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2 = ctx.saved_tensors
-        if hs is None:
+        x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2, b2, b5, b6v = ctx.saved_tensors
+        if hs is None and not ctx.recompute:
             raise RuntimeError("FusedEdgeV2 ran with keep=False (no_grad); backward is unavailable")
         g = ctx.g
         N, E = g.num_nodes, g.num_edges
+        if ctx.recompute:
+            # rebuild hv, m, hs of this layer into the shared scratch set (same kernels, same bits as the forward pass)
+            with torch.cuda.device_of(x):
+                L, st = _lib.lib(), stream(x)
+                hvT, mT, hs, agg_s, w_s = _scratch(x.device, E, N)
+                W2hp = packed_weight_scaled(W2, 0.5, cache=ctx.caches[0])
+                W5hp = packed_weight_scaled(W5, 0.5, cache=ctx.caches[1])
+                with _lib.profiled("edge2_fwd1"):
+                    L.call("pev_edge2_fwd1", ptr(ABb), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E,
+                           ptr(hvT), ptr(mT), ptr(agg_s), st)
+                with _lib.profiled("edge2_fwd2"):
+                    L.call("pev_edge2_fwd2", ptr(mT), ptr(W5hp), ptr(b5), ptr(w6v), ptr(b6v), E, ptr(w_s), ptr(hs), st)
         gagg, gxo = f32c(gagg), f32c(gxo)
         bf, f32 = torch.bfloat16, torch.float32
         L = _lib.lib()
@@ -186,7 +222,7 @@ class FusedEdgeV2(torch.autograd.Function):
                    ptr(g.csc_perm), N, E, ptr(gx), st)
             gwd = 0.5 * gwdh                            # hu = ... + (wd/2) d2
             gb6 = gw[:E].sum().reshape(1)
-        return (gAB, gx, gwd, gW2, 0.5 * db2h, gW5, 0.5 * db5h, gw6.reshape(1, H), gb6, None, None, None, None)
+        return (gAB, gx, gwd, gW2, 0.5 * db2h, gW5, 0.5 * db5h, gw6.reshape(1, H), gb6, None, None, None, None, None)
 
 
 def egn_layer_v2(layer, h, x, g, dinv):
@@ -201,7 +237,8 @@ def egn_layer_v2(layer, h, x, g, dinv):
     caches = layer.__dict__.setdefault("_pev_packed2", ({}, {}))
     agg, x_new = FusedEdgeV2.apply(ABh, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
                                    layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
-                                   layer.phi_x[2].bias, dinv, g, keep, caches)
+                                   layer.phi_x[2].bias, dinv, g, keep, caches,
+                                   bool(getattr(layer, "recompute_edges", False)))
     q = layer.phi_h[1](NodeLinear2.apply(h, agg, layer.phi_h[0].weight, layer.phi_h[0].bias))
     h_new = layer_norm(layer.norm_h, NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias), h)
     return h_new, x_new

@@ -32,6 +32,10 @@ def _default_precision() -> str:
     return os.environ.get("PEV_PRECISION", "bf16")
 
 
+def _default_recompute() -> bool:
+    return os.environ.get("PEV_RECOMPUTE_EDGES", "0") not in ("0", "")
+
+
 def _layer_forward(layer, h, x, g, dinv, precision):
     if precision == "bf16":
         from . import egnn_tc
@@ -52,11 +56,13 @@ class EGNLayer(nn.Module):
     """
 
     def __init__(self, node_dim: int, hidden_dim: int, activation: nn.Module = nn.SiLU(),
-                 precision: str | None = None):
+                 precision: str | None = None, recompute_edges: bool | None = None):
         super().__init__()
         self.node_dim = node_dim
         self.hidden_dim = hidden_dim
         self.precision = precision or _default_precision()
+        # bf16 path: rebuild the per-edge activations in backward instead of keeping them (egnn_tc2.FusedEdgeV2)
+        self.recompute_edges = _default_recompute() if recompute_edges is None else bool(recompute_edges)
         self.phi_e = nn.Sequential(nn.Linear(2 * node_dim + 1, hidden_dim), activation,
                                    nn.Linear(hidden_dim, hidden_dim), activation)
         self.phi_h = nn.Sequential(nn.Linear(node_dim + hidden_dim, hidden_dim), activation,
@@ -73,8 +79,10 @@ class EGNNDecoder(nn.Module):
     """Latents -> backbone (``models/en_gnn_decoder.py:90-333``)."""
 
     def __init__(self, z_g: int, z_l: int, hidden_dim: int = 256, num_layers: int = 8, max_neighbors: int = 20,
-                 dropout: float = 0.1, degree_normalize: bool = True, precision: str | None = None):
+                 dropout: float = 0.1, degree_normalize: bool = True, precision: str | None = None,
+                 recompute_edges: bool | None = None, cache_mask: bool = True):
         super().__init__()
+        self.cache_mask = cache_mask
         self.z_g, self.z_l = z_g, z_l
         self.hidden_dim = hidden_dim
         self.num_layers = num_layers
@@ -83,8 +91,8 @@ class EGNNDecoder(nn.Module):
         self.precision = precision or _default_precision()
         self.dropout = nn.Dropout(dropout)
         self.input_embedding = nn.Linear(z_g + z_l, hidden_dim)
-        self.layers = nn.ModuleList([EGNLayer(hidden_dim, hidden_dim, precision=self.precision)
-                                     for _ in range(num_layers)])
+        self.layers = nn.ModuleList([EGNLayer(hidden_dim, hidden_dim, precision=self.precision,
+                                              recompute_edges=recompute_edges) for _ in range(num_layers)])
         self.latent_to_coords = nn.Sequential(
             nn.Linear(z_g + z_l, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(), nn.Dropout(dropout * 0.5),
             nn.Linear(hidden_dim, hidden_dim // 2), nn.ReLU(), nn.Linear(hidden_dim // 2, 3))
@@ -144,6 +152,20 @@ class EGNNDecoder(nn.Module):
         g = band_graph(lengths, self.max_neighbors, device)
         return g, (g.dinv if self.degree_normalize else None)
 
+    def invalidate_mask_cache(self) -> None:
+        """Forget the cached lengths / packing of the last mask (needed after out-of-band writes to it)."""
+        self.__dict__.pop("_pev_mask_cache", None)
+
+    def _mask_version(self, mask):
+        if not self.__dict__.get("cache_mask", True):
+            return None
+        try:
+            if mask.is_inference():
+                return None
+            return mask._version
+        except RuntimeError:
+            return None
+
     def _run(self, module, x, fp32_forward=False):
         """Node-level heads: plain modules on the fp32 path, TF32 tensor-core linears on the bf16 path
         (``fp32_forward`` keeps the forward product in fp32 for the ill-conditioned N / C direction heads)."""
@@ -160,14 +182,20 @@ class EGNNDecoder(nn.Module):
             # The packed size needs the valid lengths on the host: one sync per forward -- unless this very mask
             # tensor (same object, same in-place version; the cache keeps it alive so its storage cannot be recycled)
             # was resolved on the previous call, as in a training loop over one resident batch.
-            c = self.__dict__.get("_pev_mask_cache")
-            if c is not None and c[0] is mask and c[1] == mask._version:
+            # The cache is keyed on the tensor object and its autograd version counter, so it cannot see writes that
+            # bypass the counter (``mask.data.*``, numpy-shared storage, a CUDA graph refilling a static buffer):
+            # after such a write call :meth:`invalidate_mask_cache`, or construct with ``cache_mask=False``.
+            # Inference-mode tensors have no version counter and are never cached.
+            ver = self._mask_version(mask)
+            c = self.__dict__.get("_pev_mask_cache") if ver is not None else None
+            if c is not None and c[0] is mask and c[1] == ver:
                 lengths, flat_idx = c[2], c[3]
             else:
                 mb = mask.bool()
                 lengths = mb.sum(1).tolist()
                 flat_idx = torch.nonzero(mb.reshape(-1)).squeeze(-1) if sum(lengths) != B * L else None
-                self.__dict__["_pev_mask_cache"] = (mask, mask._version, lengths, flat_idx)
+                if ver is not None:
+                    self.__dict__["_pev_mask_cache"] = (mask, ver, lengths, flat_idx)
         else:
             lengths, flat_idx = [L] * B, None
         N = int(sum(lengths))

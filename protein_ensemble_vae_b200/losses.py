@@ -70,10 +70,12 @@ class _LossTerms(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.tensors = t          # keeps the (possibly converted) inputs alive for backward
         ctx.inv_den = inv_den
-        return terms
+        den_inv = inv_den[:NUM_TERMS].clone()
+        ctx.mark_non_differentiable(den_inv)
+        return terms, den_inv
 
     @staticmethod
-    def backward(ctx, gterms):
+    def backward(ctx, gterms, _gden=None):
         t, cfg = ctx.tensors, ctx.cfg
         need = dict(zip(_DIFF, ctx.needs_input_grad[2:]))
         mask = t["mask"]
@@ -94,10 +96,21 @@ class _LossTerms(torch.autograd.Function):
         return (None, None) + tuple(grads[k] if need[k] else None for k in _DIFF)
 
 
-def _terms(cfg, mask, **kw):
+def _terms(cfg, mask, dp_normalize=False, **kw):
+    """The 17 base terms.  ``dp_normalize``: this process holds one shard of a data-parallel global batch; every
+    term is rescaled by ``world * den_local / sum_ranks(den_local)`` (one all-reduce of the 17 denominators), so that
+    the plain average over ranks of the returned terms -- and of their gradients -- is the term of the GLOBAL batch
+    even when ranks hold different numbers of conformers / valid residues (masked means, models/losses.py:12-21,
+    :54-57)."""
     consts = {k: kw.get(k) for k in _CONST}
     consts["mask"] = mask
-    return _LossTerms.apply(cfg, consts, *[kw.get(k) for k in _DIFF])
+    t, den_inv = _LossTerms.apply(cfg, consts, *[kw.get(k) for k in _DIFF])
+    if dp_normalize:
+        from .distributed import shard_term_scale
+        scale = shard_term_scale(den_inv)
+        if scale is not None:
+            t = torch.where(scale > 0, t * scale, torch.zeros_like(t))    # an empty shard contributes 0, not 0/0
+    return t
 
 
 # ------------------------------------------------------------------------------------ public API
@@ -259,9 +272,13 @@ def _coef_vector(values: tuple, device):
 def compute_total_loss(pred_N, pred_CA, pred_C, pred_seq, target_N, target_CA, target_C, target_seq_labels,
                        mask, mu_g, lv_g, mu_l, lv_l,
                        target_dihedrals, klw_g, klw_l, w_pair, pair_stride,
-                       w_dihedral, w_rama, w_bond, w_angle, w_rec, w_seq, w_clash):
-    """Weighted total and its 16 components (``models/losses.py:520-613``)."""
-    t = _terms({"pair_stride": pair_stride, "clash": True, "geometry": True}, mask,
+                       w_dihedral, w_rama, w_bond, w_angle, w_rec, w_seq, w_clash, *, dp_normalize=False):
+    """Weighted total and its 16 components (``models/losses.py:520-613``).
+
+    ``dp_normalize=True`` (keyword only, not in the reference): the batch is one rank's shard of a data-parallel
+    global batch -- see :func:`_terms`; averaging the returned values / gradients over ranks then equals the
+    single-process result on the concatenated batch, also for ragged shards."""
+    t = _terms({"pair_stride": pair_stride, "clash": True, "geometry": True}, mask, dp_normalize,
                pred_N=pred_N, pred_CA=pred_CA, pred_C=pred_C, logits=pred_seq, mu_l=mu_l, lv_l=lv_l,
                mu_g=mu_g, lv_g=lv_g, target_N=target_N, target_CA=target_CA, target_C=target_C,
                target_dih=target_dihedrals, labels=target_seq_labels)

@@ -194,3 +194,32 @@ def test_tile_image_layout_roundtrip_and_addressing():
             + ((((el % 64) // 8) ^ (f % 8)) << 4) + (el % 8) * 2
         assert flat[off // 2] == rows[e, f]
     assert float(img.view(3, -1)[2].float().abs().sum()) > 0 and float(T2.rows_to_tile_image(rows[:1])[0, 128:].abs().sum()) >= 0
+
+
+def test_decoder_mask_cache_inference_mode_and_invalidation(bk):
+    """A mask created under torch.inference_mode() has no version counter: the decoder must decode it
+    (uncached); cache_mask=False and invalidate_mask_cache() cover writes that bypass the counter."""
+    from protein_ensemble_vae_b200 import EGNNDecoder
+    torch.manual_seed(0)
+    dec = EGNNDecoder(8, 4, hidden_dim=32, num_layers=1, max_neighbors=3, dropout=0.0, precision="fp32").to(bk.dev).eval()
+    zg, zl = torch.randn(2, 8, device=bk.dev), torch.randn(2, 9, 4, device=bk.dev)
+    with bk.ctx():
+        with torch.inference_mode():
+            mask = torch.ones(2, 9, device=bk.dev)
+            mask[1, 5:] = 0
+            a = dec(zg, zl, mask)[1]
+            b = dec(zg, zl, mask)[1]
+        assert torch.equal(a, b) and float(a[1, 5:].abs().max()) == 0.0
+        assert "_pev_mask_cache" not in dec.__dict__
+        m2 = torch.ones(2, 9, device=bk.dev)
+        with torch.no_grad():
+            c1 = dec(zg, zl, m2)[1]
+            m2.data[1, 5:] = 0                      # bypasses the version counter: the cache cannot see it ...
+            dec.invalidate_mask_cache()             # ... so the caller says so
+            c2 = dec(zg, zl, m2)[1]
+        assert float(c1[1, 5:].abs().max()) > 0 and float(c2[1, 5:].abs().max()) == 0.0
+        dec.cache_mask = False
+        with torch.no_grad():
+            m2.data[1, 3:] = 0
+            c3 = dec(zg, zl, m2)[1]
+        assert float(c3[1, 3:].abs().max()) == 0.0

@@ -158,3 +158,33 @@ def test_total_loss_scalar_and_tensor_weights_agree(bk):
         assert abs(t0 - t1) <= 2e-6 * abs(t1), (tag, t0, t1)
         for k in g0:
             assert rel_err(g0[k], g1[k]) < 1e-5, (tag, k)
+
+
+def test_sequence_loss_ignores_out_of_range_labels(bk):
+    """-100 (F.cross_entropy's default ignore_index, which the reference's call inherits) and any other label outside
+    [0, C) contribute zero loss and a zero gradient row -- also at padded positions, where the reference pads labels."""
+    import torch.nn.functional as F
+    from protein_ensemble_vae_b200.losses import sequence_classification_loss
+    rng = np.random.default_rng(5)
+    B, L, C = 3, 11, 20
+    logits = rng.standard_normal((B, L, C)).astype(np.float32) * 2
+    labels = rng.integers(0, C, (B, L)).astype(np.int64)
+    mask = np.ones((B, L), np.float32)
+    mask[1, 7:] = 0
+    labels[1, 7:] = -100            # padding convention
+    labels[0, 3] = -100             # ignored although valid
+    labels[2, 5] = 20               # unknown residue class
+    lg = bk.t32(logits).requires_grad_()
+    with bk.ctx():
+        loss = sequence_classification_loss(lg, bk.ti(labels), bk.t32(mask))
+        loss.backward()
+    lg64 = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    lab = torch.tensor(labels)
+    lab = torch.where((lab < 0) | (lab >= C), torch.full_like(lab, -100), lab)
+    ce = F.cross_entropy(lg64.view(-1, C), lab.view(-1), reduction="none").view(B, L)
+    m64 = torch.tensor(mask, dtype=torch.float64)
+    want = (ce * m64).sum() / (m64.sum() + 1e-8)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want))
+    assert rel_err(lg.grad, lg64.grad) < 1e-5
+    assert float(lg.grad[0, 3].abs().max()) == 0.0 and float(lg.grad[2, 5].abs().max()) == 0.0
