@@ -1494,10 +1494,17 @@ static int configure(K kernel, const char* name, int smem_bytes) {
   if (e != cudaSuccess) return set_error(2, "%s: %s", name, cudaGetErrorString(e));
   return 0;
 }
+// Role-ablation switches (DBG = 1 instantiations, PEV_TC2_DEBUG bit mask) exist in profiling builds only
+// (-DPEV_TC2_ABLATE); the shipped library instantiates the DBG = 0 forms, in which every `dbg &` test is a
+// compile-time constant and folds away.
 static int debug_mask() {
+#ifdef PEV_TC2_ABLATE
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PEV_TC2_DEBUG"); dbg = e ? atoi(e) : 0; }
   return dbg;
+#else
+  return 0;
+#endif
 }
 static int grid_for(int num_tiles) {
   const int sms = sm_count();
@@ -1512,7 +1519,8 @@ typedef __nv_bfloat16 bf16_t;
 
 template <int MODE>
 static int launch_wgrad(tc2::WgradParams& p, float scale, float* dW, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
+  bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc2::wgrad_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tc2::WG_SMEM_BYTES);
@@ -1557,12 +1565,17 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   if (num_nodes > 0) cudaMemsetAsync(agg, 0, sizeof(float) * tc2::H * (size_t)num_nodes, st);
   if (num_edges == 0) return 0;
   PEV_REQUIRE(row && col && mT && d2, "edge arrays missing");
-  static bool configured = false;
+  static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
+  bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
     if (int rc = tc2::configure(tc2::fwd1_kernel<0, true>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
+#ifdef PEV_TC2_ABLATE
     if (int rc = tc2::configure(tc2::fwd1_kernel<1, true>, "fwd1_kernel", tc2::SmemT::BYTES)) return rc;
+#endif
     if (int rc = tc2::configure(tc2::fwd1_kernel<0, false>, "fwd1_kernel", tc2::SmemTI::BYTES)) return rc;
+#ifdef PEV_TC2_ABLATE
     if (int rc = tc2::configure(tc2::fwd1_kernel<1, false>, "fwd1_kernel", tc2::SmemTI::BYTES)) return rc;
+#endif
     configured = true;
   }
   tc2::Fwd1Params p = {};
@@ -1572,11 +1585,17 @@ int pev_edge2_fwd1(const void* ABh, const float* d2, const float* wd, const void
   p.dbg = tc2::debug_mask();
   const int grid = tc2::grid_for(p.num_tiles);
   if (hvT) {
+#ifdef PEV_TC2_ABLATE
     if (p.dbg) tc2::fwd1_kernel<1, true><<<grid, tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
-    else tc2::fwd1_kernel<0, true><<<grid, tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
+    else
+#endif
+    tc2::fwd1_kernel<0, true><<<grid, tc2::NUM_THREADS, tc2::SmemT::BYTES, st>>>(p);
   } else {
+#ifdef PEV_TC2_ABLATE
     if (p.dbg) tc2::fwd1_kernel<1, false><<<grid, tc2::NUM_THREADS, tc2::SmemTI::BYTES, st>>>(p);
-    else tc2::fwd1_kernel<0, false><<<grid, tc2::NUM_THREADS, tc2::SmemTI::BYTES, st>>>(p);
+    else
+#endif
+    tc2::fwd1_kernel<0, false><<<grid, tc2::NUM_THREADS, tc2::SmemTI::BYTES, st>>>(p);
   }
   return after_launch("edge2_fwd1_kernel");
 }
@@ -1588,12 +1607,17 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
   PEV_REQUIRE(mT && w_out, "edge arrays missing");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
-  static bool configured = false;
+  static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
+  bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
     if (int rc = tc2::configure(tc2::fwd2_kernel<0, true>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+#ifdef PEV_TC2_ABLATE
     if (int rc = tc2::configure(tc2::fwd2_kernel<1, true>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+#endif
     if (int rc = tc2::configure(tc2::fwd2_kernel<0, false>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+#ifdef PEV_TC2_ABLATE
     if (int rc = tc2::configure(tc2::fwd2_kernel<1, false>, "fwd2_kernel", tc2::SmemF2::BYTES)) return rc;
+#endif
     configured = true;
   }
   tc2::Fwd2Params p = {};
@@ -1607,11 +1631,17 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
     if (int rc = tc2::make_rows_map(hs_out, num_edges, &hs_map)) return rc;
   const int grid = tc2::grid_for(p.num_tiles);
   if (hs_out) {
+#ifdef PEV_TC2_ABLATE
     if (p.dbg) tc2::fwd2_kernel<1, true><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
-    else tc2::fwd2_kernel<0, true><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+    else
+#endif
+    tc2::fwd2_kernel<0, true><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
   } else {
+#ifdef PEV_TC2_ABLATE
     if (p.dbg) tc2::fwd2_kernel<1, false><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
-    else tc2::fwd2_kernel<0, false><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
+    else
+#endif
+    tc2::fwd2_kernel<0, false><<<grid, tc2::F2_THREADS, tc2::SmemF2::BYTES, st>>>(p, hs_map);
   }
   return after_launch("edge2_fwd2_kernel");
 }
@@ -1623,10 +1653,13 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   cudaMemsetAsync(db2h, 0, sizeof(float) * tc2::H, st);
   if (num_edges == 0) return 0;
   PEV_REQUIRE(hs && gw && gagg && row && hvT && ghvT, "edge arrays missing");
-  static bool configured = false;
+  static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
+  bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
     if (int rc = tc2::configure(tc2::bwd2_kernel<0>, "bwd2_kernel", tc2::SmemB2::BYTES)) return rc;
+#ifdef PEV_TC2_ABLATE
     if (int rc = tc2::configure(tc2::bwd2_kernel<1>, "bwd2_kernel", tc2::SmemB2::BYTES)) return rc;
+#endif
     configured = true;
   }
   tc2::Bwd2Params p = {};
@@ -1635,8 +1668,11 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
+#ifdef PEV_TC2_ABLATE
   if (p.dbg) tc2::bwd2_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemB2::BYTES, st>>>(p);
-  else tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemB2::BYTES, st>>>(p);
+  else
+#endif
+  tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemB2::BYTES, st>>>(p);
   return after_launch("edge2_bwd2_kernel");
 }
 
@@ -1647,10 +1683,13 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   PEV_REQUIRE(ghvT && ABh && d2 && row && col && ghu && gd2, "edge arrays missing");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
-  static bool configured = false;
+  static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
+  bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
     if (int rc = tc2::configure(tc2::bwd1_kernel<0>, "bwd1_kernel", tc2::SmemB1::BYTES)) return rc;
+#ifdef PEV_TC2_ABLATE
     if (int rc = tc2::configure(tc2::bwd1_kernel<1>, "bwd1_kernel", tc2::SmemB1::BYTES)) return rc;
+#endif
     configured = true;
   }
   tc2::Bwd1Params p = {};
@@ -1661,8 +1700,11 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   p.dbg = tc2::debug_mask();
   alignas(64) CUtensorMap ghu_map;
   if (int rc = tc2::make_rows_map(ghu, num_edges, &ghu_map)) return rc;
+#ifdef PEV_TC2_ABLATE
   if (p.dbg) tc2::bwd1_kernel<1><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemB1::BYTES, st>>>(p, ghu_map);
-  else tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemB1::BYTES, st>>>(p, ghu_map);
+  else
+#endif
+  tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemB1::BYTES, st>>>(p, ghu_map);
   return after_launch("edge2_bwd1_kernel");
 }
 

@@ -518,7 +518,8 @@ int pev_edge3_fwd(const void* ABh, const float* d2, const float* wd, const void*
   if (num_edges == 0) return 0;
   PEV_REQUIRE(row && col && d2 && w_out, "edge arrays missing");
   cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
-  static bool configured = false;
+  static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
+  bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
     if (int rc = tc3::configure(tc3::fwd_kernel<true>, "edge3_fwd_kernel", tc3::SmemF<true>::BYTES)) return rc;
     if (int rc = tc3::configure(tc3::fwd_kernel<false>, "edge3_fwd_kernel", tc3::SmemF<false>::BYTES)) return rc;

@@ -13,7 +13,7 @@ namespace pev {
 
 constexpr int kResThreads = 128;
 constexpr int kPairThreads = 128;
-constexpr int kClashThreads = 256;
+constexpr int kClashThreads = 128;
 constexpr int kMaxDynSmem = 200 * 1024;
 
 // ------------------------------------------------------------------------------------------ K3a fwd
@@ -101,32 +101,84 @@ loss_pair_kernel(pev_loss_args A, int M, double* __restrict__ ag, const float* _
   }
 }
 
-// clash tile: all 3L backbone atoms of one conformer staged in shared memory
+// clash tile (models/losses.py:439-517).  One block per (conformer, 256-atom row tile): all 3L backbone atoms of the
+// conformer are staged once as float4 {x, y, z, mask} (one broadcast LDS.128 per partner and warp), every thread keeps
+// kClashIPT of the tile's atoms in registers and walks ALL partners, so a partner load is shared by kClashIPT pair
+// evaluations and the hot loop is 3 subtractions + 3 FMAs + one compare per pair: the distance test d^2 < clash_dist^2
+// is the only thing evaluated for the >99 % of pairs that are far apart; the rare path (sqrt, residue-separation rule
+// |res_i - res_j| >= 2, penalty, force) runs for close pairs only -- bonded neighbours enter it and are dropped there.
+// The pair count (denominator) needs no loop: m_a (sum of all masks - masks of the nine atoms of residues r-1..r+1).
+// Walking the full row (both triangles) keeps the gradient atomic-free and deterministic: thread a owns atom a.
+// Forward: numerator / denominator per conformer, each unordered pair counted twice (pev_loss_final.cuh).
+// Backward: the same walk, accumulating the force on the thread's own atoms.
+constexpr int kClashIPT = 2;                               // atoms per thread
+constexpr int kClashTile = kClashThreads * kClashIPT;      // 256 atoms per block (L = 256: three full blocks)
+template <bool BACKWARD>
 __global__ void __launch_bounds__(kClashThreads)
 loss_clash_kernel(pev_loss_args A, double* __restrict__ as, const float* __restrict__ coef,
                   const float* __restrict__ inv_den, float* __restrict__ gN, float* __restrict__ gCA,
-                  float* __restrict__ gC, int backward) {
-  extern __shared__ float sm[];
+                  float* __restrict__ gC) {
+  extern __shared__ float4 sat[];                          // [3L] {x, y, z, mask}
   __shared__ float red[32];
   const int n_atoms = 3 * A.L;
-  float* at = sm;
-  float* am = sm + 3 * n_atoms;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < A.L; i += blockDim.x) {
+  float msum_part = 0.f;
+  for (int idx = threadIdx.x; idx < n_atoms; idx += blockDim.x) {
+    const int i = idx / 3, k = idx - 3 * i;
     const int64_t bi = (int64_t)b * A.L + i;
+    const float* src = (k == 0 ? A.pred_N : (k == 1 ? A.pred_CA : A.pred_C)) + bi * 3;
     const float m = A.mask[bi];
-    for (int k = 0; k < 3; ++k) {
-      at[(3 * i + 0) * 3 + k] = A.pred_N[bi * 3 + k];
-      at[(3 * i + 1) * 3 + k] = A.pred_CA[bi * 3 + k];
-      at[(3 * i + 2) * 3 + k] = A.pred_C[bi * 3 + k];
-    }
-    am[3 * i] = m; am[3 * i + 1] = m; am[3 * i + 2] = m;
+    sat[idx] = make_float4(src[0], src[1], src[2], m);
+    msum_part += m;
   }
+  const float msum = block_sum(msum_part, red);            // valid in thread 0
+  __shared__ float msum_all;
+  if (threadIdx.x == 0) msum_all = msum;
   __syncthreads();
-  const int a = blockIdx.x * kClashThreads + threadIdx.x;
-  float n = 0.f, d = 0.f;
-  if (!backward) {
-    if (a < n_atoms) clash_row(at, am, n_atoms, a, A.clash_dist, A.soft_margin, &n, &d, nullptr, 0.f);
+  const float cd = A.clash_dist, cd2 = cd * cd, sm = A.soft_margin;
+  float4 pa[kClashIPT];
+  int ai[kClashIPT];
+  float num[kClashIPT];
+  float gx[kClashIPT], gy[kClashIPT], gz[kClashIPT];
+#pragma unroll
+  for (int u = 0; u < kClashIPT; ++u) {
+    ai[u] = blockIdx.x * kClashTile + u * kClashThreads + threadIdx.x;
+    pa[u] = ai[u] < n_atoms ? sat[ai[u]] : make_float4(1e30f, 1e30f, 1e30f, 0.f);   // far from everything
+    num[u] = gx[u] = gy[u] = gz[u] = 0.f;
+  }
+  auto close_pair = [&](int u, int c, const float4 pc, float dx, float dy, float dz, float d2) {
+    const int sep = c / 3 - ai[u] / 3;
+    if (sep < 2 && sep > -2) return;                                                // :478-482
+    const float w = pa[u].w * pc.w;
+    const float dist = sqrtf(d2);
+    const float v = fmaxf(cd - dist, 0.f);                                          // :494-495
+    num[u] += (v < sm ? 0.5f * v * v : v * v) * w;                                  // :500-504
+    if (BACKWARD && v > 0.f && dist > 0.f) {
+      const float f = (v < sm ? v : 2.0f * v) * w / dist;
+      gx[u] -= dx * f; gy[u] -= dy * f; gz[u] -= dz * f;
+    }
+  };
+#pragma unroll 4
+  for (int c = 0; c < n_atoms; ++c) {
+    const float4 pc = sat[c];
+#pragma unroll
+    for (int u = 0; u < kClashIPT; ++u) {
+      const float dx = pa[u].x - pc.x, dy = pa[u].y - pc.y, dz = pa[u].z - pc.z;
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (d2 < cd2) close_pair(u, c, pc, dx, dy, dz, d2);
+    }
+  }
+  if (!BACKWARD) {
+    float n = 0.f, d = 0.f;
+#pragma unroll
+    for (int u = 0; u < kClashIPT; ++u) {
+      if (ai[u] >= n_atoms) continue;
+      n += num[u];
+      const int r = ai[u] / 3;
+      float near = 0.f;                                    // masks of the atoms of residues r-1, r, r+1 (excluded pairs)
+      for (int rr = max(r - 1, 0); rr <= min(r + 1, A.L - 1); ++rr) near += 3.f * sat[3 * rr].w;
+      d += pa[u].w * (msum_all - near);
+    }
     n = block_sum(n, red);
     d = block_sum(d, red);
     if (threadIdx.x == 0) {
@@ -134,14 +186,17 @@ loss_clash_kernel(pev_loss_args A, double* __restrict__ as, const float* __restr
       add(as + 8 * (int64_t)b + 4, (double)n);
       add(as + 8 * (int64_t)b + 5, (double)d);
     }
-  } else if (a < n_atoms) {
-    v3 g;
-    clash_row(at, am, n_atoms, a, A.clash_dist, A.soft_margin, &n, &d, &g,
-              coef[PEV_T_CLASH] * inv_den[PEV_NUM_TERMS + A.B + b]);
-    float* base = (a % 3 == 0) ? gN : ((a % 3 == 1) ? gCA : gC);
-    if (base) {
-      float* dst = base + ((int64_t)b * A.L + a / 3) * 3;
-      dst[0] += g.x; dst[1] += g.y; dst[2] += g.z;
+  } else {
+    const float cf = coef[PEV_T_CLASH] * inv_den[PEV_NUM_TERMS + A.B + b];
+#pragma unroll
+    for (int u = 0; u < kClashIPT; ++u) {
+      const int a = ai[u];
+      if (a >= n_atoms) continue;
+      float* base = (a % 3 == 0) ? gN : ((a % 3 == 1) ? gCA : gC);
+      if (base) {
+        float* dst = base + ((int64_t)b * A.L + a / 3) * 3;
+        dst[0] += gx[u] * cf; dst[1] += gy[u] * cf; dst[2] += gz[u] * cf;
+      }
     }
   }
 }
@@ -305,9 +360,9 @@ int pev_loss_fwd(const pev_loss_args* ap, double* acc_global, double* acc_sample
   }
   if (A.enable_clash) {
     const size_t smem = sizeof(float) * 12 * (size_t)A.L;
-    if ((rc = opt_in_smem(loss_clash_kernel, smem, "clash"))) return rc;
-    dim3 g((3 * A.L + kClashThreads - 1) / kClashThreads, A.B);
-    loss_clash_kernel<<<g, kClashThreads, smem, st>>>(A, acc_sample, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    if ((rc = opt_in_smem(loss_clash_kernel<false>, smem, "clash"))) return rc;
+    dim3 g((3 * A.L + kClashTile - 1) / kClashTile, A.B);
+    loss_clash_kernel<false><<<g, kClashThreads, smem, st>>>(A, acc_sample, nullptr, nullptr, nullptr, nullptr, nullptr);
     if ((rc = after_launch("loss_clash_kernel"))) return rc;
   }
   return 0;
@@ -341,9 +396,9 @@ int pev_loss_bwd(const pev_loss_args* ap, const float* coef, const float* inv_de
   }
   if (A.enable_clash && (gN || gCA || gC)) {
     const size_t smem = sizeof(float) * 12 * (size_t)A.L;
-    if ((rc = opt_in_smem(loss_clash_kernel, smem, "clash"))) return rc;
-    dim3 g((3 * A.L + kClashThreads - 1) / kClashThreads, A.B);
-    loss_clash_kernel<<<g, kClashThreads, smem, st>>>(A, nullptr, coef, inv_den, gN, gCA, gC, 1);
+    if ((rc = opt_in_smem(loss_clash_kernel<true>, smem, "clash"))) return rc;
+    dim3 g((3 * A.L + kClashTile - 1) / kClashTile, A.B);
+    loss_clash_kernel<true><<<g, kClashThreads, smem, st>>>(A, nullptr, coef, inv_den, gN, gCA, gC);
     if ((rc = after_launch("loss_clash_kernel"))) return rc;
   }
   if (A.mu_l && gmul && glvl) {

@@ -9,7 +9,9 @@ namespace pev {
 int set_error(int code, const char* fmt, ...);
 // counts one kernel launch and converts cudaGetLastError() into the ABI's error code
 int after_launch(const char* kernel_name);
-int sm_count();
+int sm_count();            // of the CURRENT device
+constexpr int kMaxDevices = 64;
+int current_device();      // cudaGetDevice(), clamped to [0, kMaxDevices)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -70,6 +70,12 @@ class EGNLayer(nn.Module):
         self.phi_x = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), activation, nn.Linear(hidden_dim, 1))
         self.norm_h = nn.LayerNorm(node_dim)
 
+    def invalidate_packed_weights(self) -> None:
+        """Drop the cached bf16 tensor-core images of ``phi_e[2]`` / ``phi_x[0]``.  They are keyed on the parameters'
+        version counters, which in-place writes through ``.data`` (e.g. ``p.data.copy_(ema)``) do not bump: call this
+        after such a write (``load_state_dict`` and optimizer steps bump the counter and need nothing)."""
+        self.__dict__.pop("_pev_packed2", None)
+
     def forward(self, h, x, edge_index, degree_inv=None):
         g = edge_index if isinstance(edge_index, PackedGraph) else graph_from_edge_index(edge_index, h.shape[0])
         return _layer_forward(self, h, x, g, degree_inv, self.precision)
@@ -151,6 +157,11 @@ class EGNNDecoder(nn.Module):
             return g, dinv
         g = band_graph(lengths, self.max_neighbors, device)
         return g, (g.dinv if self.degree_normalize else None)
+
+    def invalidate_packed_weights(self) -> None:
+        """See :meth:`EGNLayer.invalidate_packed_weights` (all layers)."""
+        for layer in self.layers:
+            layer.invalidate_packed_weights()
 
     def invalidate_mask_cache(self) -> None:
         """Forget the cached lengths / packing of the last mask (needed after out-of-band writes to it)."""
