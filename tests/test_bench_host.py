@@ -39,3 +39,32 @@ def test_workload_config_names_the_baseline_configuration():
     c = bench.workload_config(8)
     assert c["workload"].startswith("configs[1]") and c["global_batch"] == 8 * c["batch_per_gpu"]
     assert c["parallelism"] == "dp8" and "cache" in c and "model" not in c
+
+
+def test_flop_model_and_edge_counts_follow_survey_8d():
+    import bench
+    assert [bench.band_edges(L) for L in (64, 100, 256, 512, 1024)] == [3480, 6360, 18840, 39320, 80280]
+    assert bench.band_edges(1024, 1023) == 1047552
+    assert abs(bench.flops_per_conformer(256, 1, train=False) / 1e9 - 5.116) < 0.01         # per conformer-layer forward
+    assert abs(bench.flops_per_conformer(256, 6) / 1e9 - 92.1) < 0.1                        # config 2, fwd + bwd
+    assert abs(bench.flops_per_conformer(100, 8, train=False) / 1e9 - 13.9) < 0.1           # config 4, per sample
+    for cfg in ("train", "decode", "mixed", "stress"):
+        c = bench.workload_config(4, cfg)
+        assert c["workload"].startswith("configs[") and c["parallelism"] == "dp4" and "model" not in c
+
+
+def test_reference_arm_runs_on_a_tiny_sample(capsys):
+    """`--impl reference` prints one JSON line with the contract's keys (tiny shapes so that the CPU suite stays short)."""
+    import json
+    import types
+    import bench
+    old = dict(bench.CFG)
+    bench.CFG.update(L=24, layers=1, z_g=16, z_l=8)
+    try:
+        bench.run_reference(types.SimpleNamespace(gpus=1, steps=1, warmup=1, config="train"))
+    finally:
+        bench.CFG.clear()
+        bench.CFG.update(old)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"] == "train_conformers_per_s"
