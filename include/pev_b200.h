@@ -129,33 +129,37 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
 
 /* bwd2 (backward of fwd2 and of the aggregation; SURVEY.md 8a, half domain: d silu(2h)/dh = 1 + r(h)):
  * ghs = gw w6 (1 + r(hs)), gm = ghs (W5/2) + gagg[row], ghv = gm (1 + r(hv)) -> ghvT tile images;
- * db2h[256] = sum_e ghv (zeroed inside; db2 = db2h / 2).  W5thp = pack(W5, transpose=1, scale=0.5). */
+ * db2h[256] = sum_e ghv (db2 = db2h / 2; per-CTA partials in `workspace`, summed in a fixed order: no atomics).
+ * W5thp = pack(W5, transpose=1, scale=0.5); `workspace`: pev_edge2_wgrad_workspace_bytes(). */
 int pev_edge2_bwd2(const void* hs /*bf16 [E,256]*/, const float* gw /*[E]*/, const float* w6,
                    const void* W5thp, const float* gagg /*[N,256]*/, const int32_t* row,
-                   const void* hvT, int64_t num_edges, void* ghvT /*tile images*/, float* db2h,
-                   void* stream);
+                   const void* hvT, int64_t num_edges, float* workspace, void* ghvT /*tile images*/,
+                   float* db2h, void* stream);
 /* bwd1 (backward of fwd1): ga = ghv (W2/2), ghu = ga (1 + r(hu)) with hu rebuilt from ABh, d2, wd;
- * writes ghu (bf16 [E,256] = dL/dhu) and gd2[e] = ghu . (wd/2) (zeroed inside).
- * W2thp = pack(W2, transpose=1, scale=0.5). */
+ * writes ghu (bf16 [E,256] = dL/dhu) and gd2[e] = ghu . (wd/2): the four column quarters of an edge are written to
+ * gd2_parts[4][E] (scratch) and summed in a fixed order.  W2thp = pack(W2, transpose=1, scale=0.5). */
 int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh /*fp16 [N,512]*/,
                    const float* d2, const int32_t* row, const int32_t* col, const float* wd,
-                   int64_t num_edges, void* ghu /*bf16 [E,256]*/, float* gd2 /*[E]*/, void* stream);
+                   int64_t num_edges, void* ghu /*bf16 [E,256]*/, float* gd2 /*[E]*/,
+                   float* gd2_parts /*[4,E] scratch*/, void* stream);
 
 /* Segment sums of ghu over CSR rows / CSC columns (gA | gB = dL/dABh, fp32 [N,512]) and
- * gwdh[256] = sum_e d2[e] ghu[e] (zeroed inside; dL/dwd = gwdh / 2): one warp per node, deterministic order. */
+ * gwdh[256] = sum_e d2[e] ghu[e] (dL/dwd = gwdh / 2): one warp per node, deterministic order; per-block partials
+ * of gwdh in `workspace` (pev_edge2_wgrad_workspace_bytes()), summed in a fixed order. */
 int pev_edge2_sums(const void* ghu /*bf16 [E,256]*/, const float* d2, const int32_t* row_ptr,
                    const int32_t* col_ptr, const int32_t* csc_perm, int64_t num_nodes, int64_t num_edges,
-                   float* gAB /*[N,512]*/, float* gwdh /*[256]*/, void* stream);
+                   float* workspace, float* gAB /*[N,512]*/, float* gwdh /*[256]*/, void* stream);
 /* gx[i] += sum over the edges at node i of +-2 gd2[e] (x_row - x_col): the coordinate part of
  * pev_edge_prologue_bwd on its own (d d2 / d x). */
 int pev_edge_coord_bwd_accum(const float* gd2, const float* x, const int32_t* row_ptr, const int32_t* row,
                              const int32_t* col, const int32_t* col_ptr, const int32_t* csc_perm,
                              int64_t num_nodes, int64_t num_edges, float* gx_accum, void* stream);
 /* Weight gradients of the two 256x256 edge linears as split-K tcgen05 GEMMs over the edge dimension; both
- * operands come from hs / mT / ghvT and the node projection (a is rebuilt on the fly).  `workspace` holds one
- * 256x256 fp32 partial per CTA (pev_edge2_wgrad_workspace_bytes()); the partials are summed in a fixed order.
+ * operands come from hs / mT / ghvT and the node projection (a is rebuilt on the fly).  `workspace`
+ * (pev_edge2_wgrad_workspace_bytes(): one 256x256 fp32 partial per CTA + the per-CTA column-sum partials of bwd2 /
+ * wgrad5 / sums) is shared by the backward kernels of a layer; all partials are summed in a fixed order.
  *   wgrad5: dW5[k,f] = sum_e gs[e,k] m[e,f] (full-domain gradient of phi_x.0.weight), db5[256] = sum_e ghs
- *           (half domain: db5 = result / 2), dw6[256] = sum_e gw silu(s)  (db5, dw6 zeroed inside)
+ *           (half domain: db5 = result / 2), dw6[256] = sum_e gw silu(s)  (no atomics)
  *   wgrad2: dW2[f,j] = sum_e gv[e,f] a[e,j] (full-domain gradient of phi_e.2.weight) */
 int64_t pev_edge2_wgrad_workspace_bytes(void);
 int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* mT, int64_t num_edges,
@@ -170,12 +174,15 @@ int pev_edge2_wgrad2(const void* ghvT, const void* ABh, const float* d2, const i
 int pev_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
                           float eps, int64_t N, int32_t D, float* r_out, float* y, float* mean,
                           float* rstd, void* stream);
-/* One pass over gy and r: gr = dL/dr and the column sums dgamma[D], dbeta[D] (zeroed inside). */
+/* One pass over gy and r: gr = dL/dr and the column sums dgamma[D], dbeta[D].  Column sums go through per-block
+ * partials in `workspace` (pev_node_workspace_bytes()) and a fixed-order reduction: no atomics, bit-reproducible. */
+int64_t pev_node_workspace_bytes(void);
 int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const float* mean,
-                      const float* rstd, int64_t N, int32_t D, float* gr, float* dgamma, float* dbeta,
-                      void* stream);
-/* out[D] = sum over rows of g[N,D] (bias gradients of the node-level linears; zeroed inside). */
-int pev_column_sum(const float* g, int64_t N, int32_t D, float* out, void* stream);
+                      const float* rstd, int64_t N, int32_t D, float* workspace, float* gr, float* dgamma,
+                      float* dbeta, void* stream);
+/* out[D] = sum over rows of g[N,D] (bias gradients of the node-level linears), D <= 1024; per-block partials in
+ * `workspace` (pev_node_workspace_bytes()), fixed-order reduction. */
+int pev_column_sum(const float* g, int64_t N, int32_t D, float* workspace, float* out, void* stream);
 
 /* ---------------------------------------------------------------- K3: losses
  * Forward accumulators: acc_global[2*PEV_NUM_TERMS] doubles (numerator, denominator per term;

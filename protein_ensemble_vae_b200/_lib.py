@@ -59,14 +59,15 @@ _PROTOS_TC = {
     "pev_edge_d2": (c_int32, [_P, _P, _P, _L, _P, _P]),
     "pev_edge2_fwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P]),
     "pev_edge2_fwd2": (c_int32, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
-    "pev_edge2_bwd2": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
-    "pev_edge2_bwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "pev_edge2_bwd2": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
+    "pev_edge2_bwd1": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     "pev_kabsch_rmsd_pairs": (c_int32, [_P, _P, _I, _I, _I, _P, _P]),
     # node-level kernels (csrc/node_kernels.cu)
     "pev_add_layernorm_fwd": (c_int32, [_P, _P, _P, _P, c_float, _L, _I, _P, _P, _P, _P, _P]),
-    "pev_layernorm_bwd": (c_int32, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),
-    "pev_column_sum": (c_int32, [_P, _L, _I, _P, _P]),
-    "pev_edge2_sums": (c_int32, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
+    "pev_node_workspace_bytes": (c_int64, []),
+    "pev_layernorm_bwd": (c_int32, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
+    "pev_column_sum": (c_int32, [_P, _L, _I, _P, _P, _P]),
+    "pev_edge2_sums": (c_int32, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P]),
     "pev_edge_coord_bwd_accum": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pev_edge2_wgrad_workspace_bytes": (c_int64, []),
     "pev_edge2_wgrad5": (c_int32, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),

@@ -399,7 +399,7 @@ constexpr int F2_MMA_WARP = 16;
 constexpr int F2_TMA_WARP = 17;
 constexpr int F2_THREADS = 32 * (F2_EPI_WARPS + 4);     // 640 -> 96 registers at launch
 constexpr int F2_REGS_EPI = 104;
-using SmemF2 = SmemL<3, 512, 16 * 2048>;                // 3-stage ring + 16 x 2 KB row-box staging (TMA tensor store of hs)
+using SmemF2 = SmemL<3, 512 + 768, 16 * 2048>;          // 3-stage ring + b5h | w6 | 2 x 3 x 128 dot partials + 16 x 2 KB row-box staging
 
 struct Fwd2Params {
   const uint8_t* mT;      // tile images of m = silu(v)
@@ -408,11 +408,14 @@ struct Fwd2Params {
   const float* w6;        // [256]
   const float* b6;        // [1]
   __nv_bfloat16* hs;      // [E,256] hs = s/2 (training) or null
-  float* w;               // [E] (+=, zeroed by the launcher)
+  float* w;               // [E]
   int64_t E;
   int num_tiles;
   int dbg;
 };
+
+// named barrier of the four warps that share a TMEM lane quarter (ids 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
 template <int DBG, bool TRAIN>   // TRAIN: hs is written (p.hs != null)
 __global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p, const __grid_constant__ CUtensorMap hs_map) {
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p,
   uint8_t* sA = smem + SmemF2::A_OFF;
   float* sBias = reinterpret_cast<float*>(smem + SmemF2::VEC_OFF);
   float* sW6 = sBias + H;
+  float* sPart = sW6 + H;          // [tile parity 2][column quarter 1..3][128 edges]: partial dots, combined in fixed order
   const Bars B = make_bars(smem + SmemF2::BAR_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < H; k += F2_THREADS) {
@@ -556,7 +560,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) fwd2_kernel(const Fwd2Params p,
           dot = fmaf(silu_h(val[4 * j4 + 3]), w.w, dot);
         }
       }
-      if (valid) atomicAdd(p.w + e, dot + b6);
+      // w[e] = ((q0 + b6) + q1) + (q2 + q3): the four column quarters of an edge live in four warps; the partials meet
+      // in shared memory (two buffers by tile parity: a writer reaches tile n + 2 only after the reader left tile n)
+      float* part = sPart + (it & 1) * 3 * TILE_M + q * 32 + lane;
+      if (cq != 0) part[(cq - 1) * TILE_M] = dot;
+      quarter_barrier(q);
+      if (cq == 0 && valid) p.w[e] = ((dot + b6) + part[0]) + (part[TILE_M] + part[2 * TILE_M]);
     }
     if (lane == 0) bulk_wait_all();
   }
@@ -581,7 +590,7 @@ struct Bwd2Params {
   const int32_t* row;         // [E]
   const uint8_t* hvT;         // tile images of hv
   uint8_t* ghvT;              // tile images of ghv = dL/dhv (out)
-  float* db2h;                // [256] (+=) sum_e ghv
+  float* db2_partial;         // [gridDim.x][256]: per-CTA sum_e ghv, reduced in fixed order by the launcher
   int64_t E;
   int num_tiles;
   int dbg;
@@ -864,7 +873,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bwd2_kernel(const Bwd2Params p
       row_c = row_n; row_n = row_nn; gaF = gaFn; gaL = gaLn;
     }
     if (lane == 0) bulk_wait_all();
-    atomicAdd(p.db2h + f, dbacc2.x + dbacc2.y);
+    p.db2_partial[(int64_t)blockIdx.x * H + f] = dbacc2.x + dbacc2.y;
   }
   PEV_TC2_EPILOGUE()
 }
@@ -888,7 +897,7 @@ struct Bwd1Params {
   const int32_t* col;         // [E]
   const float* wd;            // [256] (full domain; halved on load)
   __nv_bfloat16* ghu;         // [E,256] (out) dL/dhu
-  float* gd2;                 // [E] (+=, zeroed by the launcher)
+  float* gd2_parts;           // [4][E]: per column quarter, summed in fixed order by sum4_kernel
   int64_t E;
   int num_tiles;
   int dbg;
@@ -1069,7 +1078,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) bwd1_kernel(const Bwd1Params p,
           if (lane == 0) tma_store_2d(&ghu_map, col0, (int)((int64_t)tile * TILE_M + q * 32), sbuf);
         }
       }
-      if (valid) atomicAdd(p.gd2 + e, dot);
+      if (valid) p.gd2_parts[(int64_t)cq * p.E + e] = dot;
       nr = nrn; nc = ncn; dd = ddn;
     }
     if (lane == 0) bulk_wait_all();
@@ -1099,8 +1108,8 @@ constexpr int WG_STAGES = 3;
 constexpr int WG_ROW_WARPS = 16;
 constexpr int WG_MMA_WARP = 16;
 constexpr int WG_TMA_WARP = 17;
-constexpr int WG_VEC_OFF = WG_STAGES * WG_STAGE_BYTES;                 // 4 x 256 floats
-constexpr int WG_BAR_OFF = WG_VEC_OFF + 4 * H * 4;
+constexpr int WG_VEC_OFF = WG_STAGES * WG_STAGE_BYTES;                 // 256 floats + 2 x [4 row groups][256] column sums
+constexpr int WG_BAR_OFF = WG_VEC_OFF + 9 * H * 4;
 constexpr int WG_SMEM_BYTES = WG_BAR_OFF + 128 + 1024;
 template <int MODE> struct WgCfg {
   static constexpr int WARPS = 20;
@@ -1114,8 +1123,7 @@ struct WgradParams {
   const float* gw;            // [E]
   const float* w6;            // [256]
   const uint8_t* mT;          // tile images of m = silu(v)
-  float* db5h;                // [256] (+=)
-  float* dw6;                 // [256] (+=)
+  float* colsum_partial;      // [gridDim.x][2][256]: per-CTA sum_e ghs | sum_e gw t, reduced in fixed order by the launcher
   // MODE 2
   const uint8_t* ghvT;        // tile images of ghv
   const __half* ABh;           // [N,512] fp16
@@ -1142,8 +1150,6 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < H; k += WgCfg<MODE>::THREADS) {
     sVec[k] = MODE == 5 ? p.w6[k] : 0.5f * p.wd[k];
-    sVec[H + k] = 0.f;
-    sVec[2 * H + k] = 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -1226,9 +1232,9 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
         a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
         a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
         a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-        if (lane < 8) {
-          atomicAdd(&sVec[H + c0 + j], a0);
-          atomicAdd(&sVec[2 * H + c0 + j], a1);
+        if (lane < 8) {                              // slot of this warp's row group: no two warps share one
+          sVec[H + (warp >> 2) * H + c0 + j] = a0;
+          sVec[5 * H + (warp >> 2) * H + c0 + j] = a1;
         }
       }
     } else {
@@ -1354,13 +1360,21 @@ __global__ void __launch_bounds__(WgCfg<MODE>::THREADS, 1) wgrad_kernel(const Wg
   tc_fence_before();
   __syncthreads();
   if (MODE == 5 && threadIdx.x < H) {
-    atomicAdd(p.db5h + threadIdx.x, sVec[H + threadIdx.x]);
-    atomicAdd(p.dw6 + threadIdx.x, sVec[2 * H + threadIdx.x]);
+    const int k = threadIdx.x;
+    float* dst = p.colsum_partial + (int64_t)blockIdx.x * 2 * H;
+    dst[k] = (sVec[H + k] + sVec[2 * H + k]) + (sVec[3 * H + k] + sVec[4 * H + k]);
+    dst[H + k] = (sVec[5 * H + k] + sVec[6 * H + k]) + (sVec[7 * H + k] + sVec[8 * H + k]);
   }
   if (warp == WG_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// out[e] = (parts[0][e] + parts[1][e]) + (parts[2][e] + parts[3][e])
+__global__ void sum4_kernel(const float* __restrict__ parts, int64_t E, float* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) out[e] = (parts[e] + parts[E + e]) + (parts[2 * E + e] + parts[3 * E + e]);
 }
 
 // out[i] = scale * sum_g partial[g][i]   (fixed summation order)
@@ -1385,10 +1399,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int G, fl
 // in ascending edge order (deterministic), 4 edge rows in flight.  gA[i] = sum_{row e = i} ghu[e], gB[j] = sum_{col e = j}
 // ghu[e]; the (wd/2)-gradient sum_e d2[e] ghu[e] stays in registers across the nodes a warp visits (one atomic per
 // feature per warp at the end).  HBM-bound: ghu is read twice (1024 B per edge), gAB written once.
-__global__ void __launch_bounds__(256)
+// (256, 3): three resident blocks per SM (see the launcher); without the second argument ptxas settles on 48 registers
+// once the kernel contains a barrier and serialises the eight row loads in flight (0.89 -> 1.22 ms)
+__global__ void __launch_bounds__(256, 3)
 edge_sums_kernel(const uint4* __restrict__ ghu, const float* __restrict__ d2, const int32_t* __restrict__ row_ptr,
                  const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ csc_perm, int64_t N,
-                 float* __restrict__ gAB, float* __restrict__ gwdh) {
+                 float* __restrict__ gAB, float* __restrict__ gwd_partial /*[gridDim.x][256]*/) {
+  __shared__ float swd[8][H];
   constexpr int UNR = 8;                        // edge rows in flight per warp
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1462,8 +1479,13 @@ edge_sums_kernel(const uint4* __restrict__ ghu, const float* __restrict__ d2, co
     ob[0] = make_float4(b[0], b[1], b[2], b[3]);
     ob[1] = make_float4(b[4], b[5], b[6], b[7]);
   }
+  // sum_e d2 ghu: per-warp sums -> fixed-order sum over the block's eight warps -> per-block partial (no atomics)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(gwdh + lane * 8 + j, wacc[j]);
+  for (int j = 0; j < 8; ++j) swd[threadIdx.x >> 5][lane * 8 + j] = wacc[j];
+  __syncthreads();
+  const int k = threadIdx.x;
+  gwd_partial[(int64_t)blockIdx.x * H + k] =
+      ((swd[0][k] + swd[1][k]) + (swd[2][k] + swd[3][k])) + ((swd[4][k] + swd[5][k]) + (swd[6][k] + swd[7][k]));
 }
 
 // d2[e] = |x[row[e]] - x[col[e]]|^2  (models/en_gnn_decoder.py:61-62), one thread per edge
@@ -1516,6 +1538,12 @@ static int grid_for(int num_tiles) {
 
 using namespace pev;
 typedef __nv_bfloat16 bf16_t;
+
+// workspace layout (floats): [sms][256*256] weight-gradient partials | [sms][256] db2 | [sms][2][256] db5, dw6 |
+// [3 sms][256] gwd
+static int64_t ws_off_db2() { return (int64_t)sm_count() * tc2::H * tc2::H; }
+static int64_t ws_off_colsum() { return ws_off_db2() + (int64_t)sm_count() * tc2::H; }
+static int64_t ws_off_gwd() { return ws_off_colsum() + (int64_t)sm_count() * 2 * tc2::H; }
 
 template <int MODE>
 static int launch_wgrad(tc2::WgradParams& p, float scale, float* dW, cudaStream_t st) {
@@ -1606,7 +1634,6 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
   if (num_edges == 0) return 0;
   PEV_REQUIRE(mT && w_out, "edge arrays missing");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(w_out, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
   bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
@@ -1647,12 +1674,15 @@ int pev_edge2_fwd2(const void* mT, const void* W5hp, const float* b5, const floa
 }
 
 int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void* W5thp, const float* gagg,
-                   const int32_t* row, const void* hvT, int64_t num_edges, void* ghvT, float* db2h, void* stream) {
+                   const int32_t* row, const void* hvT, int64_t num_edges, float* workspace, void* ghvT, float* db2h,
+                   void* stream) {
   PEV_REQUIRE(w6 && W5thp && db2h && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(db2h, 0, sizeof(float) * tc2::H, st);
-  if (num_edges == 0) return 0;
-  PEV_REQUIRE(hs && gw && gagg && row && hvT && ghvT, "edge arrays missing");
+  if (num_edges == 0) {
+    cudaMemsetAsync(db2h, 0, sizeof(float) * tc2::H, st);
+    return 0;
+  }
+  PEV_REQUIRE(hs && gw && gagg && row && hvT && ghvT && workspace, "edge arrays missing");
   static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
   bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
@@ -1664,7 +1694,8 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   }
   tc2::Bwd2Params p = {};
   p.hs = reinterpret_cast<const bf16_t*>(hs); p.gw = gw; p.w6 = w6; p.W5thp = W5thp; p.gagg = gagg; p.row = row;
-  p.hvT = reinterpret_cast<const uint8_t*>(hvT); p.ghvT = reinterpret_cast<uint8_t*>(ghvT); p.db2h = db2h;
+  p.hvT = reinterpret_cast<const uint8_t*>(hvT); p.ghvT = reinterpret_cast<uint8_t*>(ghvT);
+  p.db2_partial = workspace + ws_off_db2();
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
@@ -1673,16 +1704,17 @@ int pev_edge2_bwd2(const void* hs, const float* gw, const float* w6, const void*
   else
 #endif
   tc2::bwd2_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::NUM_THREADS, tc2::SmemB2::BYTES, st>>>(p);
-  return after_launch("edge2_bwd2_kernel");
+  if (int rc = after_launch("edge2_bwd2_kernel")) return rc;
+  return launch_partial_reduce(p.db2_partial, tc2::grid_for(p.num_tiles), tc2::H, tc2::H, 1.0f, db2h, st);
 }
 
 int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const float* d2, const int32_t* row,
-                   const int32_t* col, const float* wd, int64_t num_edges, void* ghu, float* gd2, void* stream) {
+                   const int32_t* col, const float* wd, int64_t num_edges, void* ghu, float* gd2, float* gd2_parts,
+                   void* stream) {
   PEV_REQUIRE(W2thp && wd && num_edges >= 0, "bad argument");
   if (num_edges == 0) return 0;
-  PEV_REQUIRE(ghvT && ABh && d2 && row && col && ghu && gd2, "edge arrays missing");
+  PEV_REQUIRE(ghvT && ABh && d2 && row && col && ghu && gd2 && gd2_parts, "edge arrays missing");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(gd2, 0, sizeof(float) * (size_t)num_edges, st);
   static bool configured_dev[pev::kMaxDevices] = {};   // the attribute is per device
   bool& configured = configured_dev[pev::current_device()];
   if (!configured) {
@@ -1694,7 +1726,7 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   }
   tc2::Bwd1Params p = {};
   p.ghvT = reinterpret_cast<const uint8_t*>(ghvT); p.W2thp = W2thp; p.ABh = reinterpret_cast<const __half*>(ABh);
-  p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.ghu = reinterpret_cast<bf16_t*>(ghu); p.gd2 = gd2;
+  p.d2 = d2; p.row = row; p.col = col; p.wd = wd; p.ghu = reinterpret_cast<bf16_t*>(ghu); p.gd2_parts = gd2_parts;
   p.E = num_edges;
   p.num_tiles = (int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M);
   p.dbg = tc2::debug_mask();
@@ -1705,15 +1737,20 @@ int pev_edge2_bwd1(const void* ghvT, const void* W2thp, const void* ABh, const f
   else
 #endif
   tc2::bwd1_kernel<0><<<tc2::grid_for(p.num_tiles), tc2::B1_THREADS, tc2::SmemB1::BYTES, st>>>(p, ghu_map);
-  return after_launch("edge2_bwd1_kernel");
+  if (int rc = after_launch("edge2_bwd1_kernel")) return rc;
+  tc2::sum4_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, st>>>(gd2_parts, num_edges, gd2);
+  return after_launch("sum4_kernel");
 }
 
 int pev_edge2_sums(const void* ghu, const float* d2, const int32_t* row_ptr, const int32_t* col_ptr,
-                   const int32_t* csc_perm, int64_t num_nodes, int64_t num_edges, float* gAB, float* gwdh, void* stream) {
-  PEV_REQUIRE(row_ptr && col_ptr && gAB && gwdh && num_nodes >= 0, "bad argument");
+                   const int32_t* csc_perm, int64_t num_nodes, int64_t num_edges, float* workspace, float* gAB,
+                   float* gwdh, void* stream) {
+  PEV_REQUIRE(row_ptr && col_ptr && gAB && gwdh && workspace && num_nodes >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(gwdh, 0, sizeof(float) * tc2::H, st);
-  if (num_nodes == 0) return 0;
+  if (num_nodes == 0) {
+    cudaMemsetAsync(gwdh, 0, sizeof(float) * tc2::H, st);
+    return 0;
+  }
   PEV_REQUIRE(num_edges == 0 || (ghu && d2 && csc_perm), "edge arrays missing");
   int64_t grid = (num_nodes + 7) / 8;
   // 3 blocks (24 warps) per SM: consecutive nodes go to consecutive warps, so the nodes in flight span ~3500 x 40 KB
@@ -1721,28 +1758,35 @@ int pev_edge2_sums(const void* ghu, const float* d2, const int32_t* row_ptr, con
   // neighbours i +- W); with all 32 resident warps per SM the window outgrows L2 (0.91 ms against 0.77 ms)
   const int64_t cap = (int64_t)sm_count() * 3;
   if (grid > cap) grid = cap;
+  float* part = workspace + ws_off_gwd();
   tc2::edge_sums_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(ghu), d2, row_ptr, col_ptr,
-                                                        csc_perm, num_nodes, gAB, gwdh);
-  return after_launch("edge2_sums_kernel");
+                                                        csc_perm, num_nodes, gAB, part);
+  if (int rc = after_launch("edge2_sums_kernel")) return rc;
+  return launch_partial_reduce(part, (int)grid, tc2::H, tc2::H, 1.0f, gwdh, st);
 }
 
-int64_t pev_edge2_wgrad_workspace_bytes(void) { return (int64_t)sm_count() * tc2::H * tc2::H * (int64_t)sizeof(float); }
+int64_t pev_edge2_wgrad_workspace_bytes(void) {
+  return (ws_off_gwd() + (int64_t)sm_count() * 3 * tc2::H) * (int64_t)sizeof(float);
+}
 
 int pev_edge2_wgrad5(const void* hs, const float* gw, const float* w6, const void* mT, int64_t num_edges,
                      float* workspace, float* dW5, float* db5, float* dw6, void* stream) {
   PEV_REQUIRE(w6 && dW5 && db5 && dw6 && num_edges >= 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(db5, 0, sizeof(float) * tc2::H, st);
-  cudaMemsetAsync(dw6, 0, sizeof(float) * tc2::H, st);
   if (num_edges == 0) {
+    cudaMemsetAsync(db5, 0, sizeof(float) * tc2::H, st);
+    cudaMemsetAsync(dw6, 0, sizeof(float) * tc2::H, st);
     cudaMemsetAsync(dW5, 0, sizeof(float) * tc2::H * tc2::H, st);
     return 0;
   }
   PEV_REQUIRE(hs && gw && mT && workspace, "edge arrays missing");
   tc2::WgradParams p = {};
   p.hs = reinterpret_cast<const bf16_t*>(hs); p.gw = gw; p.w6 = w6; p.mT = reinterpret_cast<const uint8_t*>(mT);
-  p.db5h = db5; p.dw6 = dw6; p.partial = workspace; p.E = num_edges;
-  return launch_wgrad<5>(p, 0.5f, dW5, st);
+  p.colsum_partial = workspace + ws_off_colsum(); p.partial = workspace; p.E = num_edges;
+  if (int rc = launch_wgrad<5>(p, 0.5f, dW5, st)) return rc;
+  const int grid = tc2::grid_for((int)((num_edges + tc2::TILE_M - 1) / tc2::TILE_M));
+  if (int rc = launch_partial_reduce(p.colsum_partial, grid, 2 * tc2::H, tc2::H, 1.0f, db5, st)) return rc;
+  return launch_partial_reduce(p.colsum_partial + tc2::H, grid, 2 * tc2::H, tc2::H, 1.0f, dw6, st);
 }
 
 int pev_edge2_wgrad2(const void* ghvT, const void* ABh, const float* d2, const int32_t* row, const int32_t* col,

@@ -63,12 +63,10 @@ template <int D>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ r, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int64_t N,
-                     float* __restrict__ gr, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     float* __restrict__ gr, float* __restrict__ partial /*[gridDim.x][2][D]*/) {
   constexpr int V = D / 128;
-  __shared__ float sG[D], sB[D];
+  __shared__ float sG[8][D], sB[8][D];                  // one slot per warp: summed in a fixed order, no atomics
   const int lane = threadIdx.x & 31;
-  for (int k = threadIdx.x; k < D; k += blockDim.x) sG[k] = sB[k] = 0.f;
-  __syncthreads();
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   float4 g4[V], dg[V], db[V];
@@ -107,20 +105,21 @@ layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ r, 
   }
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    const int c = 4 * (lane + 32 * k);
-    atomicAdd(&sG[c], dg[k].x); atomicAdd(&sG[c + 1], dg[k].y); atomicAdd(&sG[c + 2], dg[k].z); atomicAdd(&sG[c + 3], dg[k].w);
-    atomicAdd(&sB[c], db[k].x); atomicAdd(&sB[c + 1], db[k].y); atomicAdd(&sB[c + 2], db[k].z); atomicAdd(&sB[c + 3], db[k].w);
+    const int c = 4 * (lane + 32 * k), w = threadIdx.x >> 5;
+    *reinterpret_cast<float4*>(&sG[w][c]) = dg[k];
+    *reinterpret_cast<float4*>(&sB[w][c]) = db[k];
   }
   __syncthreads();
+  float* dst = partial + (int64_t)blockIdx.x * 2 * D;
   for (int k = threadIdx.x; k < D; k += blockDim.x) {
-    atomicAdd(dgamma + k, sG[k]);
-    atomicAdd(dbeta + k, sB[k]);
+    dst[k] = ((sG[0][k] + sG[1][k]) + (sG[2][k] + sG[3][k])) + ((sG[4][k] + sG[5][k]) + (sG[6][k] + sG[7][k]));
+    dst[D + k] = ((sB[0][k] + sB[1][k]) + (sB[2][k] + sB[3][k])) + ((sB[4][k] + sB[5][k]) + (sB[6][k] + sB[7][k]));
   }
 }
 
 // out[c] = sum_rows g[row, c]  (bias gradients): block of 256 threads owns 64 columns x 4 row lanes
 __global__ void __launch_bounds__(256)
-column_sum_kernel(const float* __restrict__ g, int64_t N, int D, float* __restrict__ out) {
+column_sum_kernel(const float* __restrict__ g, int64_t N, int D, float* __restrict__ partial /*[gridDim.y][D]*/) {
   __shared__ float4 sm[256];
   const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;          // 16 float4 columns x 16 row lanes
   const int col4 = blockIdx.x * 16 + c4;                            // float4 column index
@@ -138,8 +137,7 @@ column_sum_kernel(const float* __restrict__ g, int64_t N, int D, float* __restri
       const float4 v = sm[k * 16 + c4];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    atomicAdd(out + 4 * col4, acc.x); atomicAdd(out + 4 * col4 + 1, acc.y);
-    atomicAdd(out + 4 * col4 + 2, acc.z); atomicAdd(out + 4 * col4 + 3, acc.w);
+    reinterpret_cast<float4*>(partial + (int64_t)blockIdx.y * D)[col4] = acc;
   }
 }
 
@@ -168,33 +166,45 @@ int pev_add_layernorm_fwd(const float* x, const float* res, const float* gamma, 
   return after_launch("add_layernorm_fwd_kernel");
 }
 
+int64_t pev_node_workspace_bytes(void) { return (int64_t)sm_count() * 8 * 2 * 512 * (int64_t)sizeof(float); }
+
 int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const float* mean, const float* rstd,
-                      int64_t N, int32_t D, float* gr, float* dgamma, float* dbeta, void* stream) {
+                      int64_t N, int32_t D, float* workspace, float* gr, float* dgamma, float* dbeta, void* stream) {
   PEV_REQUIRE(N >= 0 && (D == 256 || D == 512) && dgamma && dbeta, "bad argument");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st);
-  cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st);
-  if (N == 0) return 0;
-  PEV_REQUIRE(gy && r && gamma && mean && rstd && gr, "null argument");
+  if (N == 0) {
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st);
+    return 0;
+  }
+  PEV_REQUIRE(gy && r && gamma && mean && rstd && gr && workspace, "null argument");
+  const int grid = rows_grid(N);
   if (D == 256)
-    layernorm_bwd_kernel<256><<<rows_grid(N), 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, dgamma, dbeta);
+    layernorm_bwd_kernel<256><<<grid, 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, workspace);
   else
-    layernorm_bwd_kernel<512><<<rows_grid(N), 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, dgamma, dbeta);
-  return after_launch("layernorm_bwd_kernel");
+    layernorm_bwd_kernel<512><<<grid, 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, workspace);
+  if (int rc = after_launch("layernorm_bwd_kernel")) return rc;
+  // dgamma | dbeta are adjacent in a partial row: one launch over 2 D columns when the outputs are adjacent too
+  if (dbeta == dgamma + D) return launch_partial_reduce(workspace, grid, 2 * D, 2 * D, 1.0f, dgamma, st);
+  if (int rc = launch_partial_reduce(workspace, grid, 2 * D, D, 1.0f, dgamma, st)) return rc;
+  return launch_partial_reduce(workspace + D, grid, 2 * D, D, 1.0f, dbeta, st);
 }
 
-int pev_column_sum(const float* g, int64_t N, int32_t D, float* out, void* stream) {
-  PEV_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && out, "bad argument (D must be a multiple of 4)");
+int pev_column_sum(const float* g, int64_t N, int32_t D, float* workspace, float* out, void* stream) {
+  PEV_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && out, "bad argument (D must be a multiple of 4, <= 1024)");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(out, 0, sizeof(float) * D, st);
-  if (N == 0) return 0;
-  PEV_REQUIRE(g, "null argument");
+  if (N == 0) {
+    cudaMemsetAsync(out, 0, sizeof(float) * D, st);
+    return 0;
+  }
+  PEV_REQUIRE(g && workspace, "null argument");
   const int gx = (D / 4 + 15) / 16;
   int64_t gy = (N + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8 / gx + 1;
   if (gy > cap) gy = cap;
-  column_sum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(g, N, D, out);
-  return after_launch("column_sum_kernel");
+  column_sum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(g, N, D, workspace);
+  if (int rc = after_launch("column_sum_kernel")) return rc;
+  return launch_partial_reduce(workspace, (int)gy, D, D, 1.0f, out, st);
 }
 
 }  // extern "C"

@@ -42,14 +42,26 @@ class _tf32_matmul:
         return False
 
 
+_NODE_WS: dict = {}
+
+
+def node_workspace(device) -> torch.Tensor:
+    """Per-device scratch for the fixed-order column-sum reductions of the node-level kernels."""
+    ws = _NODE_WS.get(device)
+    if ws is None:
+        ws = torch.empty(_lib.lib().cdll.pev_node_workspace_bytes() // 4, dtype=torch.float32, device=device)
+        _NODE_WS[device] = ws
+    return ws
+
+
 def column_sum(g: torch.Tensor) -> torch.Tensor:
-    """``g.sum(0)`` of a contiguous fp32 ``[N,D]`` (bias gradients) on ``pev_column_sum``."""
+    """``g.sum(0)`` of a contiguous fp32 ``[N,D]`` (bias gradients) on ``pev_column_sum`` (bit-reproducible)."""
     N, D = g.shape
-    if D % 4 or g.dtype != torch.float32:
+    if D % 4 or D > 1024 or g.dtype != torch.float32:
         return g.sum(0)
     with torch.cuda.device_of(g):
         out = torch.empty(D, dtype=torch.float32, device=g.device)
-        _lib.lib().call("pev_column_sum", ptr(g), N, D, ptr(out), stream(g))
+        _lib.lib().call("pev_column_sum", ptr(g), N, D, ptr(node_workspace(g.device)), ptr(out), stream(g))
     return out
 
 
@@ -80,10 +92,10 @@ class AddLayerNorm(torch.autograd.Function):
         N, D = r.shape
         with torch.cuda.device_of(r):
             gr = torch.empty_like(r)
-            dg = torch.empty(D, dtype=torch.float32, device=r.device)
-            db = torch.empty(D, dtype=torch.float32, device=r.device)
-            _lib.lib().call("pev_layernorm_bwd", ptr(gy), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), N, D, ptr(gr),
-                            ptr(dg), ptr(db), stream(r))
+            dgb = torch.empty(2 * D, dtype=torch.float32, device=r.device)     # adjacent: one reduction launch
+            dg, db = dgb[:D], dgb[D:]
+            _lib.lib().call("pev_layernorm_bwd", ptr(gy), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), N, D,
+                            ptr(node_workspace(r.device)), ptr(gr), ptr(dg), ptr(db), stream(r))
         return gr, (gr if ctx.has_res else None), dg, db, None
 
 

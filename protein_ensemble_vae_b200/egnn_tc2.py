@@ -197,7 +197,7 @@ class FusedEdgeV2(torch.autograd.Function):
             db2h = torch.empty(H, dtype=f32, device=dev)
             with _lib.profiled("edge2_bwd2"):
                 L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6v), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E,
-                       ptr(ghvT), ptr(db2h), st)
+                       ptr(ws), ptr(ghvT), ptr(db2h), st)
             gW5 = torch.empty(H, H, dtype=f32, device=dev)
             db5h, gw6 = torch.empty(H, dtype=f32, device=dev), torch.empty(H, dtype=f32, device=dev)
             with _lib.profiled("edge2_wgrad5"):
@@ -205,9 +205,11 @@ class FusedEdgeV2(torch.autograd.Function):
                        ptr(gw6), st)
             ghu = torch.empty(E, H, dtype=bf, device=dev)
             gd2 = torch.empty(max(E, 1), dtype=f32, device=dev)
+            gd2p = torch.empty(4 * max(E, 1), dtype=f32, device=dev)
             with _lib.profiled("edge2_bwd1"):
                 L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABb), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E,
-                       ptr(ghu), ptr(gd2), st)
+                       ptr(ghu), ptr(gd2), ptr(gd2p), st)
+            del gd2p
             gW2 = torch.empty(H, H, dtype=f32, device=dev)
             with _lib.profiled("edge2_wgrad2"):
                 L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(ABb), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ws),
@@ -217,7 +219,7 @@ class FusedEdgeV2(torch.autograd.Function):
             gwdh = torch.empty(H, dtype=f32, device=dev)
             with _lib.profiled("edge2_sums"):
                 L.call("pev_edge2_sums", ptr(ghu), ptr(d2), ptr(g.row_ptr), ptr(g.col_ptr), ptr(g.csc_perm), N, E,
-                       ptr(gAB), ptr(gwdh), st)
+                       ptr(ws), ptr(gAB), ptr(gwdh), st)
             L.call("pev_edge_coord_bwd_accum", ptr(gd2), ptr(x), ptr(g.row_ptr), ptr(g.row), ptr(g.col), ptr(g.col_ptr),
                    ptr(g.csc_perm), N, E, ptr(gx), st)
             gwd = 0.5 * gwdh                            # hu = ... + (wd/2) d2

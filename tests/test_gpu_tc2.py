@@ -105,10 +105,10 @@ def test_backward_kernels_match_emulation(lengths, W):
     dW5, dW2 = torch.empty(H, H, device="cuda"), torch.empty(H, H, device="cuda")
     db5h, dw6 = torch.empty(H, device="cuda"), torch.empty(H, device="cuda")
     P = lambda Wt: T2.packed_weight_scaled(Wt, 0.5, transpose=True)  # noqa: E731
-    L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(c["w6"]), ptr(P(c["W5"])), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ghvT),
+    L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(c["w6"]), ptr(P(c["W5"])), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ws), ptr(ghvT),
            ptr(db2h), st)
     L.call("pev_edge2_bwd1", ptr(ghvT), ptr(P(c["W2"])), ptr(c["ABh"]), ptr(d2), ptr(g.row), ptr(g.col), ptr(c["wd"]), E,
-           ptr(ghu), ptr(gd2), st)
+           ptr(ghu), ptr(gd2), ptr(torch.empty(4 * E, device="cuda")), st)
     L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(c["w6"]), ptr(mT), E, ptr(ws), ptr(dW5), ptr(db5h), ptr(dw6), st)
     L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(c["ABh"]), ptr(d2), ptr(g.row), ptr(g.col), ptr(c["wd"]), E, ptr(ws), ptr(dW2), st)
     ghs = gw[:, None] * c["w6"] * one_plus_r(hs.float())

@@ -77,11 +77,11 @@ db5h_k, dw6_k = torch.empty(H, device=dev), torch.empty(H, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 for rep in range(reps + 1):
     ev[0].record()
-    L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ghvT),
+    L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ws), ptr(ghvT),
            ptr(db2h_k), st)
     ev[1].record()
     L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABh), ptr(d2k), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ghu_k),
-           ptr(gd2_k), st)
+           ptr(gd2_k), ptr(torch.empty(4 * E, device=dev)), st)
     ev[2].record()
     L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(mT), E, ptr(ws), ptr(dW5_k), ptr(db5h_k), ptr(dw6_k), st)
     ev[3].record()

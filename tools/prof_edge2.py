@@ -31,6 +31,7 @@ agg, w, d2, gd2 = torch.empty(N, H, device=dev), torch.empty(E, device=dev), tor
 db2h, db5h, dw6 = (torch.empty(H, device=dev) for _ in range(3))
 dW5, dW2 = torch.empty(H, H, device=dev), torch.empty(H, H, device=dev)
 ws = torch.empty(L.cdll.pev_edge2_wgrad_workspace_bytes() // 4, device=dev)
+gd2p = torch.empty(4 * E, device=dev)
 gAB, part, gx = torch.empty(N, 2 * H, device=dev), torch.empty(N, H, device=dev), torch.zeros(N, 3, device=dev)
 names = ["fwd1", "fwd2", "bwd2", "wgrad5", "bwd1", "wgrad2", "sums", "fwd1_infer", "fwd2_infer"]
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
@@ -41,15 +42,15 @@ for rep in range(reps + 1):
     ev[1].record()
     L.call("pev_edge2_fwd2", ptr(mT), ptr(W5hp), ptr(b5), ptr(w6), ptr(b6), E, ptr(w), ptr(hs), st)
     ev[2].record()
-    L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ghvT), ptr(db2h), st)
+    L.call("pev_edge2_bwd2", ptr(hs), ptr(gw), ptr(w6), ptr(W5thp), ptr(gagg), ptr(g.row), ptr(hvT), E, ptr(ws), ptr(ghvT), ptr(db2h), st)
     ev[3].record()
     L.call("pev_edge2_wgrad5", ptr(hs), ptr(gw), ptr(w6), ptr(mT), E, ptr(ws), ptr(dW5), ptr(db5h), ptr(dw6), st)
     ev[4].record()
-    L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABh), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ghu), ptr(gd2), st)
+    L.call("pev_edge2_bwd1", ptr(ghvT), ptr(W2thp), ptr(ABh), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ghu), ptr(gd2), ptr(gd2p), st)
     ev[5].record()
     L.call("pev_edge2_wgrad2", ptr(ghvT), ptr(ABh), ptr(d2), ptr(g.row), ptr(g.col), ptr(wd), E, ptr(ws), ptr(dW2), st)
     ev[6].record()
-    L.call("pev_edge2_sums", ptr(ghu), ptr(d2), ptr(g.row_ptr), ptr(g.col_ptr), ptr(g.csc_perm), N, E, ptr(gAB), ptr(db2h), st)
+    L.call("pev_edge2_sums", ptr(ghu), ptr(d2), ptr(g.row_ptr), ptr(g.col_ptr), ptr(g.csc_perm), N, E, ptr(ws), ptr(gAB), ptr(db2h), st)
     ev[7].record()
     L.call("pev_edge2_fwd1", ptr(ABh), ptr(d2), ptr(wd), ptr(W2hp), ptr(b2), ptr(g.row), ptr(g.col), N, E, None, ptr(mT), ptr(agg), st)
     ev[8].record()
