@@ -265,6 +265,20 @@ int pev_edge3_fwd(const void* ABh /*fp16 [N,512]*/, const float* d2 /*[E]*/, con
                   int64_t num_nodes, int64_t num_edges, void* hv_rows /*bf16 [E,256] or NULL*/,
                   void* hs_rows /*bf16 [E,256] or NULL*/, float* agg /*[N,256]*/, float* w /*[E]*/, void* stream);
 
+/* ---------------------------------------------------------------- node-level linears on tcgen05 (csrc/node_gemm_kernels.cu)
+ * C[M,Nout] = epilogue(A W^T), A = [A1 | A2] (fp32 row-major [M,K1], [M,K2]; A2 may be NULL), W fp32 [Nout, K1+K2]
+ * row-major, operands read as TF32 with fp32 accumulation.  Replaces the node-level nn.Linear calls of
+ * EGNLayer.forward (models/en_gnn_decoder.py:65-73) and the element-wise kernels around them:
+ *   epilogue 0 ABH     out = fp16(scale * (C + bias))                 h-halves of phi_e[0] (:65-66), scale = 0.5
+ *            1 SILU    out = silu(C + bias), out2 = C + bias (or NULL)  phi_h[0..1] on [h | agg] (:70-71)
+ *            2 RES_LN  r = C + bias + aux; out = LayerNorm(r) (gamma, beta, eps); out2 = r, mean, rstd (or NULL)  (:71-73)
+ *            3 PLAIN   out = C + bias (+ aux)                          data gradients
+ *            4 DSILU   out = (C + bias) * silu'(aux)                   backward through phi_h[1]
+ * Nout in {256, 512}; K1, K2 multiples of 32; aux / out / out2 row-major with leading dimension Nout (RES_LN: 256). */
+int pev_node_gemm(int32_t epilogue, const float* A1, int32_t K1, const float* A2, int32_t K2, const float* W,
+                  const float* bias, int64_t M, int32_t Nout, float scale, const float* aux, const float* gamma,
+                  const float* beta, float eps, void* out, float* out2, float* mean, float* rstd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

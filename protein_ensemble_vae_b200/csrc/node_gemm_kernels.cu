@@ -1,0 +1,397 @@
+// Node-level linears of the bf16 path on tcgen05 (kind::tf32): the per-node GEMMs of one EGNN layer
+// (models/en_gnn_decoder.py:65-73 -- the h_i / h_j halves of phi_e[0], phi_h[0], phi_h[2]) with what used to be separate
+// element-wise kernels fused into the epilogue:
+//
+//   ABH     ABh = 0.5 (h [Wa|Wb]^T + [b1|0])  -> fp16 [N,512]   (the half-domain node projection the edge kernels gather;
+//                                                                replaces cuBLAS addmm + a float16 copy kernel)
+//   SILU    p = [h | agg] W3^T + b3 ; q = silu(p)               (two A operands: the concatenation is never built)
+//   RES_LN  r = h + q W4^T + b4 ; h' = LayerNorm(r)             (row statistics in the epilogue: lane = row)
+//   PLAIN   C = A B^T (+ bias) (+ residual)                     (data gradients: g W with a pre-transposed weight)
+//   DSILU   C = (A B^T) * silu'(p)                              (backward through phi_h[1])
+//
+// C[M, Nout] = A[M, K] . W[Nout, K]^T, fp32 operands read by the tensor core as TF32 (10-bit mantissa, fp32 accumulate)
+// -- the same arithmetic the round-1 path ran through cuBLAS with allow_tf32.  Tile 128 x 256, K-chunks of 32 floats
+// (128-byte SWIZZLE_128B rows) loaded by TMA tensor copies into a 4-stage ring, two TMEM accumulator stages, eight
+// epilogue warps (TMEM lane quarter x column half), persistent over the M tiles.  HBM-bound (AI ~ 100 flop/B).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "../../include/pev_b200.h"
+#include "pev_common.cuh"
+#include "tc_common.cuh"
+
+namespace pev {
+namespace ng {
+using namespace tcx;
+
+constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;     // 16 KB
+constexpr int B_BYTES = BN * BK * 4;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int VEC_OFF = STAGES * STAGE_BYTES;          // bias[512] | gamma[256] | beta[256]
+constexpr int LN_OFF = VEC_OFF + 1024 * 4;             // [2 column halves][128 rows][2] row statistics
+constexpr int BAR_OFF = LN_OFF + 2 * BM * 2 * 4;
+constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
+constexpr int THREADS = 32 * 10;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+enum Epi { EPI_ABH = 0, EPI_SILU = 1, EPI_RES_LN = 2, EPI_PLAIN = 3, EPI_DSILU = 4 };
+
+struct Params {
+  int64_t M;
+  int Nout;               // 256 or 512
+  int k1_chunks;          // K-chunks (32 floats) taken from A1, then k2_chunks from A2
+  int k2_chunks;
+  const float* bias;      // [Nout] or null
+  float scale;            // ABH: 0.5
+  // epilogue operands / outputs (row-major, leading dimension = Nout unless stated)
+  __half* out16;          // ABH
+  float* out;             // SILU: q; RES_LN: y; PLAIN / DSILU: C
+  float* out2;            // SILU: p (null in inference); RES_LN: r (null in inference)
+  const float* res;       // RES_LN: h [M,256]; PLAIN: residual [M,Nout] or null; DSILU: p [M,256]
+  const float* gamma;     // RES_LN
+  const float* beta;
+  float eps;
+  float* mean;            // RES_LN (null in inference)
+  float* rstd;
+};
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void half_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                 const __grid_constant__ CUtensorMap mapB) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* sBias = reinterpret_cast<float*>(smem + VEC_OFF);
+  float* sGamma = sBias + 512;
+  float* sBeta = sGamma + 256;
+  float* sLn = reinterpret_cast<float*>(smem + LN_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.Nout / BN;
+  const int m_tiles = (int)((p.M + BM - 1) / BM);
+  const int total = m_tiles * n_tiles;
+  const int kchunks = p.k1_chunks + p.k2_chunks;
+
+  for (int k = threadIdx.x; k < 512; k += THREADS) sBias[k] = (p.bias && k < p.Nout) ? p.bias[k] : 0.f;
+  if (EPI == EPI_RES_LN)
+    for (int k = threadIdx.x; k < 256; k += THREADS) {
+      sGamma[k] = p.gamma[k];
+      sBeta[k] = p.beta[k];
+    }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* dst = smem + stage * STAGE_BYTES;
+          if (kc < p.k1_chunks) tma_load_2d(dst, &mapA1, kc * BK, m0, &full[stage]);
+          else tma_load_2d(dst, &mapA2, (kc - p.k1_chunks) * BK, m0, &full[stage]);
+          tma_load_2d(dst + A_BYTES, &mapB, kc * BK, n0, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_tf32(BM, BN);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks)       // one tf32 MMA covers K = 8 (32 bytes)
+            umma_tf32(tmem_base + acc * BN, desc_kmajor(a_base + ks * 32), desc_kmajor(b_base + ks * 32), IDESC,
+                      (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane = row, registers = columns
+    const int q = warp & 3, hh = warp >> 2;            // TMEM lane quarter, 128-column half of the tile
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const bool valid = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hh * 128);
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (EPI == EPI_RES_LN) {
+        // pass 1: row sums of r = acc + b4 + h over this warp's 128 columns; the two column halves meet in shared memory
+        float s1 = 0.f, s2 = 0.f;
+        const float* hrow = p.res + (valid ? row : 0) * 256 + hh * 128;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          float hv[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 v = *reinterpret_cast<const float4*>(hrow + 32 * b + 4 * j4);
+            hv[4 * j4] = v.x; hv[4 * j4 + 1] = v.y; hv[4 * j4 + 2] = v.z; hv[4 * j4 + 3] = v.w;
+          }
+          tmem_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float r = __uint_as_float(raw[j]) + sBias[hh * 128 + 32 * b + j] + hv[j];
+            s1 += r;
+            s2 = fmaf(r, r, s2);
+          }
+        }
+        float* mine = sLn + (hh * BM + q * 32 + lane) * 2;
+        const float* other = sLn + ((hh ^ 1) * BM + q * 32 + lane) * 2;
+        mine[0] = s1; mine[1] = s2;
+        half_barrier(q);
+        const float t1 = hh == 0 ? s1 + other[0] : other[0] + s1;       // the same order in both halves
+        const float t2 = hh == 0 ? s2 + other[1] : other[1] + s2;
+        const float mu = t1 * (1.0f / 256.0f);
+        const float var = fmaxf(t2 * (1.0f / 256.0f) - mu * mu, 0.f);
+        const float rs = rsqrtf(var + p.eps);
+        half_barrier(q);                                               // both halves have read before the next tile writes
+        if (valid && hh == 0 && p.mean) { p.mean[row] = mu; p.rstd[row] = rs; }
+        // pass 2: normalise and write
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          float hv[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 v = *reinterpret_cast<const float4*>(hrow + 32 * b + 4 * j4);
+            hv[4 * j4] = v.x; hv[4 * j4 + 1] = v.y; hv[4 * j4 + 2] = v.z; hv[4 * j4 + 3] = v.w;
+          }
+          tmem_wait();
+          if (b == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (valid) {
+            const int c0 = hh * 128 + 32 * b;
+            float* yrow = p.out + row * 256 + c0;
+            float* rrow = p.out2 ? p.out2 + row * 256 + c0 : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float r4[4], y4[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = 4 * j4 + u;
+                r4[u] = __uint_as_float(raw[j]) + sBias[c0 + j] + hv[j];
+                y4[u] = (r4[u] - mu) * rs * sGamma[c0 + j] + sBeta[c0 + j];
+              }
+              *reinterpret_cast<float4*>(yrow + 4 * j4) = make_float4(y4[0], y4[1], y4[2], y4[3]);
+              if (rrow) *reinterpret_cast<float4*>(rrow + 4 * j4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          const int c0 = n0 + hh * 128 + 32 * b;                         // global output column
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          float aux[32];
+          if (EPI == EPI_DSILU || (EPI == EPI_PLAIN && p.res)) {
+            const float* arow = p.res + (valid ? row : 0) * p.Nout + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 v = *reinterpret_cast<const float4*>(arow + 4 * j4);
+              aux[4 * j4] = v.x; aux[4 * j4 + 1] = v.y; aux[4 * j4 + 2] = v.z; aux[4 * j4 + 3] = v.w;
+            }
+          }
+          tmem_wait();
+          if (b == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (!valid) continue;
+          float val[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[c0 + j];
+          if (EPI == EPI_ABH) {
+            __half* o = p.out16 + row * p.Nout + c0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint32_t h4[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const __half2 hp = __floats2half2_rn(p.scale * val[8 * j8 + 2 * u], p.scale * val[8 * j8 + 2 * u + 1]);
+                h4[u] = *reinterpret_cast<const uint32_t*>(&hp);
+              }
+              *reinterpret_cast<uint4*>(o + 8 * j8) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            }
+          } else {
+            float* o = p.out + row * p.Nout + c0;
+            float* o2 = (EPI == EPI_SILU && p.out2) ? p.out2 + row * p.Nout + c0 : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float w4[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = 4 * j4 + u;
+                const float v = val[j];
+                if (EPI == EPI_SILU) w4[u] = v / (1.0f + __expf(-v));
+                else if (EPI == EPI_DSILU) {
+                  const float pz = aux[j], sg = 1.0f / (1.0f + __expf(-pz));
+                  w4[u] = v * sg * (1.0f + pz * (1.0f - sg));
+                } else w4[u] = p.res ? v + aux[j] : v;
+              }
+              *reinterpret_cast<float4*>(o + 4 * j4) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+              if (o2) *reinterpret_cast<float4*>(o2 + 4 * j4) = make_float4(val[4 * j4], val[4 * j4 + 1], val[4 * j4 + 2], val[4 * j4 + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// fp32 [rows, cols] row-major (leading dimension ld floats), box [32 columns x box_rows], SWIZZLE_128B
+static int make_f32_map(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+      return set_error(2, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(2, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <int EPI>
+static int launch(const Params& p, const float* A1, int64_t K1, const float* A2, int64_t K2, const float* W, cudaStream_t st) {
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(node_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(2, "node_gemm_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  alignas(64) CUtensorMap mA1, mA2, mB;
+  if (int rc = make_f32_map(A1, p.M, K1, K1, BM, &mA1)) return rc;
+  if (A2) {
+    if (int rc = make_f32_map(A2, p.M, K2, K2, BM, &mA2)) return rc;
+  } else {
+    memcpy(&mA2, &mA1, sizeof(mA1));
+  }
+  if (int rc = make_f32_map(W, p.Nout, K1 + K2, K1 + K2, BN, &mB)) return rc;
+  const int total = (int)((p.M + BM - 1) / BM) * (p.Nout / BN);
+  const int grid = total < sm_count() ? total : sm_count();
+  node_gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(p, mA1, mA2, mB);
+  return after_launch("node_gemm_kernel");
+}
+
+}  // namespace ng
+}  // namespace pev
+
+using namespace pev;
+
+extern "C" int pev_node_gemm(int32_t epilogue, const float* A1, int32_t K1, const float* A2, int32_t K2, const float* W,
+                             const float* bias, int64_t M, int32_t Nout, float scale, const float* aux, const float* gamma,
+                             const float* beta, float eps, void* out, float* out2, float* mean, float* rstd, void* stream) {
+  PEV_REQUIRE(A1 && W && out && M >= 0, "null argument");
+  PEV_REQUIRE((Nout == 256 || Nout == 512) && K1 > 0 && K1 % 32 == 0 && K2 >= 0 && K2 % 32 == 0 && (K2 == 0) == (A2 == nullptr),
+              "shape: Nout in {256, 512}, K1 / K2 multiples of 32");
+  if (M == 0) return 0;
+  ng::Params p = {};
+  p.M = M; p.Nout = Nout; p.k1_chunks = K1 / 32; p.k2_chunks = K2 / 32; p.bias = bias; p.scale = scale;
+  p.res = aux; p.gamma = gamma; p.beta = beta; p.eps = eps; p.out2 = out2; p.mean = mean; p.rstd = rstd;
+  cudaStream_t st = as_stream(stream);
+  switch (epilogue) {
+    case ng::EPI_ABH:
+      p.out16 = reinterpret_cast<__half*>(out);
+      return ng::launch<ng::EPI_ABH>(p, A1, K1, A2, K2, W, st);
+    case ng::EPI_SILU:
+      p.out = reinterpret_cast<float*>(out);
+      return ng::launch<ng::EPI_SILU>(p, A1, K1, A2, K2, W, st);
+    case ng::EPI_RES_LN:
+      PEV_REQUIRE(Nout == 256 && aux && gamma && beta && (mean == nullptr) == (rstd == nullptr), "RES_LN: Nout = 256, h / gamma / beta");
+      p.out = reinterpret_cast<float*>(out);
+      return ng::launch<ng::EPI_RES_LN>(p, A1, K1, A2, K2, W, st);
+    case ng::EPI_PLAIN:
+      p.out = reinterpret_cast<float*>(out);
+      return ng::launch<ng::EPI_PLAIN>(p, A1, K1, A2, K2, W, st);
+    case ng::EPI_DSILU:
+      PEV_REQUIRE(aux, "DSILU needs p");
+      p.out = reinterpret_cast<float*>(out);
+      return ng::launch<ng::EPI_DSILU>(p, A1, K1, A2, K2, W, st);
+    default:
+      return set_error(1, "pev_node_gemm: unknown epilogue %d", epilogue);
+  }
+}

@@ -27,7 +27,9 @@ NODE_TF32_FORWARD = os.environ.get("PEV_NODE_TF32", "1") != "0"
 
 def supports(layer) -> bool:
     return (layer.node_dim == H and layer.hidden_dim == H
-            and all(isinstance(layer.phi_e[i], nn.SiLU) for i in (1, 3)) and isinstance(layer.phi_x[1], nn.SiLU))
+            and all(isinstance(layer.phi_e[i], nn.SiLU) for i in (1, 3)) and isinstance(layer.phi_x[1], nn.SiLU)
+            and isinstance(layer.phi_h[1], nn.SiLU) and layer.norm_h.elementwise_affine
+            and layer.norm_h.bias is not None)
 
 
 class _tf32_matmul:
@@ -158,6 +160,83 @@ class NodeLinear2(torch.autograd.Function):
             gW = torch.cat([g.t() @ x1, g.t() @ x2], 1) if ctx.needs_input_grad[2] else None
         gb = column_sum(g) if ctx.needs_input_grad[3] else None
         return g1, g2, gW, gb
+
+
+EPI_ABH, EPI_SILU, EPI_RES_LN, EPI_PLAIN, EPI_DSILU = range(5)
+
+
+def node_gemm(epi, A1, W, bias=None, A2=None, scale=1.0, aux=None, gamma=None, beta=None, eps=1e-5, out2=False,
+              stats=False):
+    """``pev_node_gemm``: ``epilogue([A1 | A2] W^T)`` on the tensor cores (TF32 operands, fp32 accumulation), see
+    ``include/pev_b200.h``.  Returns ``(out, out2, mean, rstd)`` (unused ones ``None``)."""
+    M, K1 = A1.shape
+    K2 = 0 if A2 is None else A2.shape[1]
+    Nout = W.shape[0]
+    dev = A1.device
+    with torch.cuda.device_of(A1):
+        out = torch.empty(M, Nout, dtype=torch.float16 if epi == EPI_ABH else torch.float32, device=dev)
+        o2 = torch.empty(M, Nout, dtype=torch.float32, device=dev) if out2 else None
+        mean = torch.empty(M, dtype=torch.float32, device=dev) if stats else None
+        rstd = torch.empty(M, dtype=torch.float32, device=dev) if stats else None
+        _lib.lib().call("pev_node_gemm", epi, ptr(A1), K1, ptr(A2), K2, ptr(W), ptr(bias), M, Nout, float(scale), ptr(aux),
+                        ptr(gamma), ptr(beta), float(eps), ptr(out), ptr(o2), ptr(mean), ptr(rstd), stream(A1))
+    return out, o2, mean, rstd
+
+
+def node_abh(h, W1, b1):
+    """fp16 half-domain node projection ``0.5 [h Wa^T + b1 | h Wb^T]`` ([N,512]) of ``phi_e[0]``'s factored form
+    (``models/en_gnn_decoder.py:65-66``): one GEMM, scaling / bias / fp16 staging in its epilogue.  Not an autograd
+    function: :class:`egnn_tc2.FusedEdgeV2` calls it and owns the backward (:func:`node_abh_backward`)."""
+    Wcat = torch.cat([W1[:, :H], W1[:, H:2 * H]], 0).contiguous()               # [512, 256]
+    bias = torch.cat([b1, torch.zeros_like(b1)]).contiguous()
+    return node_gemm(EPI_ABH, f32c(h), Wcat, bias, scale=0.5)[0]
+
+
+def node_abh_backward(gAB, h, W1, need_h=True):
+    """``(gh, gWa|gWb as [256,512], gb1)`` from ``gAB = dL/dABh`` (fp32 [N,512])."""
+    Wcat_t = (0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)).t().contiguous()   # [256, 512]: gh = gAB (0.5 Wcat)
+    gh = node_gemm(EPI_PLAIN, gAB, Wcat_t)[0] if need_h else None
+    with _tf32_matmul():
+        gWab = 0.5 * (gAB.t() @ h)                                               # [512, 256] = [gWa ; gWb]
+    gb1 = 0.5 * column_sum(gAB)[:H]
+    return gh, gWab, gb1
+
+
+class NodePhiH(torch.autograd.Function):
+    """``LayerNorm(h + phi_h([h, agg]))`` (``models/en_gnn_decoder.py:70-73``) as two tensor-core GEMMs whose epilogues
+    hold the SiLU and the residual + LayerNorm; backward: LayerNorm backward (one pass), two data-gradient GEMMs with
+    the SiLU derivative in the first one's epilogue, weight gradients as library TF32 GEMMs."""
+
+    @staticmethod
+    def forward(ctx, h, agg, W3, b3, W4, b4, gamma, beta, eps):
+        h, agg = f32c(h), f32c(agg)
+        train = any(ctx.needs_input_grad)          # (grad mode is off inside forward: ask the context)
+        W3c, W4c = f32c(W3.detach()), f32c(W4.detach())
+        q, p, _, _ = node_gemm(EPI_SILU, h, W3c, f32c(b3.detach()), A2=agg, out2=train)
+        y, r, mean, rstd = node_gemm(EPI_RES_LN, q, W4c, f32c(b4.detach()), aux=h, gamma=f32c(gamma.detach()),
+                                     beta=f32c(beta.detach()), eps=eps, out2=train, stats=train)
+        if train:
+            ctx.save_for_backward(h, agg, W3c, W4c, f32c(gamma.detach()), p, q, r, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        h, agg, W3, W4, gamma, p, q, r, mean, rstd = ctx.saved_tensors
+        gy = f32c(gy)
+        N, D = r.shape
+        with torch.cuda.device_of(r):
+            gr = torch.empty_like(r)
+            dgb = torch.empty(2 * D, dtype=torch.float32, device=r.device)
+            _lib.lib().call("pev_layernorm_bwd", ptr(gy), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), N, D,
+                            ptr(node_workspace(r.device)), ptr(gr), ptr(dgb), ptr(dgb[D:]), stream(r))
+        gp = node_gemm(EPI_DSILU, gr, W4.t().contiguous(), aux=p)[0]              # (gr W4) * silu'(p)
+        gha = node_gemm(EPI_PLAIN, gp, W3.t().contiguous())[0]                    # [N,512] = [dL/dh (phi_h part) | dL/dagg]
+        gh = gr + gha[:, :D]
+        gagg = gha[:, D:]
+        with _tf32_matmul():
+            gW4 = gr.t() @ q
+            gW3 = torch.cat([gp.t() @ h, gp.t() @ agg], 1)
+        return gh, gagg, gW3, column_sum(gp), gW4, column_sum(gr), dgb[:D], dgb[D:], None
 
 
 def apply_tf32(module, x, fp32_forward=False):

@@ -110,9 +110,10 @@ def _scratch(device, E: int, N: int = 0):
 
 
 class FusedEdgeV2(torch.autograd.Function):
-    """(ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3]) on the v2 kernels.
+    """(h, W1, b1, x, W2, b2, W5, b5, w6, b6, dinv, graph) -> (agg[N,256], x'[N,3]) on the v2 kernels.
 
-    ``ABh`` is the fp32 half-domain node projection ``0.5 [h Wa^T + b1 | h Wb^T]`` (rounded to fp16 here, once).
+    The fp16 half-domain node projection ``ABh = 0.5 [h Wa^T + b1 | h Wb^T]`` comes from one tensor-core GEMM with the
+    scaling / bias / fp16 staging in its epilogue (``egnn_tc.node_abh``); its backward is part of this function.
     Forward: ``pev_edge_d2`` -> ``pev_edge2_fwd1`` -> ``pev_edge2_fwd2`` -> exact-order coordinate update (K2).
     Kept for the backward pass: the ``hv`` and ``m`` tile images and ``hs`` rows (bf16, 3 x 2.47 GB per layer at
     config 2), ``w``, ``d2`` and the fp16 ``ABh``.  With ``recompute`` the three per-edge streams are NOT kept: the
@@ -123,17 +124,20 @@ class FusedEdgeV2(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, ABh, x, wd, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches, recompute: bool = False):
+    def forward(ctx, h, W1, b1, x, W2, b2, W5, b5, w6, b6, dinv, g, keep: bool, caches, recompute: bool = False):
+        from .egnn_tc import node_abh
         L = _lib.lib()
         N, E = g.num_nodes, g.num_edges
         dev = x.device
-        x = f32c(x)
-        wd, b2, b5 = f32c(wd), f32c(b2), f32c(b5)
+        x, h = f32c(x), f32c(h)
+        W1d, b1d = W1.detach(), b1.detach()
+        wd = f32c(W1d[:, 2 * H])
+        b2, b5 = f32c(b2), f32c(b5)
         w6v, b6v = f32c(w6).reshape(-1), f32c(b6).reshape(-1)
         dinv = f32c(dinv)
         with torch.cuda.device_of(x):
             st = stream(x)
-            ABb = ABh.detach().to(torch.float16).contiguous()   # fp16 staging (see edge_tc2_kernels.cu)
+            ABb = node_abh(h.detach(), W1d, b1d)                 # fp16 [N,512] (see edge_tc2_kernels.cu)
             W2hp = packed_weight_scaled(W2, 0.5, cache=caches[0])
             W5hp = packed_weight_scaled(W5, 0.5, cache=caches[1])
             d2 = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
@@ -155,16 +159,17 @@ class FusedEdgeV2(torch.autograd.Function):
         ctx.g, ctx.caches = g, caches
         ctx.recompute = bool(keep and recompute)
         if ctx.recompute:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, None, None, None, w, d2, b2, b5, b6v)
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, None, None, None, w, d2, b2, b5, b6v, h, W1d)
         elif keep:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2, None, None, None)
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2, None, None, None, h, W1d)
         else:
-            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None, None, None, None, None)
+            ctx.save_for_backward(x, wd, W2, W5, w6v, dinv, None, None, None, None, None, None, None, None, None, None,
+                                  None)
         return agg, x_out
 
     @staticmethod
     def backward(ctx, gagg, gxo):
-        x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2, b2, b5, b6v = ctx.saved_tensors
+        x, wd, W2, W5, w6v, dinv, ABb, hvT, mT, hs, w, d2, b2, b5, b6v, h, W1d = ctx.saved_tensors
         if hs is None and not ctx.recompute:
             raise RuntimeError("FusedEdgeV2 ran with keep=False (no_grad); backward is unavailable")
         g = ctx.g
@@ -224,23 +229,24 @@ class FusedEdgeV2(torch.autograd.Function):
                    ptr(g.csc_perm), N, E, ptr(gx), st)
             gwd = 0.5 * gwdh                            # hu = ... + (wd/2) d2
             gb6 = gw[:E].sum().reshape(1)
-        return (gAB, gx, gwd, gW2, 0.5 * db2h, gW5, 0.5 * db5h, gw6.reshape(1, H), gb6, None, None, None, None, None)
+            from .egnn_tc import node_abh_backward
+            gh, gWab, gb1 = node_abh_backward(gAB, h, W1d, ctx.needs_input_grad[0])
+            gW1 = torch.cat([gWab[:H], gWab[H:], gwd.unsqueeze(1)], 1)            # [256, 513] = [gWa | gWb | gwd]
+        return (gh, gW1, gb1, gx, gW2, 0.5 * db2h, gW5, 0.5 * db5h, gw6.reshape(1, H), gb6, None, None, None, None, None)
 
 
 def egn_layer_v2(layer, h, x, g, dinv):
     """One EGNN layer with the edge MLP on the v2 kernels; ``layer`` is an ``EGNLayer`` (parameter holder)."""
-    from .egnn_tc import NodeLinear, NodeLinear2, layer_norm
+    from .egnn_tc import NodePhiH
     W1 = layer.phi_e[0].weight                                            # [256, 513] = [Wa | Wb | wd]
     keep = torch.is_grad_enabled() and any(
         t.requires_grad for t in (h, x, W1, layer.phi_e[2].weight, layer.phi_x[0].weight))
-    Wcat = 0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)                # half domain
-    bias = 0.5 * torch.cat([layer.phi_e[0].bias, torch.zeros_like(layer.phi_e[0].bias)])
-    ABh = NodeLinear.apply(h, Wcat, bias)                                 # fp32 [N,512]
     caches = layer.__dict__.setdefault("_pev_packed2", ({}, {}))
-    agg, x_new = FusedEdgeV2.apply(ABh, x, W1[:, 2 * H], layer.phi_e[2].weight, layer.phi_e[2].bias,
+    agg, x_new = FusedEdgeV2.apply(h, W1, layer.phi_e[0].bias, x, layer.phi_e[2].weight, layer.phi_e[2].bias,
                                    layer.phi_x[0].weight, layer.phi_x[0].bias, layer.phi_x[2].weight,
                                    layer.phi_x[2].bias, dinv, g, keep, caches,
                                    bool(getattr(layer, "recompute_edges", False)))
-    q = layer.phi_h[1](NodeLinear2.apply(h, agg, layer.phi_h[0].weight, layer.phi_h[0].bias))
-    h_new = layer_norm(layer.norm_h, NodeLinear.apply(q, layer.phi_h[2].weight, layer.phi_h[2].bias), h)
+    ln = layer.norm_h
+    h_new = NodePhiH.apply(h, agg, layer.phi_h[0].weight, layer.phi_h[0].bias, layer.phi_h[2].weight,
+                           layer.phi_h[2].bias, ln.weight, ln.bias, ln.eps)
     return h_new, x_new

@@ -1,0 +1,70 @@
+"""Node-level tcgen05 TF32 GEMMs with fused epilogues (csrc/node_gemm_kernels.cu, ``pev_node_gemm``) against torch float64
+on the same operands; tolerance 2e-3 of max|ref| = TF32's 10-bit mantissa over K = 256 / 512 (the same arithmetic the
+cuBLAS allow_tf32 path had), through the C ABI."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+ABH, SILU, RES_LN, PLAIN, DSILU = range(5)
+
+
+def gemm(epi, A1, W, bias=None, A2=None, Nout=None, scale=1.0, aux=None, gamma=None, beta=None, eps=1e-5, train=True):
+    from protein_ensemble_vae_b200 import _lib
+    from protein_ensemble_vae_b200._lib import ptr, stream
+    M, K1 = A1.shape
+    K2 = 0 if A2 is None else A2.shape[1]
+    Nout = Nout or W.shape[0]
+    dev = A1.device
+    out = torch.full((M, Nout), 7.0, dtype=torch.float16 if epi == ABH else torch.float32, device=dev)
+    out2 = torch.full((M, Nout), 7.0, device=dev) if (train and epi in (SILU, RES_LN)) else None
+    mean = torch.empty(M, device=dev) if (train and epi == RES_LN) else None
+    rstd = torch.empty(M, device=dev) if (train and epi == RES_LN) else None
+    _lib.lib().call("pev_node_gemm", epi, ptr(A1), K1, ptr(A2), K2, ptr(W), ptr(bias), M, Nout, float(scale), ptr(aux),
+                    ptr(gamma), ptr(beta), float(eps), ptr(out), ptr(out2), ptr(mean), ptr(rstd), stream(A1))
+    return out, out2, mean, rstd
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 1000, 20000])
+def test_node_gemm_epilogues(M):
+    torch.manual_seed(M)
+    r = lambda *s: torch.randn(*s, device="cuda")  # noqa: E731
+    h, agg = r(M, 256), r(M, 256) * 3
+    Wcat, b1 = r(512, 256) / 16, r(512) * 0.1
+    W3, b3 = r(256, 512) / 22, r(256) * 0.1
+    W4, b4 = r(256, 256) / 16, r(256) * 0.1
+    gamma, beta = 1 + 0.1 * r(256), 0.1 * r(256)
+    d = lambda t: t.double()  # noqa: E731
+    # ABH: fp16(0.5 (h Wcat^T + b1))
+    out, *_ = gemm(ABH, h, Wcat, b1, scale=0.5)
+    ref = 0.5 * (d(h) @ d(Wcat).t() + d(b1))
+    assert out.dtype == torch.float16 and rel_err(out.float(), ref) < 2e-3
+    # SILU on two operands
+    q, p, *_ = gemm(SILU, h, W3, b3, A2=agg)
+    pref = torch.cat([d(h), d(agg)], 1) @ d(W3).t() + d(b3)
+    assert rel_err(p, pref) < 2e-3 and rel_err(q, F.silu(pref)) < 2e-3
+    q_inf, p_inf, *_ = gemm(SILU, h, W3, b3, A2=agg, train=False)
+    assert p_inf is None and torch.equal(q_inf, q)
+    # RES_LN
+    y, rr, mean, rstd = gemm(RES_LN, q, W4, b4, aux=h, gamma=gamma, beta=beta)
+    rref = d(h) + d(q) @ d(W4).t() + d(b4)
+    assert rel_err(rr, rref) < 2e-3
+    assert rel_err(y, F.layer_norm(rref, (256,), d(gamma), d(beta), 1e-5)) < 3e-3
+    assert rel_err(mean, rref.mean(1)) < 2e-3 and rel_err(rstd, 1 / torch.sqrt(rref.var(1, unbiased=False) + 1e-5)) < 3e-3
+    y_inf, r_inf, m_inf, _ = gemm(RES_LN, q, W4, b4, aux=h, gamma=gamma, beta=beta, train=False)
+    assert r_inf is None and m_inf is None and torch.equal(y_inf, y)
+    # PLAIN (Nout = 512, no bias), PLAIN + residual, DSILU
+    gp = r(M, 256)
+    W3t = W3.t().contiguous()                       # [512, 256]
+    c, *_ = gemm(PLAIN, gp, W3t)
+    assert rel_err(c, d(gp) @ d(W3)) < 2e-3
+    c2, *_ = gemm(PLAIN, gp, W4.t().contiguous(), aux=h)
+    assert rel_err(c2, d(gp) @ d(W4) + d(h)) < 2e-3
+    gAB = r(M, 512)
+    c3, *_ = gemm(PLAIN, gAB, Wcat.t().contiguous())                 # K = 512 from one operand
+    assert rel_err(c3, d(gAB) @ d(Wcat)) < 2e-3
+    g, *_ = gemm(DSILU, gp, W4.t().contiguous(), aux=p)
+    sg = torch.sigmoid(pref)
+    assert rel_err(g, (d(gp) @ d(W4)) * sg * (1 + pref * (1 - sg))) < 3e-3
