@@ -594,6 +594,12 @@ def run_train(ctx, args):
     sampler.mark_stop()
     value = B * world * args.steps / (ms / 1e3)
 
+    if args.train_only:
+        if rank == 0:
+            print(json.dumps({"metric": "train_conformers_per_s", "value": value, "ms_per_step": ms / args.steps,
+                              "gpu_launches": int(launches), "note": "--train-only profiling run"}), flush=True)
+        return
+
     # end to end: pinned host buffers -> device every step (DevicePrefetcher: the copy of step i+1 runs on a side
     # stream under step i's kernels), loss read back to the host every step; K copies and K read-backs per K steps
     def e2e_steps(k):
@@ -830,6 +836,8 @@ def main():
     ap.add_argument("--config", default="train", choices=["train", "decode", "mixed", "stress"],
                     help="train = BASELINE configs[1] (the headline); decode / mixed / stress = configs[3] / [2] / [4]")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--train-only", action="store_true",
+                    help="profiling runs: only the timed training steps (no e2e / decode / per-kernel side measurements)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -252,6 +252,15 @@ int pev_kabsch_rmsd(const float* a, const float* b, const float* mask, int32_t S
 int pev_kabsch_rmsd_pairs(const float* a, const float* mask, int32_t S, int32_t L, int32_t mode,
                           float* out /*[S,S]*/, void* stream);
 
+/* ---------------------------------------------------------------- generation driver: geometry validity filter
+ * Replaces validate_protein_geometry, generate_ensemble_pdbs.py:290-340 (a Python loop over residues with one
+ * device->host .item() per distance / angle), for S conformers at once: CA-CA distances and CA-CA-CA angles over the
+ * compacted valid residues.  ca[S,L,3]; mask[S or 1,L] float or NULL.  status[S]: 0 valid, 1 no valid residues,
+ * 2 extreme CA-CA distance (> 6.0), 3 abnormal average CA-CA distance (< 2.5 or > 5.0), 4 abnormal average CA-CA-CA
+ * angle (< 60 or > 180 degrees); stats[S,3] = {max distance, mean distance, mean angle} (may be NULL). */
+int pev_validate_geometry(const float* ca, const float* mask, int32_t S, int32_t L, int32_t mask_batch,
+                          int32_t* status, float* stats, void* stream);
+
 /* ---------------------------------------------------------------- K1, fused CTA-pair form (csrc/edge_tc3_kernels.cu)
  * One kernel for the whole forward edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79): phi_e[1..3] ->
  * agg = index_add_(m) (:68-69) and phi_x (:76), with m kept on chip between the two 256 x 256 GEMMs.  Run by CTA
@@ -275,6 +284,12 @@ int pev_edge3_fwd(const void* ABh /*fp16 [N,512]*/, const float* d2 /*[E]*/, con
  *            3 PLAIN   out = C + bias (+ aux)                          data gradients
  *            4 DSILU   out = (C + bias) * silu'(aux)                   backward through phi_h[1]
  * Nout in {256, 512}; K1, K2 multiples of 32; aux / out / out2 row-major with leading dimension Nout (RES_LN: 256). */
+/* Weight gradients of the node-level linears: out[Mo, 256] (leading dimension ldc >= 256) = scale * G^T X with G fp32
+ * [N, Mo] (Mo = 256 or 512), X fp32 [N, 256]: split-K over row slices on tcgen05 (TF32, MN-major operands), per-CTA
+ * partials in `workspace` (pev_node_wgrad_workspace_bytes()) summed in a fixed order. */
+int64_t pev_node_wgrad_workspace_bytes(void);
+int pev_node_wgrad(const float* G, int32_t Mo, const float* X, int64_t N, float scale, float* workspace, float* out,
+                   int32_t ldc, void* stream);
 int pev_node_gemm(int32_t epilogue, const float* A1, int32_t K1, const float* A2, int32_t K2, const float* W,
                   const float* bias, int64_t M, int32_t Nout, float scale, const float* aux, const float* gamma,
                   const float* beta, float eps, void* out, float* out2, float* mean, float* rstd, void* stream);

@@ -50,6 +50,7 @@ _PROTOS = {
     "pev_dihedral_terms_fwd": (c_int32, [_P, _P, _P, _I, _I, _P, _P]),
     "pev_dihedral_terms_bwd": (c_int32, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "pev_kabsch_rmsd": (c_int32, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "pev_validate_geometry": (c_int32, [_P, _P, _I, _I, _I, _P, _P, _P]),
 }
 # tensor-core entry points: present in libpev_b200.so only (no host restatement)
 _PROTOS_TC = {
@@ -73,6 +74,8 @@ _PROTOS_TC = {
     "pev_edge2_wgrad5": (c_int32, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
     "pev_edge2_wgrad2": (c_int32, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     # node-level tcgen05 TF32 GEMMs with fused epilogues (csrc/node_gemm_kernels.cu)
+    "pev_node_wgrad_workspace_bytes": (c_int64, []),
+    "pev_node_wgrad": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
     "pev_node_gemm": (c_int32, [_I, _P, _I, _P, _I, _P, _P, _L, _I, c_float, _P, _P, _P, c_float, _P, _P, _P, _P, _P]),
     # fused CTA-pair edge kernels (csrc/edge_tc3_kernels.cu)
     "pev_edge3_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),

@@ -70,6 +70,40 @@ partial_reduce2_kernel(const float* __restrict__ partial, int G, int64_t stride,
   if (r == 0 && i < n) out[i] = scale * sm[0][c];
 }
 
+// the same reduction for a [rows, cols] block written with leading dimension ldc (a column block of a wider matrix)
+__global__ void __launch_bounds__(1024)
+partial_reduce2d_kernel(const float* __restrict__ partial, int G, int64_t stride, int rows, int cols, float scale,
+                        float* __restrict__ out, int ldc) {
+  __shared__ float sm[32][33];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + c;                 // flat index into the [rows, cols] block
+  const int n = rows * cols;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n) {
+    int g = r;
+    for (; g + 96 < G; g += 128) {
+      s0 += partial[(int64_t)g * stride + i];
+      s1 += partial[(int64_t)(g + 32) * stride + i];
+      s2 += partial[(int64_t)(g + 64) * stride + i];
+      s3 += partial[(int64_t)(g + 96) * stride + i];
+    }
+    for (; g < G; g += 32) s0 += partial[(int64_t)g * stride + i];
+  }
+  sm[r][c] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  for (int half = 16; half >= 1; half >>= 1) {
+    if (r < half) sm[r][c] += sm[r + half][c];
+    __syncthreads();
+  }
+  if (r == 0 && i < n) out[(int64_t)(i / cols) * ldc + (i % cols)] = scale * sm[0][c];
+}
+
+int launch_partial_reduce_2d(const float* partial, int G, int64_t stride, int rows, int cols, float scale, float* out,
+                             int ldc, cudaStream_t st) {
+  partial_reduce2d_kernel<<<(rows * cols + 31) / 32, 1024, 0, st>>>(partial, G, stride, rows, cols, scale, out, ldc);
+  return after_launch("partial_reduce_kernel");
+}
+
 int launch_partial_reduce(const float* partial, int G, int64_t stride, int n, float scale, float* out, cudaStream_t st) {
   partial_reduce2_kernel<<<(n + 31) / 32, 1024, 0, st>>>(partial, G, stride, n, scale, out);
   return after_launch("partial_reduce_kernel");

@@ -103,7 +103,28 @@ kabsch_pairs_kernel(const float* __restrict__ a, const float* __restrict__ mask,
   }
 }
 
+// geometry validity filter: one thread per conformer (12 L bytes each; 100 000 x L=100 = 120 MB, latency-trivial)
+__global__ void __launch_bounds__(128)
+validate_geometry_kernel(const float* __restrict__ ca, const float* __restrict__ mask, int S, int L, int mask_batch,
+                         int32_t* __restrict__ status, float* __restrict__ stats) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float st[3];
+  status[s] = validate_geometry_serial(ca + (int64_t)s * L * 3, mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr,
+                                       L, st);
+  if (stats) { stats[3 * s] = st[0]; stats[3 * s + 1] = st[1]; stats[3 * s + 2] = st[2]; }
+}
+
 }  // namespace pev
+
+extern "C" int pev_validate_geometry(const float* ca, const float* mask, int32_t S, int32_t L, int32_t mask_batch,
+                                     int32_t* status, float* stats, void* stream) {
+  using namespace pev;
+  PEV_REQUIRE(ca && status && S >= 0 && L > 0, "bad argument");
+  if (S == 0) return 0;
+  validate_geometry_kernel<<<(S + 127) / 128, 128, 0, as_stream(stream)>>>(ca, mask, S, L, mask_batch, status, stats);
+  return after_launch("validate_geometry_kernel");
+}
 
 extern "C" int pev_kabsch_rmsd(const float* a, const float* b, const float* mask, int32_t S, int32_t L,
                                int32_t b_batch, int32_t mask_batch, int32_t mode, float* out, void* stream) {

@@ -27,13 +27,14 @@ namespace ng {
 using namespace tcx;
 
 constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 4;     // 16 KB
 constexpr int B_BYTES = BN * BK * 4;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int VEC_OFF = STAGES * STAGE_BYTES;          // bias[512] | gamma[256] | beta[256]
 constexpr int LN_OFF = VEC_OFF + 1024 * 4;             // [2 column halves][128 rows][2] row statistics
-constexpr int BAR_OFF = LN_OFF + 2 * BM * 2 * 4;
+constexpr int STG_OFF = LN_OFF + 2 * BM * 2 * 4;        // 8 warps x 4 KB: [32 rows][32 floats] transposition buffers
+constexpr int BAR_OFF = STG_OFF + 8 * 4096;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
 constexpr int THREADS = 32 * 10;
@@ -71,6 +72,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       : "memory");
 }
 __device__ __forceinline__ void half_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+// Coalesced store of a warp's [32 rows x 32 floats] register block (lane = row, as tcgen05.ld delivers it): through a 4 KB
+// staging buffer (16-byte chunks XOR-swizzled by row: conflict-free both ways) so that one store instruction writes four
+// complete 128-byte row segments instead of 32 scattered 16-byte pieces (the per-lane-row form ran at 2 TB/s).
+__device__ __forceinline__ void store_block32(float* stg, const float (&v)[32], float* gbase, int64_t ld, int rows_valid,
+                                              int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + rr;
+    const float4 x = *reinterpret_cast<const float4*>(stg + row * 32 + ((ch ^ (row & 7)) << 2));
+    if (row < rows_valid) *reinterpret_cast<float4*>(gbase + row * ld + 4 * ch) = x;
+  }
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -163,12 +183,15 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
   } else {
     // ------------------------------------------------------------------ epilogue: lane = row, registers = columns
     const int q = warp & 3, hh = warp >> 2;            // TMEM lane quarter, 128-column half of the tile
+    float* stg = reinterpret_cast<float*>(smem + STG_OFF) + warp * 1024;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
       const int64_t row = (int64_t)m0 + q * 32 + lane;
       const bool valid = row < p.M;
+      const int64_t wrow0 = (int64_t)m0 + q * 32;                                  // first row of this warp's block
+      const int rows_valid = (int)((p.M - wrow0) < 0 ? 0 : ((p.M - wrow0) > 32 ? 32 : (p.M - wrow0)));
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hh * 128);
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -222,22 +245,16 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          if (valid) {
+          {
             const int c0 = hh * 128 + 32 * b;
-            float* yrow = p.out + row * 256 + c0;
-            float* rrow = p.out2 ? p.out2 + row * 256 + c0 : nullptr;
+            float yv[32];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float r4[4], y4[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = 4 * j4 + u;
-                r4[u] = __uint_as_float(raw[j]) + sBias[c0 + j] + hv[j];
-                y4[u] = (r4[u] - mu) * rs * sGamma[c0 + j] + sBeta[c0 + j];
-              }
-              *reinterpret_cast<float4*>(yrow + 4 * j4) = make_float4(y4[0], y4[1], y4[2], y4[3]);
-              if (rrow) *reinterpret_cast<float4*>(rrow + 4 * j4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+            for (int j = 0; j < 32; ++j) {
+              hv[j] = __uint_as_float(raw[j]) + sBias[c0 + j] + hv[j];                   // r
+              yv[j] = (hv[j] - mu) * rs * sGamma[c0 + j] + sBeta[c0 + j];
             }
+            store_block32(stg, yv, p.out + wrow0 * 256 + c0, 256, rows_valid, lane);
+            if (p.out2) store_block32(stg, hv, p.out2 + wrow0 * 256 + c0, 256, rows_valid, lane);
           }
         }
       } else {
@@ -261,41 +278,35 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          if (!valid) continue;
           float val[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[c0 + j];
           if (EPI == EPI_ABH) {
-            __half* o = p.out16 + row * p.Nout + c0;
+            if (valid) {
+              __half* o = p.out16 + row * p.Nout + c0;
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              uint32_t h4[4];
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t h4[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const __half2 hp = __floats2half2_rn(p.scale * val[8 * j8 + 2 * u], p.scale * val[8 * j8 + 2 * u + 1]);
-                h4[u] = *reinterpret_cast<const uint32_t*>(&hp);
+                for (int u = 0; u < 4; ++u) {
+                  const __half2 hp = __floats2half2_rn(p.scale * val[8 * j8 + 2 * u], p.scale * val[8 * j8 + 2 * u + 1]);
+                  h4[u] = *reinterpret_cast<const uint32_t*>(&hp);
+                }
+                *reinterpret_cast<uint4*>(o + 8 * j8) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
               }
-              *reinterpret_cast<uint4*>(o + 8 * j8) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
             }
           } else {
-            float* o = p.out + row * p.Nout + c0;
-            float* o2 = (EPI == EPI_SILU && p.out2) ? p.out2 + row * p.Nout + c0 : nullptr;
+            if (EPI == EPI_SILU && p.out2) store_block32(stg, val, p.out2 + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float w4[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = 4 * j4 + u;
-                const float v = val[j];
-                if (EPI == EPI_SILU) w4[u] = v / (1.0f + __expf(-v));
-                else if (EPI == EPI_DSILU) {
-                  const float pz = aux[j], sg = 1.0f / (1.0f + __expf(-pz));
-                  w4[u] = v * sg * (1.0f + pz * (1.0f - sg));
-                } else w4[u] = p.res ? v + aux[j] : v;
-              }
-              *reinterpret_cast<float4*>(o + 4 * j4) = make_float4(w4[0], w4[1], w4[2], w4[3]);
-              if (o2) *reinterpret_cast<float4*>(o2 + 4 * j4) = make_float4(val[4 * j4], val[4 * j4 + 1], val[4 * j4 + 2], val[4 * j4 + 3]);
+            for (int j = 0; j < 32; ++j) {
+              const float v = val[j];
+              if (EPI == EPI_SILU) val[j] = v / (1.0f + __expf(-v));
+              else if (EPI == EPI_DSILU) {
+                const float pz = aux[j], sg = 1.0f / (1.0f + __expf(-pz));
+                val[j] = v * sg * (1.0f + pz * (1.0f - sg));
+              } else if (p.res) val[j] = v + aux[j];
             }
+            store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
           }
         }
       }
@@ -314,7 +325,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // fp32 [rows, cols] row-major (leading dimension ld floats), box [32 columns x box_rows], SWIZZLE_128B
-static int make_f32_map(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+static int make_f32_map(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -328,7 +340,7 @@ static int make_f32_map(const void* base, int64_t rows, int64_t cols, int64_t ld
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(2, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
@@ -357,10 +369,185 @@ static int launch(const Params& p, const float* A1, int64_t K1, const float* A2,
   return after_launch("node_gemm_kernel");
 }
 
+// =================================================================================================== weight gradients
+// C[Mo, 256] = scale * G^T X, G fp32 [N, Mo] (Mo = 256 or 512), X fp32 [N, 256], contraction over the N node rows:
+// split-K over row slices (one per CTA and 256-row output block), both operands MN-major (the contraction index is the
+// slow one in memory), K-chunks of 32 rows loaded as [32 rows x 128 B] TMA boxes (eight per operand), the 256 x 256
+// fp32 block accumulated in TMEM over the CTA's whole slice (2 x 256 columns) and written once as a per-CTA partial;
+// launch_partial_reduce sums the partials in a fixed order.  Replaces the cuBLAS g^T x GEMMs of the node-level linears
+// (K = 65 536 with 256 x 256 outputs: sixteen CTAs' worth of output tiles for a library GEMM).
+// 32-bit MN-major operands need their own swizzle: 32-byte chunks XOR-ed with the row index inside atoms of FOUR
+// 128-byte rows (UMMA layout type SWIZZLE_128B_BASE32B = TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); plain SWIZZLE_128B
+// silently produces zeros for kind::tf32.
+__device__ __forceinline__ uint64_t desc_mn_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+constexpr int WK = 32;                                  // rows per K-chunk
+constexpr int W_BOX = WK * 128;                         // 4 KB: [32 rows][32 floats]
+constexpr int W_OP = 8 * W_BOX;                         // 32 KB: 256 columns of one operand
+constexpr int W_STAGE = 2 * W_OP;
+constexpr int W_STAGES = 3;
+constexpr int W_BAR_OFF = W_STAGES * W_STAGE;
+constexpr int W_SMEM = W_BAR_OFF + 128 + 1024;
+constexpr int W_THREADS = 32 * 6;                       // 0..3 flush, 4 TMA, 5 MMA
+
+struct WParams {
+  int64_t N;
+  int nblk;               // Mo / 256
+  int rows_per_slice;     // multiple of WK
+  float* partial;         // [slices][nblk][256*256]
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1)
+node_wgrad_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W_BAR_OFF);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + W_STAGES;
+  uint64_t* done = bars + 2 * W_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = blockIdx.x % p.nblk, slice = blockIdx.x / p.nblk;
+  const int64_t r0 = (int64_t)slice * p.rows_per_slice;
+  int64_t r1 = r0 + p.rows_per_slice;
+  if (r1 > p.N) r1 = p.N;
+  const int chunks = r1 > r0 ? (int)((r1 - r0 + WK - 1) / WK) : 0;     // rows past N are zero-filled by TMA
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < W_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], W_STAGE);
+        uint8_t* dst = smem + stage * W_STAGE;
+        const int row = (int)(r0 + (int64_t)c * WK);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          tma_load_2d(dst + b * W_BOX, &mapG, blk * 256 + 32 * b, row, &full[stage]);
+          tma_load_2d(dst + W_OP + b * W_BOX, &mapX, 32 * b, row, &full[stage]);
+        }
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // D[m, n] += sum_k G[k, m] X[k, n]: A = G (MN-major: 32 m per 128-byte row, 8 k rows per atom), B = X likewise
+      constexpr uint32_t IDESC = idesc_tf32(128, 256) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * W_STAGE);
+        const uint32_t b_base = a_base + W_OP;
+#pragma unroll
+        for (int ks = 0; ks < WK / 8; ++ks)
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh)
+            umma_tf32(tmem_base + mh * 256, desc_mn_32b(a_base + mh * 4 * W_BOX + ks * 1024, W_BOX, 512),
+                      desc_mn_32b(b_base + ks * 1024, W_BOX, 512), IDESC, (c | ks) != 0 ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    // flush: TMEM -> this CTA's partial block (lane = output row)
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* dst = p.partial + ((int64_t)slice * p.nblk + blk) * 65536;
+#pragma unroll 1
+    for (int mh = 0; mh < 2; ++mh) {
+      float* drow = dst + (int64_t)(mh * 128 + warp * 32 + lane) * 256;
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t raw[32];
+        if (chunks > 0) {
+          tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mh * 256 + cb * 32), raw);
+          tmem_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(drow + cb * 32 + 4 * k) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace ng
 }  // namespace pev
 
 using namespace pev;
+
+extern "C" int64_t pev_node_wgrad_workspace_bytes(void) { return (int64_t)sm_count() * 65536 * (int64_t)sizeof(float); }
+
+extern "C" int pev_node_wgrad(const float* G, int32_t Mo, const float* X, int64_t N, float scale, float* workspace,
+                              float* out, int32_t ldc, void* stream) {
+  PEV_REQUIRE(G && X && out && workspace && N >= 0 && (Mo == 256 || Mo == 512) && ldc >= 256, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int nblk = Mo / 256;
+  if (N == 0) {
+    for (int r = 0; r < Mo; ++r) cudaMemsetAsync(out + (int64_t)r * ldc, 0, sizeof(float) * 256, st);
+    return 0;
+  }
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ng::node_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::W_SMEM);
+    if (e != cudaSuccess) return set_error(2, "node_wgrad_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int slices = sm_count() / nblk;
+  const int64_t chunks = (N + ng::WK - 1) / ng::WK;
+  if (slices > chunks) slices = (int)chunks;
+  ng::WParams p = {};
+  p.N = N; p.nblk = nblk; p.partial = workspace;
+  p.rows_per_slice = (int)(((chunks + slices - 1) / slices) * ng::WK);
+  slices = (int)((N + p.rows_per_slice - 1) / p.rows_per_slice);
+  alignas(64) CUtensorMap mG, mX;
+  if (int rc = ng::make_f32_map(G, N, Mo, Mo, ng::WK, &mG, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = ng::make_f32_map(X, N, 256, 256, ng::WK, &mX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  ng::node_wgrad_kernel<<<slices * nblk, ng::W_THREADS, ng::W_SMEM, st>>>(p, mG, mX);
+  if (int rc = after_launch("node_wgrad_kernel")) return rc;
+  // partial layout [slice][blk][256*256]; output block blk = rows 256 blk .. of out (leading dimension ldc)
+  for (int b = 0; b < nblk; ++b) {
+    if (ldc == 256) {
+      if (int rc = launch_partial_reduce(workspace + (int64_t)b * 65536, slices, (int64_t)nblk * 65536, 65536, scale,
+                                         out + (int64_t)b * 65536, st)) return rc;
+    } else {
+      if (int rc = launch_partial_reduce_2d(workspace + (int64_t)b * 65536, slices, (int64_t)nblk * 65536, 256, 256, scale,
+                                            out + (int64_t)b * 256 * ldc, ldc, st)) return rc;
+    }
+  }
+  return 0;
+}
 
 extern "C" int pev_node_gemm(int32_t epilogue, const float* A1, int32_t K1, const float* A2, int32_t K2, const float* W,
                              const float* bias, int64_t M, int32_t Nout, float scale, const float* aux, const float* gamma,

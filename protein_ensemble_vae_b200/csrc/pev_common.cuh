@@ -16,6 +16,8 @@ int current_device();      // cudaGetDevice(), clamped to [0, kMaxDevices)
 // out[i] = scale * sum_g partial[g * stride + i], i < n, summed in a FIXED order (32 interleaved chains per column, then
 // a fixed tree): the second stage of every per-CTA-partial reduction (bit-reproducible, no atomics).  capi.cu
 int launch_partial_reduce(const float* partial, int G, int64_t stride, int n, float scale, float* out, cudaStream_t st);
+int launch_partial_reduce_2d(const float* partial, int G, int64_t stride, int rows, int cols, float scale, float* out,
+                             int ldc, cudaStream_t st);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

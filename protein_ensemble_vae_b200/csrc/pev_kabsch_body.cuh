@@ -137,4 +137,45 @@ PEV_HD float kabsch_rmsd_serial(const float* a, const float* b, const float* mas
   return (float)sqrt(e / n);
 }
 
+// ------------------------------------------------------------------------------------------
+// Geometry validity filter of the generation driver (generate_ensemble_pdbs.py:290-340), one conformer: CA-CA distances
+// and CA-CA-CA angles over the COMPACTED valid residues (mask gaps are bridged, as there).  Status: 0 valid, 1 no valid
+// residues, 2 extreme CA-CA distance (> 6.0), 3 abnormal average CA-CA distance (< 2.5 or > 5.0), 4 abnormal average
+// CA-CA-CA angle (< 60 or > 180 degrees).  stats = {max distance, mean distance, mean angle in degrees}.
+PEV_HD int validate_geometry_serial(const float* ca, const float* mask, int L, float* stats) {
+  int n = 0, nd = 0, na = 0;
+  float p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};          // previous and the one before it
+  float dmax = 0.f, dsum = 0.f, asum = 0.f;
+  for (int l = 0; l < L; ++l) {
+    if (mask && mask[l] == 0.f) continue;
+    const float p[3] = {ca[3 * l], ca[3 * l + 1], ca[3 * l + 2]};
+    if (n >= 1) {
+      const float v2[3] = {p[0] - p1[0], p[1] - p1[1], p[2] - p1[2]};
+      const float d = sqrtf(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);                    // :306-308
+      dmax = d > dmax ? d : dmax;
+      dsum += d;
+      ++nd;
+      if (n >= 2) {
+        const float v1[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+        const float n1 = sqrtf(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+        float c = (v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2]) / (n1 * d + 1e-8f);          // :328
+        c = c < -1.f ? -1.f : (c > 1.f ? 1.f : c);
+        asum += acosf(c) * 57.29577951308232f;                                                 // :330
+        ++na;
+      }
+    }
+    for (int k = 0; k < 3; ++k) { p2[k] = p1[k]; p1[k] = p[k]; }
+    ++n;
+  }
+  const float davg = nd ? dsum / nd : 0.f, aavg = na ? asum / na : 0.f;
+  if (stats) { stats[0] = dmax; stats[1] = davg; stats[2] = aavg; }
+  if (n == 0) return 1;                                                                        // :302-303
+  if (nd) {
+    if (dmax > 6.0f) return 2;                                                                 // :314-315
+    if (davg < 2.5f || davg > 5.0f) return 3;                                                  // :317-318
+    if (na && (aavg < 60.f || aavg > 180.f)) return 4;                                         // :334-336
+  }
+  return 0;
+}
+
 }  // namespace pev

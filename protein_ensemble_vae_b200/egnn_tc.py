@@ -18,6 +18,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ctypes import c_void_p
+
 from ._lib import f32c, ptr, stream
 from .graph import PackedGraph
 
@@ -183,6 +185,26 @@ def node_gemm(epi, A1, W, bias=None, A2=None, scale=1.0, aux=None, gamma=None, b
     return out, o2, mean, rstd
 
 
+_WGRAD_WS: dict = {}
+
+
+def node_wgrad(G, X, scale=1.0, out=None):
+    """``scale * G^T X`` (``G[N,Mo]``, ``Mo`` in {256, 512}; ``X[N,256]``) on ``pev_node_wgrad`` (tcgen05 TF32 split-K,
+    fixed-order reduction); ``out`` may be a ``[Mo,256]`` column block of a wider row-major matrix."""
+    N, Mo = G.shape
+    dev = G.device
+    ws = _WGRAD_WS.get(dev)
+    with torch.cuda.device_of(G):
+        if ws is None:
+            ws = _WGRAD_WS[dev] = torch.empty(_lib.lib().cdll.pev_node_wgrad_workspace_bytes() // 4, dtype=torch.float32,
+                                              device=dev)
+        if out is None:
+            out = torch.empty(Mo, X.shape[1], dtype=torch.float32, device=dev)
+        _lib.lib().call("pev_node_wgrad", ptr(G), Mo, ptr(X), N, float(scale), ptr(ws), c_void_p(out.data_ptr()),
+                        out.stride(0), stream(G))
+    return out
+
+
 def node_abh(h, W1, b1):
     """fp16 half-domain node projection ``0.5 [h Wa^T + b1 | h Wb^T]`` ([N,512]) of ``phi_e[0]``'s factored form
     (``models/en_gnn_decoder.py:65-66``): one GEMM, scaling / bias / fp16 staging in its epilogue.  Not an autograd
@@ -196,8 +218,7 @@ def node_abh_backward(gAB, h, W1, need_h=True):
     """``(gh, gWa|gWb as [256,512], gb1)`` from ``gAB = dL/dABh`` (fp32 [N,512])."""
     Wcat_t = (0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)).t().contiguous()   # [256, 512]: gh = gAB (0.5 Wcat)
     gh = node_gemm(EPI_PLAIN, gAB, Wcat_t)[0] if need_h else None
-    with _tf32_matmul():
-        gWab = 0.5 * (gAB.t() @ h)                                               # [512, 256] = [gWa ; gWb]
+    gWab = node_wgrad(gAB, h, 0.5)                                               # [512, 256] = [gWa ; gWb]
     gb1 = 0.5 * column_sum(gAB)[:H]
     return gh, gWab, gb1
 
@@ -233,9 +254,10 @@ class NodePhiH(torch.autograd.Function):
         gha = node_gemm(EPI_PLAIN, gp, W3.t().contiguous())[0]                    # [N,512] = [dL/dh (phi_h part) | dL/dagg]
         gh = gr + gha[:, :D]
         gagg = gha[:, D:]
-        with _tf32_matmul():
-            gW4 = gr.t() @ q
-            gW3 = torch.cat([gp.t() @ h, gp.t() @ agg], 1)
+        gW4 = node_wgrad(gr, q)
+        gW3 = torch.empty(D, 2 * D, dtype=torch.float32, device=r.device)
+        node_wgrad(gp, h, out=gW3[:, :D])
+        node_wgrad(gp, agg, out=gW3[:, D:])
         return gh, gagg, gW3, column_sum(gp), gW4, column_sum(gr), dgb[:D], dgb[D:], None
 
 

@@ -265,4 +265,12 @@ int pev_kabsch_rmsd(const float* a, const float* b, const float* mask, int32_t S
   return 0;
 }
 
+int pev_validate_geometry(const float* ca, const float* mask, int32_t S, int32_t L, int32_t mask_batch, int32_t* status,
+                          float* stats, void*) {
+  for (int s = 0; s < S; ++s)
+    status[s] = validate_geometry_serial(ca + (int64_t)s * L * 3, mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr,
+                                         L, stats ? stats + 3 * s : nullptr);
+  return 0;
+}
+
 }  // extern "C"

@@ -68,3 +68,22 @@ def test_node_gemm_epilogues(M):
     g, *_ = gemm(DSILU, gp, W4.t().contiguous(), aux=p)
     sg = torch.sigmoid(pref)
     assert rel_err(g, (d(gp) @ d(W4)) * sg * (1 + pref * (1 - sg))) < 3e-3
+
+
+@pytest.mark.parametrize("N", [1, 31, 32, 1000, 65536])
+def test_node_wgrad_matches_float64(N):
+    """out[Mo,256] = scale G^T X over N rows (split-K, MN-major TF32 operands); also into a column block of a wider matrix."""
+    from protein_ensemble_vae_b200.egnn_tc import node_wgrad
+    torch.manual_seed(N)
+    X = torch.randn(N, 256, device="cuda")
+    for Mo in (256, 512):
+        G = torch.randn(N, Mo, device="cuda")
+        ref = 0.5 * (G.double().t() @ X.double())
+        got = node_wgrad(G, X, 0.5)
+        assert got.shape == (Mo, 256) and rel_err(got, ref) < 2e-3
+    wide = torch.full((256, 512), 7.0, device="cuda")
+    G = torch.randn(N, 256, device="cuda")
+    node_wgrad(G, X, out=wide[:, 256:])
+    assert rel_err(wide[:, 256:], G.double().t() @ X.double()) < 2e-3 and float((wide[:, :256] - 7.0).abs().max()) == 0.0
+    a, b = node_wgrad(G, X), node_wgrad(G, X)
+    assert torch.equal(a, b)                                  # fixed-order reduction: bit-reproducible
