@@ -12,35 +12,41 @@ namespace pev {
 // RMSD of one pair of structures after Kabsch superposition, computed by one warp; returns the value in every lane
 __device__ __forceinline__ float kabsch_pair(const float* __restrict__ pa, const float* __restrict__ pb,
                                              const float* __restrict__ pm, int L, int mode, int lane) {
+  // The per-residue arithmetic runs in fp32 (B200 issues fp64 at 1/64 of the fp32 rate: the all-double form of round 1
+  // was fp64-bound at 3 % of the HBM roofline); every lane keeps at most ceil(L / 32) terms per partial sum, the warp
+  // reductions and the 3 x 3 eigen-solve stay in double.
   // pass 1: centroids
-  double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+  float sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f};
   int n = 0;
   for (int l = lane; l < L; l += 32) {
     if (pm && pm[l] == 0.f) continue;
     ++n;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ca[k] += pa[3 * l + k]; cb[k] += pb[3 * l + k]; }
+    for (int k = 0; k < 3; ++k) { sa[k] += pa[3 * l + k]; sb[k] += pb[3 * l + k]; }
   }
   n = warp_sum(n);
   if (n == 0) return 0.f;
+  double ca[3], cb[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { ca[k] = warp_sum(ca[k]) / n; cb[k] = warp_sum(cb[k]) / n; }
+  for (int k = 0; k < 3; ++k) { ca[k] = warp_sum((double)sa[k]) / n; cb[k] = warp_sum((double)sb[k]) / n; }
+  const float caf[3] = {(float)ca[0], (float)ca[1], (float)ca[2]}, cbf[3] = {(float)cb[0], (float)cb[1], (float)cb[2]};
   // pass 2: covariance of the centred sets
-  double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  float Hf[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   for (int l = lane; l < L; l += 32) {
     if (pm && pm[l] == 0.f) continue;
-    double p[3], q[3];
+    float p[3], q[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { p[k] = pa[3 * l + k] - ca[k]; q[k] = pb[3 * l + k] - cb[k]; }
+    for (int k = 0; k < 3; ++k) { p[k] = pa[3 * l + k] - caf[k]; q[k] = pb[3 * l + k] - cbf[k]; }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) H[i][j] += p[i] * q[j];
+      for (int j = 0; j < 3; ++j) Hf[i][j] = fmaf(p[i], q[j], Hf[i][j]);
   }
+  double H[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) H[i][j] = warp_sum(H[i][j]);
+    for (int j = 0; j < 3; ++j) H[i][j] = warp_sum((double)Hf[i][j]);
   double R[3][3];
   if (lane == 0) kabsch_rotation(H, R);
 #pragma unroll
@@ -48,21 +54,25 @@ __device__ __forceinline__ float kabsch_pair(const float* __restrict__ pa, const
 #pragma unroll
     for (int j = 0; j < 3; ++j) R[i][j] = __shfl_sync(0xffffffffu, R[i][j], 0);
   // pass 3: residual
-  double e = 0.0;
+  float Rf[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Rf[i][k] = (float)(mode == 0 ? R[i][k] : R[k][i]);
+  float ef = 0.f;
   for (int l = lane; l < L; l += 32) {
     if (pm && pm[l] == 0.f) continue;
-    double p[3];
+    float p[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) p[k] = pa[3 * l + k] - ca[k];
+    for (int k = 0; k < 3; ++k) p[k] = pa[3 * l + k] - caf[k];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double q = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) q += (mode == 0 ? R[i][k] : R[k][i]) * p[k];
-      double d = q - (pb[3 * l + i] - cb[i]);
-      e += d * d;
+      const float q = fmaf(Rf[i][2], p[2], fmaf(Rf[i][1], p[1], Rf[i][0] * p[0]));
+      const float d = q - (pb[3 * l + i] - cbf[i]);
+      ef = fmaf(d, d, ef);
     }
   }
+  double e = (double)ef;
   e = warp_sum(e);
   return (float)sqrt(e / n);
 }
