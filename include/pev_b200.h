@@ -261,6 +261,19 @@ int pev_kabsch_rmsd_pairs(const float* a, const float* mask, int32_t S, int32_t 
 int pev_validate_geometry(const float* ca, const float* mask, int32_t S, int32_t L, int32_t mask_batch,
                           int32_t* status, float* stats, void* stream);
 
+/* ---------------------------------------------------------------- evaluation metrics
+ * scripts/validation_metrics.py for S structures at once.  pev_superpose_scores: kabsch_align (:57-85, over all L
+ * residues) of a[s] onto b[s or 0]; dist[S,L] = per-residue distance after superposition, aligned[S,L,3] (or NULL),
+ * tm[S] = compute_tm_score_python (:23-54), gdt_ts / gdt_ha[S] = compute_gdt (:156-199, masked, percent) (each may be
+ * NULL).  pev_lddt: compute_lddt (:92-149): per_residue[S,L] and global[S].  pev_rmsf: compute_rmsf (:206-241) of an
+ * ensemble already aligned to its first member (pev_superpose_scores with b = a[0]): out[L]. */
+int pev_superpose_scores(const float* a, const float* b, const float* mask, int32_t S, int32_t L, int32_t b_batch,
+                         int32_t mask_batch, float* aligned, float* dist, float* tm, float* gdt_ts, float* gdt_ha,
+                         void* stream);
+int pev_lddt(const float* pred, const float* tru, const float* mask, int32_t S, int32_t L, int32_t t_batch,
+             int32_t mask_batch, float cutoff, float* per_residue, float* global, void* stream);
+int pev_rmsf(const float* aligned, int32_t N, int32_t L, float* out, void* stream);
+
 /* ---------------------------------------------------------------- K1, fused CTA-pair form (csrc/edge_tc3_kernels.cu)
  * One kernel for the whole forward edge MLP of EGNLayer.forward (models/en_gnn_decoder.py:60-79): phi_e[1..3] ->
  * agg = index_add_(m) (:68-69) and phi_x (:76), with m kept on chip between the two 256 x 256 GEMMs.  Run by CTA

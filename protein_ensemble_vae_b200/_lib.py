@@ -51,6 +51,9 @@ _PROTOS = {
     "pev_dihedral_terms_bwd": (c_int32, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "pev_kabsch_rmsd": (c_int32, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pev_validate_geometry": (c_int32, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "pev_superpose_scores": (c_int32, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pev_lddt": (c_int32, [_P, _P, _P, _I, _I, _I, _I, c_float, _P, _P, _P]),
+    "pev_rmsf": (c_int32, [_P, _I, _I, _P, _P]),
 }
 # tensor-core entry points: present in libpev_b200.so only (no host restatement)
 _PROTOS_TC = {

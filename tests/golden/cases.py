@@ -132,3 +132,19 @@ def kabsch_inputs():
     return a, b, mask
 
 
+
+
+def metrics_inputs():
+    """Structure pairs and an ensemble for the evaluation metrics (scripts/validation_metrics.py): S pairs of length L with
+    growing noise (one rigidly moved, one reflected), float32; masks with gaps."""
+    rng = np.random.default_rng(71)
+    S, L = 6, 48
+    true = np.cumsum(rng.standard_normal((S, L, 3)) * 2.2, axis=1)
+    q, _ = np.linalg.qr(rng.standard_normal((S, 3, 3)))
+    q[:, :, 0] *= np.sign(np.linalg.det(q))[:, None]
+    pred = np.einsum("slk,sjk->slj", true, q) + 4.0 * rng.standard_normal((S, 1, 3))
+    pred = pred + np.array([0.0, 0.2, 0.6, 1.5, 3.0, 8.0])[:, None, None] * rng.standard_normal((S, L, 3))
+    pred[4] = pred[4] * np.array([1.0, 1.0, -1.0])
+    mask = synth.make_masks(S, L, 73, "gaps")
+    ens = true[0][None] + 0.8 * rng.standard_normal((7, L, 3)) * np.linspace(0.2, 2.0, L)[None, :, None]
+    return synth.f32(pred), synth.f32(true), mask, synth.f32(ens)

@@ -278,6 +278,32 @@ def gen_kabsch():
                         optimal=np.array(correct, np.float64))
 
 
+# --------------------------------------------------------------------------- evaluation metrics
+def gen_metrics():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_validation_metrics", os.path.join(REF, "scripts", "validation_metrics.py"))
+    vm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vm)
+    pred, true, mask, ens = cases.metrics_inputs()
+    out = {"tm": [], "gdt_ts": [], "gdt_ha": [], "gdt_ts_masked": [], "gdt_ha_masked": [], "lddt": [], "lddt_res": [],
+           "lddt_masked": [], "lddt_res_masked": []}
+    for s in range(pred.shape[0]):
+        p, t, m = pred[s].astype(np.float64), true[s].astype(np.float64), mask[s].astype(bool)
+        out["tm"].append(vm.compute_tm_score_python(p, t))
+        a, b = vm.compute_gdt(p, t)
+        out["gdt_ts"].append(a), out["gdt_ha"].append(b)
+        a, b = vm.compute_gdt(p, t, m)
+        out["gdt_ts_masked"].append(a), out["gdt_ha_masked"].append(b)
+        g, r = vm.compute_lddt(p, t)
+        out["lddt"].append(g), out["lddt_res"].append(r)
+        g, r = vm.compute_lddt(p, t, m)
+        out["lddt_masked"].append(g), out["lddt_res_masked"].append(r)
+    out = {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
+    out["rmsf"] = vm.compute_rmsf(ens.astype(np.float64))
+    out["aligned0"] = vm.kabsch_align(pred[0].astype(np.float64), true[0].astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_edges()
     gen_layers()
@@ -285,6 +311,7 @@ if __name__ == "__main__":
     gen_big_decoders()
     gen_losses()
     gen_kabsch()
+    gen_metrics()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

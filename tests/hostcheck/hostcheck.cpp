@@ -9,6 +9,7 @@
 #include "../../include/pev_b200.h"
 #include "../../protein_ensemble_vae_b200/csrc/pev_egnn_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_kabsch_body.cuh"
+#include "../../protein_ensemble_vae_b200/csrc/pev_metrics_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_loss_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_loss_final.cuh"
 
@@ -270,6 +271,41 @@ int pev_validate_geometry(const float* ca, const float* mask, int32_t S, int32_t
   for (int s = 0; s < S; ++s)
     status[s] = validate_geometry_serial(ca + (int64_t)s * L * 3, mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr,
                                          L, stats ? stats + 3 * s : nullptr);
+  return 0;
+}
+
+int pev_superpose_scores(const float* a, const float* b, const float* mask, int32_t S, int32_t L, int32_t b_batch,
+                         int32_t mask_batch, float* aligned, float* dist, float* tm, float* gdt_ts, float* gdt_ha, void*) {
+  for (int s = 0; s < S; ++s) {
+    float* d = dist + (int64_t)s * L;
+    superpose_serial(a + (int64_t)s * L * 3, b + (b_batch ? (int64_t)s * L * 3 : 0), L,
+                     aligned ? aligned + (int64_t)s * L * 3 : nullptr, d);
+    float t, g1, g2;
+    superposition_scores(d, mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr, L, &t, &g1, &g2);
+    if (tm) tm[s] = t;
+    if (gdt_ts) gdt_ts[s] = g1;
+    if (gdt_ha) gdt_ha[s] = g2;
+  }
+  return 0;
+}
+
+int pev_lddt(const float* pred, const float* tru, const float* mask, int32_t S, int32_t L, int32_t t_batch,
+             int32_t mask_batch, float cutoff, float* per_residue, float* global, void*) {
+  for (int s = 0; s < S; ++s) {
+    const float* m = mask ? mask + (mask_batch ? (int64_t)s * L : 0) : nullptr;
+    float sum = 0.f, cnt = 0.f;
+    for (int i = 0; i < L; ++i) {
+      const float v = lddt_residue(pred + (int64_t)s * L * 3, tru + (t_batch ? (int64_t)s * L * 3 : 0), m, L, i, cutoff);
+      per_residue[(int64_t)s * L + i] = v;
+      if (!m || m[i] != 0.f) { sum += v; cnt += 1.f; }
+    }
+    global[s] = cnt > 0.f ? sum / cnt : 0.f;
+  }
+  return 0;
+}
+
+int pev_rmsf(const float* aligned, int32_t N, int32_t L, float* out, void*) {
+  for (int l = 0; l < L; ++l) out[l] = rmsf_residue(aligned, N, L, l);
   return 0;
 }
 
