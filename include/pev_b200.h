@@ -307,6 +307,28 @@ int pev_node_gemm(int32_t epilogue, const float* A1, int32_t K1, const float* A2
                   const float* bias, int64_t M, int32_t Nout, float scale, const float* aux, const float* gamma,
                   const float* beta, float eps, void* out, float* out2, float* mean, float* rstd, void* stream);
 
+/* fp32-accurate forms of the two calls above for the exact path (precision="fp32"): every product is the 3xTF32 sum
+ * hi lo + lo hi + hi hi accumulated in fp32 (error ~2^-22 relative), operands split on chip.  Replace the fp32 nn.Linear
+ * calls of EGNLayer.forward (models/en_gnn_decoder.py:61-79: phi_e[0] node halves, phi_e[2], phi_x[0], phi_h) and their
+ * autograd GEMMs.  pev_split_tf32 writes the split image [hi ; lo] ([2 R, C]) of W [rows, cols] (transpose = 0) or of W^T
+ * (transpose = 1); pev_node_gemm3: out[M,Nout] = A[M,K] W^T (+ bias) (+ res), W3 = split image of W [Nout,K];
+ * pev_node_wgrad3: arguments as pev_node_wgrad (same workspace size). */
+int pev_split_tf32(const float* W, int32_t rows, int32_t cols, int32_t transpose, float* out, void* stream);
+int pev_node_gemm3(const float* A, int32_t K, const float* W3, const float* bias, int64_t M, int32_t Nout,
+                   const float* res, float* out, void* stream);
+int pev_node_wgrad3(const float* G, int32_t Mo, const float* X, int64_t N, float scale, float* workspace, float* out,
+                    int32_t ldc, void* stream);
+
+/* ---------------------------------------------------------------- ragged packed batches (csrc/data_kernels.cu)
+ * Device-side replacement for the host centring + zero-padding of models/data.py (:166-172, :219-266): the packed rows of
+ * B conformers (n / ca / c [T,3], mask [T], dih [T,6], labels [T] int64, emb [T,D] or NULL; conformer b = rows
+ * cu_seqlens[b] .. cu_seqlens[b+1]) -> padded [B,Lmax,...] tensors, coordinates centred on each conformer's valid-CA
+ * centroid when center != 0, exact zeros past a conformer's length. */
+int pev_unpack_center(const float* n, const float* ca, const float* c, const float* mask, const float* dih,
+                      const int64_t* labels, const float* emb, const int32_t* cu_seqlens, int32_t B, int32_t Lmax, int32_t D,
+                      int32_t center, float* o_n, float* o_ca, float* o_c, float* o_mask, float* o_dih, int64_t* o_labels,
+                      float* o_emb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

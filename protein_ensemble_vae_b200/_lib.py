@@ -79,6 +79,10 @@ _PROTOS_TC = {
     # node-level tcgen05 TF32 GEMMs with fused epilogues (csrc/node_gemm_kernels.cu)
     "pev_node_wgrad_workspace_bytes": (c_int64, []),
     "pev_node_wgrad": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
+    "pev_unpack_center": (c_int32, [_P] * 8 + [_I, _I, _I, _I] + [_P] * 8),
+    "pev_split_tf32": (c_int32, [_P, _I, _I, _I, _P, _P]),
+    "pev_node_gemm3": (c_int32, [_P, _I, _P, _P, _L, _I, _P, _P, _P]),
+    "pev_node_wgrad3": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
     "pev_node_gemm": (c_int32, [_I, _P, _I, _P, _I, _P, _P, _L, _I, c_float, _P, _P, _P, c_float, _P, _P, _P, _P, _P]),
     # fused CTA-pair edge kernels (csrc/edge_tc3_kernels.cu)
     "pev_edge3_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),

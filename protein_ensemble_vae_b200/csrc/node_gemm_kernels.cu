@@ -501,6 +501,344 @@ node_wgrad_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, con
   }
 }
 
+
+// =================================================================================================== 3xTF32 forms
+// fp32-accurate products on the TF32 tensor cores for the exact path (precision="fp32", 1e-5 parity): every operand is
+// split as x ~= hi + lo with hi = rna_tf32(x) and lo = rna_tf32(x - hi) (both exact TF32 values, 22 significant bits
+// together), and  x w ~= hi_x lo_w + lo_x hi_w + hi_x hi_w  is accumulated in fp32 in TMEM: the
+// dropped lo lo term and the truncation of the lo parts are ~2^-22 relative, the level of fp32 rounding itself.  Weights are
+// split once per parameter version into a stacked [2 rows, K] image (pev_split_tf32); activations are split INSIDE the
+// kernel by four extra warps between the TMA landing and the MMA issue, so they cross HBM once.  Replaces the SIMT
+// sgemm calls of the fp32 form of EGNLayer.forward (models/en_gnn_decoder.py:61-79).
+__device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& lo) {
+  uint32_t h0, h1, h2, h3;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v.x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v.y));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h2) : "f"(v.z));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h3) : "f"(v.w));
+  hi = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+  // lo rounded to TF32 here: the tensor core would TRUNCATE it, a bias that adds up coherently over K (measured 3.7e-6 at
+  // K = 512 against 8.8e-7 for an fp32 library GEMM)
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v.x - hi.x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v.y - hi.y));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h2) : "f"(v.z - hi.z));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h3) : "f"(v.w - hi.w));
+  lo = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+}
+// hi in place, lo at +lo_off, over `bytes` of shared memory, by the 128 threads of the split warps
+__device__ __forceinline__ void split_region(uint8_t* base, int lo_off, int bytes, int tid) {
+#pragma unroll 4
+  for (int off = tid * 16; off < bytes; off += 128 * 16) {
+    float4 hi, lo;
+    split_tf32(*reinterpret_cast<const float4*>(base + off), hi, lo);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + lo_off + off) = lo;
+  }
+}
+
+namespace x3 {
+constexpr int STAGES = 2;
+constexpr int A_LO_OFF = A_BYTES;                          // [A hi 16 KB][A lo 16 KB][W hi 32 KB][W lo 32 KB]
+constexpr int B_HI_OFF = 2 * A_BYTES;
+constexpr int B_LO_OFF = 2 * A_BYTES + B_BYTES;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 96 KB
+constexpr int STG_OFF = STAGES * STAGE_BYTES;
+constexpr int BAR_OFF = STG_OFF + 8 * 4096;
+constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+constexpr int SPLIT_WARP0 = 10;
+constexpr int THREADS = 32 * 14;                           // 0..7 epilogue, 8 TMA, 9 MMA, 10..13 split
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+}  // namespace x3
+
+// out[M, Nout] = A[M, K] W^T (+ bias) (+ res), W given as its split image W3 = [hi ; lo] ([2 Nout, K]).
+__global__ void __launch_bounds__(x3::THREADS, 1)
+node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + x3::BAR_OFF);
+  uint64_t* full = bars;                       // [2] TMA -> split warps, MMA
+  uint64_t* split = bars + 2;                  // [2] split warps -> MMA
+  uint64_t* empty = bars + 4;                  // [2] MMA -> TMA
+  uint64_t* tfull = bars + 6;
+  uint64_t* tempty = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.Nout / BN;
+  const int total = (int)((p.M + BM - 1) / BM) * n_tiles;
+  const int kchunks = p.k1_chunks;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < x3::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], A_BYTES + 2 * B_BYTES);
+          uint8_t* dst = smem + stage * x3::STAGE_BYTES;
+          tma_load_2d(dst, &mapA, kc * BK, m0, &full[stage]);
+          tma_load_2d(dst + x3::B_HI_OFF, &mapB, kc * BK, n0, &full[stage]);
+          tma_load_2d(dst + x3::B_LO_OFF, &mapB, kc * BK, p.Nout + n0, &full[stage]);
+          if (++stage == x3::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_tf32(BM, BN);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&full[stage], phase);
+          mbar_wait(&split[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * x3::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + x3::A_LO_OFF, b_hi = a_hi + x3::B_HI_OFF, b_lo = a_hi + x3::B_LO_OFF;
+          const uint32_t d = tmem_base + acc * BN;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {       // the two small products first, then hi hi
+            umma_tf32(d, desc_kmajor(a_hi + ks * 32), desc_kmajor(b_lo + ks * 32), IDESC, (kc | ks) != 0 ? 1u : 0u);
+            umma_tf32(d, desc_kmajor(a_lo + ks * 32), desc_kmajor(b_hi + ks * 32), IDESC, 1u);
+            umma_tf32(d, desc_kmajor(a_hi + ks * 32), desc_kmajor(b_hi + ks * 32), IDESC, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == x3::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= x3::SPLIT_WARP0) {
+    const int tid = threadIdx.x - 32 * x3::SPLIT_WARP0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x)
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&full[stage], phase);
+        split_region(smem + stage * x3::STAGE_BYTES, x3::A_LO_OFF, A_BYTES, tid);
+        fence_proxy_async();
+        mbar_arrive(&split[stage]);
+        if (++stage == x3::STAGES) { stage = 0; phase ^= 1; }
+      }
+  } else {
+    const int q = warp & 3, hh = warp >> 2;
+    float* stg = reinterpret_cast<float*>(smem + x3::STG_OFF) + warp * 1024;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const bool valid = row < p.M;
+      const int64_t wrow0 = (int64_t)m0 + q * 32;
+      const int rows_valid = (int)((p.M - wrow0) < 0 ? 0 : ((p.M - wrow0) > 32 ? 32 : (p.M - wrow0)));
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hh * 128);
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        const int c0 = n0 + hh * 128 + 32 * b;
+        uint32_t raw[32];
+        tmem_ld32_issue(taddr + 32 * b, raw);
+        float val[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+        if (p.res) {
+          const float* arow = p.res + (valid ? row : 0) * p.Nout + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + 4 * j4);
+            val[4 * j4] += v.x; val[4 * j4 + 1] += v.y; val[4 * j4 + 2] += v.z; val[4 * j4 + 3] += v.w;
+          }
+        }
+        tmem_wait();
+        if (b == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] += __uint_as_float(raw[j]);
+        store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Weight gradients, 3xTF32: as node_wgrad_kernel with K-chunks of 16 rows, both operands split in shared memory.
+namespace w3 {
+constexpr int WK = 16;
+constexpr int BOX = WK * 128;                    // 2 KB: [16 rows][32 floats]
+constexpr int OP = 8 * BOX;                      // 16 KB: 256 columns of one operand
+constexpr int LO_OFF = 2 * OP;                   // [G hi][X hi][G lo][X lo]
+constexpr int STAGE = 4 * OP;                    // 64 KB
+constexpr int STAGES = 3;
+constexpr int BAR_OFF = STAGES * STAGE;
+constexpr int SMEM = BAR_OFF + 128 + 1024;
+constexpr int THREADS = 32 * 10;                 // 0..3 flush, 4 TMA, 5 MMA, 6..9 split
+}  // namespace w3
+
+__global__ void __launch_bounds__(w3::THREADS, 1)
+node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w3::BAR_OFF);
+  uint64_t* full = bars;
+  uint64_t* split = bars + w3::STAGES;
+  uint64_t* empty = bars + 2 * w3::STAGES;
+  uint64_t* done = bars + 3 * w3::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = blockIdx.x % p.nblk, slice = blockIdx.x / p.nblk;
+  const int64_t r0 = (int64_t)slice * p.rows_per_slice;
+  int64_t r1 = r0 + p.rows_per_slice;
+  if (r1 > p.N) r1 = p.N;
+  const int chunks = r1 > r0 ? (int)((r1 - r0 + w3::WK - 1) / w3::WK) : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < w3::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], 2 * w3::OP);
+        uint8_t* dst = smem + stage * w3::STAGE;
+        const int row = (int)(r0 + (int64_t)c * w3::WK);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          tma_load_2d(dst + b * w3::BOX, &mapG, blk * 256 + 32 * b, row, &full[stage]);
+          tma_load_2d(dst + w3::OP + b * w3::BOX, &mapX, 32 * b, row, &full[stage]);
+        }
+        if (++stage == w3::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_tf32(128, 256) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&full[stage], phase);
+        mbar_wait(&split[stage], phase);
+        tc_fence_after();
+        const uint32_t g_hi = smem_u32(smem + stage * w3::STAGE);
+        const uint32_t x_hi = g_hi + w3::OP, g_lo = g_hi + w3::LO_OFF, x_lo = x_hi + w3::LO_OFF;
+#pragma unroll
+        for (int ks = 0; ks < w3::WK / 8; ++ks)
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const uint32_t ao = mh * 4 * w3::BOX + ks * 1024, bo = ks * 1024;
+            const uint32_t d = tmem_base + mh * 256;
+            umma_tf32(d, desc_mn_32b(g_hi + ao, w3::BOX, 512), desc_mn_32b(x_lo + bo, w3::BOX, 512), IDESC, (c | ks) != 0 ? 1u : 0u);
+            umma_tf32(d, desc_mn_32b(g_lo + ao, w3::BOX, 512), desc_mn_32b(x_hi + bo, w3::BOX, 512), IDESC, 1u);
+            umma_tf32(d, desc_mn_32b(g_hi + ao, w3::BOX, 512), desc_mn_32b(x_hi + bo, w3::BOX, 512), IDESC, 1u);
+          }
+        umma_commit(&empty[stage]);
+        if (++stage == w3::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    const int tid = threadIdx.x - 32 * 6;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < chunks; ++c) {
+      mbar_wait(&full[stage], phase);
+      split_region(smem + stage * w3::STAGE, w3::LO_OFF, 2 * w3::OP, tid);
+      fence_proxy_async();
+      mbar_arrive(&split[stage]);
+      if (++stage == w3::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* dst = p.partial + ((int64_t)slice * p.nblk + blk) * 65536;
+#pragma unroll 1
+    for (int mh = 0; mh < 2; ++mh) {
+      float* drow = dst + (int64_t)(mh * 128 + warp * 32 + lane) * 256;
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t raw[32];
+        if (chunks > 0) {
+          tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mh * 256 + cb * 32), raw);
+          tmem_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(drow + cb * 32 + 4 * k) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// W fp32 [rows, cols] -> out [2 R, C] = [hi ; lo] of W (transpose = 0: R = rows, C = cols) or of W^T (R = cols, C = rows)
+__global__ void split_weight_kernel(const float* __restrict__ W, int rows, int cols, int transpose, float* __restrict__ out) {
+  const int R = transpose ? cols : rows, C = transpose ? rows : cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)R * C; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i % C);
+    const float v = transpose ? W[(int64_t)c * cols + r] : W[i];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    out[i] = __uint_as_float(h);
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
+    out[(int64_t)R * C + i] = __uint_as_float(l);
+  }
+}
+
 }  // namespace ng
 }  // namespace pev
 
@@ -581,4 +919,77 @@ extern "C" int pev_node_gemm(int32_t epilogue, const float* A1, int32_t K1, cons
     default:
       return set_error(1, "pev_node_gemm: unknown epilogue %d", epilogue);
   }
+}
+
+extern "C" int pev_split_tf32(const float* W, int32_t rows, int32_t cols, int32_t transpose, float* out, void* stream) {
+  PEV_REQUIRE(W && out && rows > 0 && cols > 0, "bad argument");
+  const int64_t n = (int64_t)rows * cols;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 4 * sm_count()) grid = 4 * sm_count();
+  ng::split_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, rows, cols, transpose, out);
+  return after_launch("split_weight_kernel");
+}
+
+extern "C" int pev_node_gemm3(const float* A, int32_t K, const float* W3, const float* bias, int64_t M, int32_t Nout,
+                              const float* res, float* out, void* stream) {
+  PEV_REQUIRE(A && W3 && out && M >= 0, "null argument");
+  PEV_REQUIRE((Nout == 256 || Nout == 512) && K > 0 && K % 32 == 0, "shape: Nout in {256, 512}, K a multiple of 32");
+  if (M == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ng::node_gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::x3::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(2, "node_gemm3_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  ng::Params p = {};
+  p.M = M; p.Nout = Nout; p.k1_chunks = K / 32; p.bias = bias; p.res = res; p.out = out;
+  alignas(64) CUtensorMap mA, mB;
+  if (int rc = ng::make_f32_map(A, M, K, K, ng::BM, &mA)) return rc;
+  if (int rc = ng::make_f32_map(W3, 2 * (int64_t)Nout, K, K, ng::BN, &mB)) return rc;
+  const int total = (int)((M + ng::BM - 1) / ng::BM) * (Nout / ng::BN);
+  const int grid = total < sm_count() ? total : sm_count();
+  ng::node_gemm3_kernel<<<grid, ng::x3::THREADS, ng::x3::SMEM_BYTES, st>>>(p, mA, mB);
+  return after_launch("node_gemm3_kernel");
+}
+
+extern "C" int pev_node_wgrad3(const float* G, int32_t Mo, const float* X, int64_t N, float scale, float* workspace,
+                               float* out, int32_t ldc, void* stream) {
+  PEV_REQUIRE(G && X && out && workspace && N >= 0 && (Mo == 256 || Mo == 512) && ldc >= 256, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int nblk = Mo / 256;
+  if (N == 0) {
+    for (int r = 0; r < Mo; ++r) cudaMemsetAsync(out + (int64_t)r * ldc, 0, sizeof(float) * 256, st);
+    return 0;
+  }
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ng::node_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::w3::SMEM);
+    if (e != cudaSuccess) return set_error(2, "node_wgrad3_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int slices = sm_count() / nblk;
+  const int64_t chunks = (N + ng::w3::WK - 1) / ng::w3::WK;
+  if (slices > chunks) slices = (int)chunks;
+  ng::WParams p = {};
+  p.N = N; p.nblk = nblk; p.partial = workspace;
+  p.rows_per_slice = (int)(((chunks + slices - 1) / slices) * ng::w3::WK);
+  slices = (int)((N + p.rows_per_slice - 1) / p.rows_per_slice);
+  alignas(64) CUtensorMap mG, mX;
+  if (int rc = ng::make_f32_map(G, N, Mo, Mo, ng::w3::WK, &mG, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = ng::make_f32_map(X, N, 256, 256, ng::w3::WK, &mX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  ng::node_wgrad3_kernel<<<slices * nblk, ng::w3::THREADS, ng::w3::SMEM, st>>>(p, mG, mX);
+  if (int rc = after_launch("node_wgrad3_kernel")) return rc;
+  for (int b = 0; b < nblk; ++b) {
+    if (ldc == 256) {
+      if (int rc = launch_partial_reduce(workspace + (int64_t)b * 65536, slices, (int64_t)nblk * 65536, 65536, scale,
+                                         out + (int64_t)b * 65536, st)) return rc;
+    } else {
+      if (int rc = launch_partial_reduce_2d(workspace + (int64_t)b * 65536, slices, (int64_t)nblk * 65536, 256, 256, scale,
+                                            out + (int64_t)b * 256 * ldc, ldc, st)) return rc;
+    }
+  }
+  return 0;
 }

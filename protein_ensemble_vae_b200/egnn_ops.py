@@ -91,14 +91,30 @@ class ScatterCoord(torch.autograd.Function):
         return gm, gw, gx, None, None
 
 
+def _linear(lin, *xs):
+    """``lin([x1 | x2 ...])``: 3xTF32 tensor-core GEMMs on the device (``egnn_tc.Linear3x``), plain torch elsewhere."""
+    from . import egnn_tc
+    if all(x.shape[1] == 256 for x in xs) and egnn_tc.linear3x_supported(xs[0], lin.weight[:, :256]) \
+            and lin.weight.shape[1] == 256 * len(xs):
+        return egnn_tc.Linear3x.apply(lin.weight, lin.bias, *xs)
+    return lin(xs[0] if len(xs) == 1 else torch.cat(xs, -1))
+
+
 def egn_layer_fp32(layer, h, x, g: PackedGraph, dinv):
-    """One EGNN layer on the exact-order fp32 path; ``layer`` is an ``EGNLayer`` (parameter holder)."""
+    """One EGNN layer on the exact-order fp32 path; ``layer`` is an ``EGNLayer`` (parameter holder).  Every 256-wide
+    linear (``phi_e[0]``'s node halves, ``phi_e[2]``, ``phi_x[0]``, ``phi_h``) runs on the tensor cores as a 3xTF32 product
+    with fp32-level accuracy; ``phi_x[2]`` (256 -> 1) is a row dot product and stays a GEMV."""
     D = layer.node_dim
     W1 = layer.phi_e[0].weight                                    # [H, 2D+1] = [Wa | Wb | wd]
-    AB = h @ torch.cat([W1[:, :D], W1[:, D:2 * D]], 0).t()        # [N, 2H]: A = h Wa^T, B = h Wb^T
+    Wab = torch.cat([W1[:, :D], W1[:, D:2 * D]], 0)               # [2H, D]: AB = h [Wa ; Wb]^T
+    from . import egnn_tc
+    if egnn_tc.linear3x_supported(h, Wab):
+        AB = egnn_tc.Linear3x.apply(Wab, None, h)
+    else:
+        AB = h @ Wab.t()
     u = EdgePrologue.apply(AB, x, W1[:, 2 * D], layer.phi_e[0].bias, g)
-    m = layer.phi_e[3](layer.phi_e[2](layer.phi_e[1](u)))         # silu -> Linear -> silu
-    w = layer.phi_x(m).squeeze(-1)                                # [E]
+    m = layer.phi_e[3](_linear(layer.phi_e[2], layer.phi_e[1](u)))   # silu -> Linear -> silu
+    w = layer.phi_x[2](layer.phi_x[1](_linear(layer.phi_x[0], m))).squeeze(-1)   # [E]
     agg, x_new = ScatterCoord.apply(m, w, x, dinv, g)
-    h_new = layer.norm_h(h + layer.phi_h(torch.cat([h, agg], -1)))
+    h_new = layer.norm_h(h + _linear(layer.phi_h[2], layer.phi_h[1](_linear(layer.phi_h[0], h, agg))))
     return h_new, x_new

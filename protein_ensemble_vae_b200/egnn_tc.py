@@ -261,6 +261,83 @@ class NodePhiH(torch.autograd.Function):
         return gh, gagg, gW3, column_sum(gp), gW4, column_sum(gr), dgb[:D], dgb[D:], None
 
 
+# ------------------------------------------------------------------------------------------------- 3xTF32 (exact path)
+def split_weight(W, transpose=False):
+    """Split image ``[hi ; lo]`` (``[2R, C]``) of ``W`` (or of ``W^T``) for :func:`node_gemm3` (``pev_split_tf32``)."""
+    W = f32c(W.detach())
+    rows, cols = W.shape
+    R, C = (cols, rows) if transpose else (rows, cols)
+    with torch.cuda.device_of(W):
+        out = torch.empty(2 * R, C, dtype=torch.float32, device=W.device)
+        _lib.lib().call("pev_split_tf32", ptr(W), rows, cols, int(transpose), ptr(out), stream(W))
+    return out
+
+
+def node_gemm3(A, W3, bias=None, res=None):
+    """``A W^T (+ bias) (+ res)`` with fp32-level accuracy on the TF32 tensor cores (``pev_node_gemm3``); ``W3`` is the
+    split image of ``W [Nout,K]``."""
+    M, K = A.shape
+    Nout = W3.shape[0] // 2
+    with torch.cuda.device_of(A):
+        out = torch.empty(M, Nout, dtype=torch.float32, device=A.device)
+        _lib.lib().call("pev_node_gemm3", ptr(A), K, ptr(W3), ptr(bias), M, Nout, ptr(res), ptr(out), stream(A))
+    return out
+
+
+def node_wgrad3(G, X, scale=1.0, out=None):
+    """:func:`node_wgrad` with 3xTF32 products (``pev_node_wgrad3``)."""
+    N, Mo = G.shape
+    dev = G.device
+    ws = _WGRAD_WS.get(dev)
+    with torch.cuda.device_of(G):
+        if ws is None:
+            ws = _WGRAD_WS[dev] = torch.empty(_lib.lib().cdll.pev_node_wgrad_workspace_bytes() // 4, dtype=torch.float32,
+                                              device=dev)
+        if out is None:
+            out = torch.empty(Mo, X.shape[1], dtype=torch.float32, device=dev)
+        _lib.lib().call("pev_node_wgrad3", ptr(G), Mo, ptr(X), N, float(scale), ptr(ws), c_void_p(out.data_ptr()),
+                        out.stride(0), stream(G))
+    return out
+
+
+def linear3x_supported(x, W) -> bool:
+    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and W.shape[0] in (256, 512)
+            and W.shape[1] == 256 and x.shape[1] == 256)
+
+
+class Linear3x(torch.autograd.Function):
+    """``[x1 | x2 ...] W^T + b`` (256-column operands ``xs``, never concatenated) on the tensor cores at fp32 accuracy:
+    forward, ``g W`` and ``g^T x`` are all 3xTF32 (``csrc/node_gemm_kernels.cu``).  The exact path's replacement for
+    ``nn.Linear`` in ``EGNLayer.forward`` (``models/en_gnn_decoder.py:61-79``)."""
+
+    @staticmethod
+    def forward(ctx, W, b, *xs):
+        xs = tuple(f32c(x) for x in xs)
+        Wd = f32c(W.detach())
+        y = None
+        for i, x in enumerate(xs):
+            y = node_gemm3(x, split_weight(Wd[:, 256 * i:256 * (i + 1)]),
+                           f32c(b.detach()) if (i == 0 and b is not None) else None, y)
+        ctx.save_for_backward(Wd, *xs)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        Wd, *xs = ctx.saved_tensors
+        g = f32c(g)
+        Nout, K = Wd.shape
+        gW = torch.empty(Nout, K, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        gxs = []
+        for i, x in enumerate(xs):                                           # every operand is 256 columns wide
+            Wk = Wd[:, 256 * i:256 * (i + 1)]
+            gxs.append(node_gemm3(g, split_weight(Wk, transpose=True)) if ctx.needs_input_grad[2 + i] else None)
+            if gW is not None:
+                node_wgrad3(g, x, out=gW[:, 256 * i:256 * (i + 1)])
+        gb = column_sum(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        return (gW, gb, *gxs)
+
+
 def apply_tf32(module, x, fp32_forward=False):
     """Run an ``nn.Linear`` / ``nn.Sequential`` of the decoder with its linears on :class:`NodeLinear` (bf16 path)."""
     if isinstance(module, nn.Linear):

@@ -148,3 +148,24 @@ def metrics_inputs():
     mask = synth.make_masks(S, L, 73, "gaps")
     ens = true[0][None] + 0.8 * rng.standard_normal((7, L, 3)) * np.linspace(0.2, 2.0, L)[None, :, None]
     return synth.f32(pred), synth.f32(true), mask, synth.f32(ens)
+
+
+def data_conformers():
+    """Raw conformer dicts as ``EnsembleDataset._load`` builds them (models/data.py:120-131): lengths 37 / 64 / 5 / 50, one
+    with interior mask gaps, one fully masked, uncentred coordinates, 24-wide sequence embeddings."""
+    rng = np.random.default_rng(81)
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    confs = []
+    for i, L in enumerate((37, 64, 5, 50)):
+        ca = np.cumsum(rng.standard_normal((L, 3)) * 2.2, axis=0) + 30.0 * rng.standard_normal(3)
+        mask = np.ones(L)
+        if i == 1:
+            mask[10:15] = 0
+        if i == 2:
+            mask[:] = 0
+        confs.append({"n": synth.f32(ca + 0.8 * rng.standard_normal((L, 3))), "ca": synth.f32(ca),
+                      "c": synth.f32(ca + 0.8 * rng.standard_normal((L, 3))), "mask": synth.f32(mask),
+                      "seq_emb": synth.f32(rng.standard_normal((L, 24))), "dihedrals": synth.f32(rng.uniform(-1, 1, (L, 6))),
+                      "sequence": "".join(aa[k] for k in rng.integers(0, 20, L)) + ("X" if i == 0 else "")})
+    confs[0]["sequence"] = "X" + confs[0]["sequence"][1:37]        # unknown letter -> label 0 (:183)
+    return confs

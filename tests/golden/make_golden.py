@@ -304,6 +304,22 @@ def gen_metrics():
     np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
 
 
+# --------------------------------------------------------------------------- data path (centring + padding collate)
+def gen_data():
+    import importlib.util, types
+    for name in ("h5py",):                       # models/data.py imports h5py at the top; nothing used here touches it
+        sys.modules.setdefault(name, types.ModuleType(name))
+    spec = importlib.util.spec_from_file_location("ref_data", os.path.join(REF, "models", "data.py"))
+    rd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rd)
+    confs = cases.data_conformers()
+    items = [rd.EnsembleDataset._process_conformer(None, c) for c in confs]          # centred 7-tuples (:153-194)
+    n, ca, c, mask, emb, dih, lbl = rd._collate_single_batch(items)                  # (:219-266)
+    np.savez_compressed(os.path.join(HERE, "data.npz"), n=n.numpy(), ca=ca.numpy(), c=c.numpy(), mask=mask.numpy(),
+                        emb=emb.numpy(), dih=dih.numpy(), labels=lbl.numpy(),
+                        item_labels=np.concatenate([it[6].numpy() for it in items]))
+
+
 if __name__ == "__main__":
     gen_edges()
     gen_layers()
@@ -312,6 +328,7 @@ if __name__ == "__main__":
     gen_losses()
     gen_kabsch()
     gen_metrics()
+    gen_data()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

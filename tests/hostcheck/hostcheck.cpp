@@ -9,6 +9,7 @@
 #include "../../include/pev_b200.h"
 #include "../../protein_ensemble_vae_b200/csrc/pev_egnn_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_kabsch_body.cuh"
+#include "../../protein_ensemble_vae_b200/csrc/pev_data_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_metrics_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_loss_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_loss_final.cuh"
@@ -306,6 +307,31 @@ int pev_lddt(const float* pred, const float* tru, const float* mask, int32_t S, 
 
 int pev_rmsf(const float* aligned, int32_t N, int32_t L, float* out, void*) {
   for (int l = 0; l < L; ++l) out[l] = rmsf_residue(aligned, N, L, l);
+  return 0;
+}
+
+int pev_unpack_center(const float* n, const float* ca, const float* c, const float* mask, const float* dih,
+                      const int64_t* labels, const float* emb, const int32_t* cu, int32_t B, int32_t Lmax, int32_t D,
+                      int32_t center, float* o_n, float* o_ca, float* o_c, float* o_mask, float* o_dih, int64_t* o_labels,
+                      float* o_emb, void*) {
+  UnpackArgs a = {n, ca, c, mask, dih, labels, emb, cu, B, Lmax, D, o_n, o_ca, o_c, o_mask, o_dih, o_labels, o_emb};
+  for (int b = 0; b < B; ++b) {
+    const int L = cu[b + 1] - cu[b];
+    double s[3] = {0, 0, 0}, cnt = 0;
+    if (center)
+      for (int l = 0; l < L; ++l)
+        if (mask[cu[b] + l] != 0.f) {
+          for (int k = 0; k < 3; ++k) s[k] += ca[3 * (int64_t)(cu[b] + l) + k];
+          cnt += 1;
+        }
+    const float cen[3] = {cnt > 0 ? (float)(s[0] / cnt) : 0.f, cnt > 0 ? (float)(s[1] / cnt) : 0.f, cnt > 0 ? (float)(s[2] / cnt) : 0.f};
+    for (int l = 0; l < Lmax; ++l) {
+      unpack_row(a, b, l, cen);
+      if (emb)
+        for (int d = 0; d < D; ++d)
+          o_emb[((int64_t)b * Lmax + l) * D + d] = l < L ? emb[((int64_t)cu[b] + l) * D + d] : 0.f;
+    }
+  }
   return 0;
 }
 

@@ -87,3 +87,60 @@ def test_node_wgrad_matches_float64(N):
     assert rel_err(wide[:, 256:], G.double().t() @ X.double()) < 2e-3 and float((wide[:, :256] - 7.0).abs().max()) == 0.0
     a, b = node_wgrad(G, X), node_wgrad(G, X)
     assert torch.equal(a, b)                                  # fixed-order reduction: bit-reproducible
+
+
+# ------------------------------------------------------------------------------------------------- 3xTF32 forms
+@pytest.mark.parametrize("M,K,Nout", [(1000, 256, 256), (77, 256, 512), (4096 + 5, 512, 256), (300, 768, 512)])
+def test_gemm3_has_fp32_accuracy(M, K, Nout):
+    """pev_node_gemm3 against float64: error at the level of an fp32 GEMM (<= 2e-6 of the output scale), two orders of
+    magnitude below plain TF32 on the same inputs."""
+    from protein_ensemble_vae_b200 import egnn_tc
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g) * torch.exp(torch.randn(M, 1, device="cuda", generator=g))
+    W = torch.randn(Nout, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(Nout, device="cuda", generator=g)
+    res = torch.randn(M, Nout, device="cuda", generator=g)
+    ref = A.double() @ W.double().t() + b.double() + res.double()
+    out = egnn_tc.node_gemm3(A, egnn_tc.split_weight(W), b, res)
+    e3 = float((out.double() - ref).abs().max() / ref.abs().max())
+    e1 = float((egnn_tc.node_gemm(egnn_tc.EPI_PLAIN, A, W, b, aux=res)[0].double() - ref).abs().max() / ref.abs().max())
+    ef = float(((A @ W.t() + b + res).double() - ref).abs().max() / ref.abs().max())
+    assert e3 < 2e-6 and e3 < 0.05 * e1, (e3, e1, ef)
+    W3t = egnn_tc.split_weight(W, transpose=True)                    # [2K, Nout]: the image of W^T
+    assert float((W3t[:K] + W3t[K:] - W.t()).abs().max() / W.abs().max()) < 2e-7
+
+
+@pytest.mark.parametrize("N,Mo", [(5000, 256), (33, 512), (65536 + 17, 512)])
+def test_wgrad3_has_fp32_accuracy(N, Mo):
+    from protein_ensemble_vae_b200 import egnn_tc
+    g = torch.Generator(device="cuda").manual_seed(N)
+    G = torch.randn(N, Mo, device="cuda", generator=g)
+    X = torch.randn(N, 256, device="cuda", generator=g) + 0.5
+    ref = 0.5 * (G.double().t() @ X.double())
+    out = egnn_tc.node_wgrad3(G, X, 0.5)
+    e3 = float((out.double() - ref).abs().max() / ref.abs().max())
+    e1 = float((egnn_tc.node_wgrad(G, X, 0.5).double() - ref).abs().max() / ref.abs().max())
+    assert e3 < 2e-6 and e3 < 0.05 * e1, (e3, e1)
+    wide = torch.zeros(Mo, 512, device="cuda")
+    egnn_tc.node_wgrad3(G, X, 0.5, out=wide[:, 256:])
+    assert torch.equal(wide[:, 256:], out) and float(wide[:, :256].abs().max()) == 0.0
+    assert torch.equal(egnn_tc.node_wgrad3(G, X, 0.5), out)          # fixed-order reduction: bit-reproducible
+
+
+def test_linear3x_autograd_matches_float64():
+    from protein_ensemble_vae_b200 import egnn_tc
+    torch.manual_seed(5)
+    N = 3000
+    x1 = torch.randn(N, 256, device="cuda", requires_grad=True)
+    x2 = torch.randn(N, 256, device="cuda", requires_grad=True)
+    W = (torch.randn(256, 512, device="cuda") / 16).requires_grad_()
+    b = torch.randn(256, device="cuda", requires_grad=True)
+    coef = torch.randn(N, 256, device="cuda")
+    y = egnn_tc.Linear3x.apply(W, b, x1, x2)
+    grads = torch.autograd.grad((y * coef).sum(), [x1, x2, W, b])
+    d = [t.detach().double().requires_grad_() for t in (x1, x2, W, b)]
+    yr = torch.cat([d[0], d[1]], 1) @ d[2].t() + d[3]
+    gr = torch.autograd.grad((yr * coef.double()).sum(), d)
+    assert float((y.double() - yr).abs().max() / yr.abs().max()) < 2e-6
+    for a, r in zip(grads, gr):
+        assert float((a.double() - r).abs().max() / r.abs().max()) < 3e-6
