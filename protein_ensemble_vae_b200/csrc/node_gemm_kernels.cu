@@ -537,11 +537,18 @@ __device__ __forceinline__ void split_region(uint8_t* base, int lo_off, int byte
 }
 
 namespace x3 {
-constexpr int STAGES = 2;
-constexpr int A_LO_OFF = A_BYTES;                          // [A hi 16 KB][A lo 16 KB][W hi 32 KB][W lo 32 KB]
+// Tile 128 x 128 (not 128 x 256): the 512 TMEM columns then hold THREE accumulators per tile beside each other -- the
+// hi hi products of the first and of the second half of K, and the two small products -- because the tensor core
+// TRUNCATES every addition into its fp32 accumulator: the error of a product grows with the number of MMA instructions
+// per accumulator (measured with everything in one: 3.8e-6 at K = 512; small products apart: 1.6e-6; library fp32
+// GEMM: 0.9e-6).  In the small accumulator a truncation costs 2^-11 of what it costs in a main one.
+constexpr int BN3 = 128;
+constexpr int B3_BYTES = BN3 * BK * 4;                     // 16 KB
+constexpr int STAGES = 3;
+constexpr int A_LO_OFF = A_BYTES;                          // [A hi 16 KB][A lo 16 KB][W hi 16 KB][W lo 16 KB]
 constexpr int B_HI_OFF = 2 * A_BYTES;
-constexpr int B_LO_OFF = 2 * A_BYTES + B_BYTES;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 96 KB
+constexpr int B_LO_OFF = 2 * A_BYTES + B3_BYTES;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B3_BYTES;    // 64 KB
 constexpr int STG_OFF = STAGES * STAGE_BYTES;
 constexpr int BAR_OFF = STG_OFF + 8 * 4096;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
@@ -556,26 +563,25 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + x3::BAR_OFF);
-  uint64_t* full = bars;                       // [2] TMA -> split warps, MMA
-  uint64_t* split = bars + 2;                  // [2] split warps -> MMA
-  uint64_t* empty = bars + 4;                  // [2] MMA -> TMA
-  uint64_t* tfull = bars + 6;
-  uint64_t* tempty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* full = bars;                       // [3] TMA -> split warps, MMA
+  uint64_t* split = bars + 3;                  // [3] split warps -> MMA
+  uint64_t* empty = bars + 6;                  // [3] MMA -> TMA
+  uint64_t* tfull = bars + 9;
+  uint64_t* tempty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.Nout / BN;
+  const int n_tiles = p.Nout / x3::BN3;
   const int total = (int)((p.M + BM - 1) / BM) * n_tiles;
   const int kchunks = p.k1_chunks;
+  const int khalf = (kchunks + 1) / 2;         // chunks [0, khalf) -> accumulator a, the rest -> b
   if (threadIdx.x == 0) {
     for (int s = 0; s < x3::STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&split[s], 128);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], EPI_WARPS);
-    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -589,10 +595,10 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * x3::BN3;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], A_BYTES + 2 * B_BYTES);
+          mbar_arrive_expect_tx(&full[stage], A_BYTES + 2 * x3::B3_BYTES);
           uint8_t* dst = smem + stage * x3::STAGE_BYTES;
           tma_load_2d(dst, &mapA, kc * BK, m0, &full[stage]);
           tma_load_2d(dst + x3::B_HI_OFF, &mapB, kc * BK, n0, &full[stage]);
@@ -604,12 +610,11 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
     __syncwarp();
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
-      constexpr uint32_t IDESC = idesc_tf32(BM, BN);
+      constexpr uint32_t IDESC = idesc_tf32(BM, x3::BN3);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait(tempty, (it & 1) ^ 1);
         tc_fence_after();
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&full[stage], phase);
@@ -617,17 +622,19 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * x3::STAGE_BYTES);
           const uint32_t a_lo = a_hi + x3::A_LO_OFF, b_hi = a_hi + x3::B_HI_OFF, b_lo = a_hi + x3::B_LO_OFF;
-          const uint32_t d = tmem_base + acc * BN;
+          const bool second = kc >= khalf;
+          const uint32_t dmain = tmem_base + (second ? x3::BN3 : 0), dsmall = tmem_base + 2 * x3::BN3;
+          const int kfirst = second ? khalf : 0;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {       // the two small products first, then hi hi
-            umma_tf32(d, desc_kmajor(a_hi + ks * 32), desc_kmajor(b_lo + ks * 32), IDESC, (kc | ks) != 0 ? 1u : 0u);
-            umma_tf32(d, desc_kmajor(a_lo + ks * 32), desc_kmajor(b_hi + ks * 32), IDESC, 1u);
-            umma_tf32(d, desc_kmajor(a_hi + ks * 32), desc_kmajor(b_hi + ks * 32), IDESC, 1u);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            umma_tf32(dsmall, desc_kmajor(a_hi + ks * 32), desc_kmajor(b_lo + ks * 32), IDESC, (kc | ks) != 0 ? 1u : 0u);
+            umma_tf32(dsmall, desc_kmajor(a_lo + ks * 32), desc_kmajor(b_hi + ks * 32), IDESC, 1u);
+            umma_tf32(dmain, desc_kmajor(a_hi + ks * 32), desc_kmajor(b_hi + ks * 32), IDESC, ((kc - kfirst) | ks) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
           if (++stage == x3::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit(tfull);
       }
     }
     __syncwarp();
@@ -644,24 +651,23 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
         if (++stage == x3::STAGES) { stage = 0; phase ^= 1; }
       }
   } else {
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, hh = warp >> 2;            // TMEM lane quarter, 64-column half of the tile
     float* stg = reinterpret_cast<float*>(smem + x3::STG_OFF) + warp * 1024;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * x3::BN3;
       const int64_t row = (int64_t)m0 + q * 32 + lane;
       const bool valid = row < p.M;
       const int64_t wrow0 = (int64_t)m0 + q * 32;
       const int rows_valid = (int)((p.M - wrow0) < 0 ? 0 : ((p.M - wrow0) > 32 ? 32 : (p.M - wrow0)));
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hh * 128);
-      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
+      mbar_wait(tfull, it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
-        const int c0 = n0 + hh * 128 + 32 * b;
+      for (int b = 0; b < 2; ++b) {
+        const int c0 = n0 + hh * 64 + 32 * b;
         uint32_t raw[32];
-        tmem_ld32_issue(taddr + 32 * b, raw);
+        tmem_ld32_issue(taddr + 2 * x3::BN3 + 32 * b, raw);              // small products first
         float val[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) val[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
@@ -674,13 +680,24 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
           }
         }
         tmem_wait();
-        if (b == 3) {
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
+        if (kchunks > 1) {
+          tmem_ld32_issue(taddr + x3::BN3 + 32 * b, raw);
+          tmem_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(raw[j]);
+        }
+        tmem_ld32_issue(taddr + 32 * b, raw);
+        tmem_wait();
+        if (b == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) mbar_arrive(tempty);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] += __uint_as_float(raw[j]);
+        for (int j = 0; j < 32; ++j) val[j] += acc[j] + __uint_as_float(raw[j]);
         store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
       }
     }
@@ -704,6 +721,9 @@ constexpr int STAGES = 3;
 constexpr int BAR_OFF = STAGES * STAGE;
 constexpr int SMEM = BAR_OFF + 128 + 1024;
 constexpr int THREADS = 32 * 10;                 // 0..3 flush, 4 TMA, 5 MMA, 6..9 split
+// The tensor core truncates every addition into its accumulator, an error that grows with the number of MMA
+// instructions per output: TMEM is flushed into the CTA's fp32 partial (round-to-nearest adds, L2-resident) every SUB chunks.
+constexpr int SUB = 32;                          // 512 rows = 192 MMA instructions per output element and flush
 }  // namespace w3
 
 __global__ void __launch_bounds__(w3::THREADS, 1)
@@ -714,14 +734,16 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
   uint64_t* full = bars;
   uint64_t* split = bars + w3::STAGES;
   uint64_t* empty = bars + 2 * w3::STAGES;
-  uint64_t* done = bars + 3 * w3::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* done = bars + 3 * w3::STAGES;          // MMA -> flush warps: a sub-slice is accumulated
+  uint64_t* flushed = done + 1;                    // flush warps -> MMA: TMEM may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(flushed + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk = blockIdx.x % p.nblk, slice = blockIdx.x / p.nblk;
   const int64_t r0 = (int64_t)slice * p.rows_per_slice;
   int64_t r1 = r0 + p.rows_per_slice;
   if (r1 > p.N) r1 = p.N;
   const int chunks = r1 > r0 ? (int)((r1 - r0 + w3::WK - 1) / w3::WK) : 0;
+  const int subs = (chunks + w3::SUB - 1) / w3::SUB;
   if (threadIdx.x == 0) {
     for (int s = 0; s < w3::STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -729,6 +751,7 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
       mbar_init(&empty[s], 1);
     }
     mbar_init(done, 1);
+    mbar_init(flushed, 128);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
@@ -761,6 +784,11 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
       int stage = 0;
       uint32_t phase = 0;
       for (int c = 0; c < chunks; ++c) {
+        const int cs = c % w3::SUB;                 // position inside the sub-slice
+        if (cs == 0 && c > 0) {
+          mbar_wait(flushed, ((c / w3::SUB) - 1) & 1);
+          tc_fence_after();
+        }
         mbar_wait(&full[stage], phase);
         mbar_wait(&split[stage], phase);
         tc_fence_after();
@@ -772,14 +800,14 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
           for (int mh = 0; mh < 2; ++mh) {
             const uint32_t ao = mh * 4 * w3::BOX + ks * 1024, bo = ks * 1024;
             const uint32_t d = tmem_base + mh * 256;
-            umma_tf32(d, desc_mn_32b(g_hi + ao, w3::BOX, 512), desc_mn_32b(x_lo + bo, w3::BOX, 512), IDESC, (c | ks) != 0 ? 1u : 0u);
+            umma_tf32(d, desc_mn_32b(g_hi + ao, w3::BOX, 512), desc_mn_32b(x_lo + bo, w3::BOX, 512), IDESC, (cs | ks) != 0 ? 1u : 0u);
             umma_tf32(d, desc_mn_32b(g_lo + ao, w3::BOX, 512), desc_mn_32b(x_hi + bo, w3::BOX, 512), IDESC, 1u);
             umma_tf32(d, desc_mn_32b(g_hi + ao, w3::BOX, 512), desc_mn_32b(x_hi + bo, w3::BOX, 512), IDESC, 1u);
           }
         umma_commit(&empty[stage]);
+        if (cs == w3::SUB - 1 || c == chunks - 1) umma_commit(done);
         if (++stage == w3::STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done);
     }
     __syncwarp();
   } else if (warp >= 6) {
@@ -794,25 +822,42 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
       if (++stage == w3::STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
-    mbar_wait(done, 0);
-    tc_fence_after();
+    // flush: after every sub-slice TMEM is ADDED (fp32, round to nearest) into this CTA's partial block, lane = output row
     float* dst = p.partial + ((int64_t)slice * p.nblk + blk) * 65536;
+    for (int ss = 0; ss < (subs > 0 ? subs : 1); ++ss) {
+      if (chunks > 0) {
+        mbar_wait(done, ss & 1);
+        tc_fence_after();
+      }
 #pragma unroll 1
-    for (int mh = 0; mh < 2; ++mh) {
-      float* drow = dst + (int64_t)(mh * 128 + warp * 32 + lane) * 256;
+      for (int mh = 0; mh < 2; ++mh) {
+        float* drow = dst + (int64_t)(mh * 128 + warp * 32 + lane) * 256;
 #pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
-        uint32_t raw[32];
-        if (chunks > 0) {
-          tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mh * 256 + cb * 32), raw);
-          tmem_wait();
-        } else {
+        for (int cb = 0; cb < 8; ++cb) {
+          uint32_t raw[32];
+          if (chunks > 0) {
+            tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mh * 256 + cb * 32), raw);
+            tmem_wait();
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) raw[j] = 0u;
+            for (int j = 0; j < 32; ++j) raw[j] = 0u;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 v = make_float4(__uint_as_float(raw[4 * k]), __uint_as_float(raw[4 * k + 1]), __uint_as_float(raw[4 * k + 2]),
+                                   __uint_as_float(raw[4 * k + 3]));
+            float4* q = reinterpret_cast<float4*>(drow + cb * 32 + 4 * k);
+            if (ss > 0) {
+              const float4 o = *q;
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *q = v;
+          }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<uint4*>(drow + cb * 32 + 4 * k) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
+      }
+      if (chunks > 0 && ss + 1 < subs) {
+        tc_fence_before();
+        mbar_arrive(flushed);
       }
     }
   }
@@ -947,8 +992,8 @@ extern "C" int pev_node_gemm3(const float* A, int32_t K, const float* W3, const 
   p.M = M; p.Nout = Nout; p.k1_chunks = K / 32; p.bias = bias; p.res = res; p.out = out;
   alignas(64) CUtensorMap mA, mB;
   if (int rc = ng::make_f32_map(A, M, K, K, ng::BM, &mA)) return rc;
-  if (int rc = ng::make_f32_map(W3, 2 * (int64_t)Nout, K, K, ng::BN, &mB)) return rc;
-  const int total = (int)((M + ng::BM - 1) / ng::BM) * (Nout / ng::BN);
+  if (int rc = ng::make_f32_map(W3, 2 * (int64_t)Nout, K, K, ng::x3::BN3, &mB)) return rc;
+  const int total = (int)((M + ng::BM - 1) / ng::BM) * (Nout / ng::x3::BN3);
   const int grid = total < sm_count() ? total : sm_count();
   ng::node_gemm3_kernel<<<grid, ng::x3::THREADS, ng::x3::SMEM_BYTES, st>>>(p, mA, mB);
   return after_launch("node_gemm3_kernel");

@@ -92,8 +92,8 @@ def test_node_wgrad_matches_float64(N):
 # ------------------------------------------------------------------------------------------------- 3xTF32 forms
 @pytest.mark.parametrize("M,K,Nout", [(1000, 256, 256), (77, 256, 512), (4096 + 5, 512, 256), (300, 768, 512)])
 def test_gemm3_has_fp32_accuracy(M, K, Nout):
-    """pev_node_gemm3 against float64: error at the level of an fp32 GEMM (<= 2e-6 of the output scale), two orders of
-    magnitude below plain TF32 on the same inputs."""
+    """pev_node_gemm3 against float64: error at the level of an fp32 library GEMM (tools/check_gemm3.py prints the table),
+    more than two orders of magnitude below plain TF32 on the same inputs."""
     from protein_ensemble_vae_b200 import egnn_tc
     g = torch.Generator(device="cuda").manual_seed(M + K)
     A = torch.randn(M, K, device="cuda", generator=g) * torch.exp(torch.randn(M, 1, device="cuda", generator=g))
@@ -105,12 +105,13 @@ def test_gemm3_has_fp32_accuracy(M, K, Nout):
     e3 = float((out.double() - ref).abs().max() / ref.abs().max())
     e1 = float((egnn_tc.node_gemm(egnn_tc.EPI_PLAIN, A, W, b, aux=res)[0].double() - ref).abs().max() / ref.abs().max())
     ef = float(((A @ W.t() + b + res).double() - ref).abs().max() / ref.abs().max())
-    assert e3 < 2e-6 and e3 < 0.05 * e1, (e3, e1, ef)
+    print(f"gemm3 M={M} K={K} Nout={Nout}: 3xTF32 {e3:.2e}, TF32 {e1:.2e}, library fp32 {ef:.2e}")
+    assert e3 < 1.5e-6 and e3 < 0.01 * e1, (e3, e1, ef)           # measured 0.25 - 1.1e-6 (library fp32: 0.4 - 0.9e-6)
     W3t = egnn_tc.split_weight(W, transpose=True)                    # [2K, Nout]: the image of W^T
     assert float((W3t[:K] + W3t[K:] - W.t()).abs().max() / W.abs().max()) < 2e-7
 
 
-@pytest.mark.parametrize("N,Mo", [(5000, 256), (33, 512), (65536 + 17, 512)])
+@pytest.mark.parametrize("N,Mo", [(5000, 256), (33, 512), (65536 + 17, 512), (1205760, 256)])
 def test_wgrad3_has_fp32_accuracy(N, Mo):
     from protein_ensemble_vae_b200 import egnn_tc
     g = torch.Generator(device="cuda").manual_seed(N)
@@ -120,7 +121,9 @@ def test_wgrad3_has_fp32_accuracy(N, Mo):
     out = egnn_tc.node_wgrad3(G, X, 0.5)
     e3 = float((out.double() - ref).abs().max() / ref.abs().max())
     e1 = float((egnn_tc.node_wgrad(G, X, 0.5).double() - ref).abs().max() / ref.abs().max())
-    assert e3 < 2e-6 and e3 < 0.05 * e1, (e3, e1)
+    ef = float(((0.5 * (G.t() @ X)).double() - ref).abs().max() / ref.abs().max())
+    print(f"wgrad3 N={N} Mo={Mo}: 3xTF32 {e3:.2e}, TF32 {e1:.2e}, library fp32 {ef:.2e}")
+    assert e3 < 6e-6 and e3 < 0.02 * e1, (e3, e1, ef)             # measured 0.3 - 4.3e-6 (library fp32: 0.2 - 6.2e-6)
     wide = torch.zeros(Mo, 512, device="cuda")
     egnn_tc.node_wgrad3(G, X, 0.5, out=wide[:, 256:])
     assert torch.equal(wide[:, 256:], out) and float(wide[:, :256].abs().max()) == 0.0
@@ -141,6 +144,6 @@ def test_linear3x_autograd_matches_float64():
     d = [t.detach().double().requires_grad_() for t in (x1, x2, W, b)]
     yr = torch.cat([d[0], d[1]], 1) @ d[2].t() + d[3]
     gr = torch.autograd.grad((yr * coef.double()).sum(), d)
-    assert float((y.double() - yr).abs().max() / yr.abs().max()) < 2e-6
+    assert float((y.detach().double() - yr.detach()).abs().max() / yr.detach().abs().max()) < 3e-6
     for a, r in zip(grads, gr):
-        assert float((a.double() - r).abs().max() / r.abs().max()) < 3e-6
+        assert float((a.double() - r).abs().max() / r.abs().max()) < 6e-6
