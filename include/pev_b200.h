@@ -319,6 +319,17 @@ int pev_node_gemm3(const float* A, int32_t K, const float* W3, const float* bias
 int pev_node_wgrad3(const float* G, int32_t Mo, const float* X, int64_t N, float scale, float* workspace, float* out,
                     int32_t ldc, void* stream);
 
+/* General linear layer on the same kernels (used by the encoder, models/encoder.py:30-262): out[M,Nout] (leading dimension
+ * ldc) = act(A[M,K] W^T + bias + res), act = ReLU when relu != 0; A / res / out may be column blocks of wider row-major
+ * tensors (lda / ldres / ldc, multiples of 4).  precise = 0: TF32, W fp32 [Nout,K], Nout a multiple of 256; precise = 1:
+ * 3xTF32, W = pev_split_tf32 image [2 Nout, K], Nout a multiple of 128.  K a multiple of 32.
+ * pev_linear_wgrad: out[Mo,256] (leading dimension ldc) = scale * G^T X for G [N,Mo] (ldg; Mo = 256 or 512) and
+ * X [N,256] (ldx); workspace of pev_node_wgrad_workspace_bytes(). */
+int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t K, const float* W, const float* bias, int64_t M,
+               int32_t Nout, int32_t relu, const float* res, int64_t ldres, float* out, int64_t ldc, void* stream);
+int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int64_t N,
+                     float scale, float* workspace, float* out, int64_t ldc, void* stream);
+
 /* ---------------------------------------------------------------- ragged packed batches (csrc/data_kernels.cu)
  * Device-side replacement for the host centring + zero-padding of models/data.py (:166-172, :219-266): the packed rows of
  * B conformers (n / ca / c [T,3], mask [T], dih [T,6], labels [T] int64, emb [T,D] or NULL; conformer b = rows

@@ -80,6 +80,8 @@ _PROTOS_TC = {
     "pev_node_wgrad_workspace_bytes": (c_int64, []),
     "pev_node_wgrad": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
     "pev_unpack_center": (c_int32, [_P] * 8 + [_I, _I, _I, _I] + [_P] * 8),
+    "pev_linear": (c_int32, [_I, _P, _L, _I, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P]),
+    "pev_linear_wgrad": (c_int32, [_I, _P, _L, _I, _P, _L, _L, c_float, _P, _P, _L, _P]),
     "pev_split_tf32": (c_int32, [_P, _I, _I, _I, _P, _P]),
     "pev_node_gemm3": (c_int32, [_P, _I, _P, _P, _L, _I, _P, _P, _P]),
     "pev_node_wgrad3": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),

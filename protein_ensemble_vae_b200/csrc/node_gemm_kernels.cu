@@ -59,6 +59,9 @@ struct Params {
   float eps;
   float* mean;            // RES_LN (null in inference)
   float* rstd;
+  int64_t ldc;            // PLAIN (and the 3xTF32 kernel): leading dimensions of out / res; 0 = Nout
+  int64_t ldres;
+  int relu;               // PLAIN: out = max(., 0)
 };
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
@@ -115,6 +118,8 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
   const int kchunks = p.k1_chunks + p.k2_chunks;
 
   for (int k = threadIdx.x; k < 512; k += THREADS) sBias[k] = (p.bias && k < p.Nout) ? p.bias[k] : 0.f;
+  const bool wide = p.Nout > 512;                      // PLAIN only: bias read from global memory
+  const int64_t ldc = p.ldc ? p.ldc : p.Nout, ldres = p.ldres ? p.ldres : p.Nout;
   if (EPI == EPI_RES_LN)
     for (int k = threadIdx.x; k < 256; k += THREADS) {
       sGamma[k] = p.gamma[k];
@@ -265,7 +270,7 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
           tmem_ld32_issue(taddr + 32 * b, raw);
           float aux[32];
           if (EPI == EPI_DSILU || (EPI == EPI_PLAIN && p.res)) {
-            const float* arow = p.res + (valid ? row : 0) * p.Nout + c0;
+            const float* arow = p.res + (valid ? row : 0) * (EPI == EPI_PLAIN ? ldres : (int64_t)p.Nout) + c0;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 v = *reinterpret_cast<const float4*>(arow + 4 * j4);
@@ -280,7 +285,8 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
           }
           float val[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(raw[j]) + sBias[c0 + j];
+          for (int j = 0; j < 32; ++j)
+            val[j] = __uint_as_float(raw[j]) + ((EPI == EPI_PLAIN && wide) ? (p.bias ? __ldg(p.bias + c0 + j) : 0.f) : sBias[c0 + j]);
           if (EPI == EPI_ABH) {
             if (valid) {
               __half* o = p.out16 + row * p.Nout + c0;
@@ -304,9 +310,13 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
               else if (EPI == EPI_DSILU) {
                 const float pz = aux[j], sg = 1.0f / (1.0f + __expf(-pz));
                 val[j] = v * sg * (1.0f + pz * (1.0f - sg));
-              } else if (p.res) val[j] = v + aux[j];
+              } else {
+                if (p.res) val[j] = v + aux[j];
+                if (p.relu) val[j] = fmaxf(val[j], 0.f);
+              }
             }
-            store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
+            if (EPI == EPI_PLAIN) store_block32(stg, val, p.out + wrow0 * ldc + c0, ldc, rows_valid, lane);
+            else store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
           }
         }
       }
@@ -347,7 +357,8 @@ static int make_f32_map(const void* base, int64_t rows, int64_t cols, int64_t ld
 }
 
 template <int EPI>
-static int launch(const Params& p, const float* A1, int64_t K1, const float* A2, int64_t K2, const float* W, cudaStream_t st) {
+static int launch(const Params& p, const float* A1, int64_t K1, const float* A2, int64_t K2, const float* W, cudaStream_t st,
+                  int64_t lda = 0, int64_t ldw = 0) {
   static bool configured_dev[kMaxDevices] = {};
   bool& configured = configured_dev[current_device()];
   if (!configured) {
@@ -356,13 +367,13 @@ static int launch(const Params& p, const float* A1, int64_t K1, const float* A2,
     configured = true;
   }
   alignas(64) CUtensorMap mA1, mA2, mB;
-  if (int rc = make_f32_map(A1, p.M, K1, K1, BM, &mA1)) return rc;
+  if (int rc = make_f32_map(A1, p.M, K1, lda ? lda : K1, BM, &mA1)) return rc;
   if (A2) {
     if (int rc = make_f32_map(A2, p.M, K2, K2, BM, &mA2)) return rc;
   } else {
     memcpy(&mA2, &mA1, sizeof(mA1));
   }
-  if (int rc = make_f32_map(W, p.Nout, K1 + K2, K1 + K2, BN, &mB)) return rc;
+  if (int rc = make_f32_map(W, p.Nout, K1 + K2, ldw ? ldw : K1 + K2, BN, &mB)) return rc;
   const int total = (int)((p.M + BM - 1) / BM) * (p.Nout / BN);
   const int grid = total < sm_count() ? total : sm_count();
   node_gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(p, mA1, mA2, mB);
@@ -672,7 +683,7 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) val[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
         if (p.res) {
-          const float* arow = p.res + (valid ? row : 0) * p.Nout + c0;
+          const float* arow = p.res + (valid ? row : 0) * (p.ldres ? p.ldres : (int64_t)p.Nout) + c0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 v = *reinterpret_cast<const float4*>(arow + 4 * j4);
@@ -697,8 +708,14 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
           if (lane == 0) mbar_arrive(tempty);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] += acc[j] + __uint_as_float(raw[j]);
-        store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
+        for (int j = 0; j < 32; ++j) {
+          val[j] += acc[j] + __uint_as_float(raw[j]);
+          if (p.relu) val[j] = fmaxf(val[j], 0.f);
+        }
+        {
+          const int64_t ldc = p.ldc ? p.ldc : (int64_t)p.Nout;
+          store_block32(stg, val, p.out + wrow0 * ldc + c0, ldc, rows_valid, lane);
+        }
       }
     }
   }
@@ -1036,5 +1053,74 @@ extern "C" int pev_node_wgrad3(const float* G, int32_t Mo, const float* X, int64
                                             out + (int64_t)b * 256 * ldc, ldc, st)) return rc;
     }
   }
+  return 0;
+}
+
+// General linear layer on the node-level GEMM kernels: out[M,Nout] (leading dimension ldc) = act(A[M,K] W^T + bias + res),
+// A / res with leading dimensions lda / ldres; precise = 0: TF32 (W fp32 [Nout,K], Nout a multiple of 256), precise = 1:
+// 3xTF32 (W = split image [2 Nout, K], Nout a multiple of 128).
+extern "C" int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t K, const float* W, const float* bias, int64_t M,
+                          int32_t Nout, int32_t relu, const float* res, int64_t ldres, float* out, int64_t ldc, void* stream) {
+  PEV_REQUIRE(A && W && out && M >= 0 && K > 0 && K % 32 == 0 && lda >= K && ldc >= Nout && (!res || ldres >= Nout), "bad argument");
+  PEV_REQUIRE(Nout > 0 && Nout % (precise ? 128 : 256) == 0, "Nout: a multiple of 256 (TF32) / 128 (3xTF32)");
+  PEV_REQUIRE(lda % 4 == 0 && ldc % 4 == 0 && (!res || ldres % 4 == 0), "leading dimensions: multiples of 4 floats");
+  if (M == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  ng::Params p = {};
+  p.M = M; p.Nout = Nout; p.k1_chunks = K / 32; p.bias = bias; p.res = res; p.out = out; p.ldc = ldc; p.ldres = ldres; p.relu = relu;
+  if (!precise) return ng::launch<ng::EPI_PLAIN>(p, A, K, nullptr, 0, W, st, lda);
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ng::node_gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::x3::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(2, "node_gemm3_kernel: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  alignas(64) CUtensorMap mA, mB;
+  if (int rc = ng::make_f32_map(A, M, K, lda, ng::BM, &mA)) return rc;
+  if (int rc = ng::make_f32_map(W, 2 * (int64_t)Nout, K, K, ng::x3::BN3, &mB)) return rc;
+  const int total = (int)((M + ng::BM - 1) / ng::BM) * (Nout / ng::x3::BN3);
+  const int grid = total < sm_count() ? total : sm_count();
+  ng::node_gemm3_kernel<<<grid, ng::x3::THREADS, ng::x3::SMEM_BYTES, st>>>(p, mA, mB);
+  return after_launch("node_gemm3_kernel");
+}
+
+// Weight-gradient block: out[Mo, 256] (leading dimension ldc) = scale * G^T X, G [N, Mo] (leading dimension ldg, Mo = 256 or
+// 512), X [N, 256] (leading dimension ldx): column blocks of wider activations without copies.
+extern "C" int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int64_t N,
+                                float scale, float* workspace, float* out, int64_t ldc, void* stream) {
+  PEV_REQUIRE(G && X && out && workspace && N >= 0 && (Mo == 256 || Mo == 512) && ldc >= 256 && ldg >= Mo && ldx >= 256 &&
+              ldg % 4 == 0 && ldx % 4 == 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int nblk = Mo / 256;
+  if (N == 0) {
+    for (int r = 0; r < Mo; ++r) cudaMemsetAsync(out + (int64_t)r * ldc, 0, sizeof(float) * 256, st);
+    return 0;
+  }
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ng::node_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::W_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ng::node_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::w3::SMEM);
+    if (e != cudaSuccess) return set_error(2, "node_wgrad kernels: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int wk = precise ? ng::w3::WK : ng::WK;
+  int slices = sm_count() / nblk;
+  const int64_t chunks = (N + wk - 1) / wk;
+  if (slices > chunks) slices = (int)chunks;
+  ng::WParams p = {};
+  p.N = N; p.nblk = nblk; p.partial = workspace;
+  p.rows_per_slice = (int)(((chunks + slices - 1) / slices) * wk);
+  slices = (int)((N + p.rows_per_slice - 1) / p.rows_per_slice);
+  alignas(64) CUtensorMap mG, mX;
+  if (int rc = ng::make_f32_map(G, N, Mo, ldg, wk, &mG, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = ng::make_f32_map(X, N, 256, ldx, wk, &mX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (precise) ng::node_wgrad3_kernel<<<slices * nblk, ng::w3::THREADS, ng::w3::SMEM, st>>>(p, mG, mX);
+  else ng::node_wgrad_kernel<<<slices * nblk, ng::W_THREADS, ng::W_SMEM, st>>>(p, mG, mX);
+  if (int rc = after_launch("node_wgrad_kernel")) return rc;
+  for (int b = 0; b < nblk; ++b)
+    if (int rc = launch_partial_reduce_2d(workspace + (int64_t)b * 65536, slices, (int64_t)nblk * 65536, 256, 256, scale,
+                                          out + (int64_t)b * 256 * ldc, (int)ldc, st)) return rc;
   return 0;
 }

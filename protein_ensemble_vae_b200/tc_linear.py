@@ -1,0 +1,102 @@
+"""General linear layers on the tcgen05 node-GEMM kernels (``pev_linear`` / ``pev_linear_wgrad``,
+``csrc/node_gemm_kernels.cu``): forward, data gradient and weight gradient of ``y = act(x W^T + b (+ res))`` for row-major
+fp32 activations of any width that is a multiple of 256, either single-pass TF32 or fp32-accurate 3xTF32.  Used by the
+encoder (``encoder.py``); the EGNN layer has its own specialised epilogues (``egnn_tc.py``)."""
+from __future__ import annotations
+
+from ctypes import c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import stream
+from .egnn_tc import _WGRAD_WS, column_sum, split_weight
+
+
+def _p(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _rows(t):
+    """2-D fp32 CUDA tensor whose rows are contiguous (column blocks of wider tensors are fine)."""
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
+        t = t.float().contiguous()
+    return t
+
+
+def supported(x, W) -> bool:
+    return x.is_cuda and x.dim() == 2 and W.shape[0] % 256 == 0 and W.shape[1] % 256 == 0 and x.shape[1] == W.shape[1]
+
+
+def linear_fwd(x, W, bias=None, relu=False, res=None, precise=False, out=None):
+    """``act(x W^T + bias + res)``; ``W`` is the fp32 weight ``[Nout,K]`` (TF32) or its split image (``precise``)."""
+    x = _rows(x)
+    M, K = x.shape
+    Nout = W.shape[0] // 2 if precise else W.shape[0]
+    res = None if res is None else _rows(res)
+    with torch.cuda.device_of(x):
+        if out is None:
+            out = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
+        _lib.lib().call("pev_linear", int(precise), _p(x), x.stride(0), K, _p(W), _p(bias), M, Nout, int(relu), _p(res),
+                        0 if res is None else res.stride(0), _p(out), out.stride(0), stream(x))
+    return out
+
+
+def linear_wgrad(g, x, precise=False):
+    """``g^T x`` (``[Nout,K]``) in 256-column blocks of ``x`` and <= 512-column blocks of ``g``."""
+    g, x = _rows(g), _rows(x)
+    N, Nout = g.shape
+    K = x.shape[1]
+    dev = g.device
+    with torch.cuda.device_of(g):
+        ws = _WGRAD_WS.get(dev)
+        if ws is None:
+            ws = _WGRAD_WS[dev] = torch.empty(_lib.lib().cdll.pev_node_wgrad_workspace_bytes() // 4, dtype=torch.float32,
+                                              device=dev)
+        gW = torch.empty(Nout, K, dtype=torch.float32, device=dev)
+        for n0 in range(0, Nout, 512):
+            Mo = min(512, Nout - n0)
+            for k0 in range(0, K, 256):
+                _lib.lib().call("pev_linear_wgrad", int(precise), _p(g[:, n0:]), g.stride(0), Mo, _p(x[:, k0:]), x.stride(0),
+                                N, 1.0, _p(ws), _p(gW[n0:, k0:]), K, stream(g))
+    return gW
+
+
+class TCLinear(torch.autograd.Function):
+    """``relu?(x W^T + b) (+ res)`` with all three GEMMs on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu, precise, res):
+        Wd = W.detach().float().contiguous()
+        bd = None if b is None else b.detach().float().contiguous()
+        y = linear_fwd(x, split_weight(Wd) if precise else Wd, bd, relu=relu and res is None, res=res, precise=precise)
+        assert not (relu and res is not None)
+        ctx.relu, ctx.precise, ctx.has_res = relu, precise, res is not None
+        ctx.save_for_backward(x, Wd, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, Wd, y = ctx.saved_tensors
+        g = _rows(g)
+        if ctx.relu:
+            g = g * (y > 0)
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = linear_fwd(g, split_weight(Wd, transpose=True) if ctx.precise else Wd.t().contiguous(), precise=ctx.precise)
+        if ctx.needs_input_grad[1]:
+            gW = linear_wgrad(g, x, ctx.precise)
+        if ctx.needs_input_grad[2]:
+            gb = column_sum(g) if g.shape[1] <= 1024 else torch.cat([column_sum(g[:, j:j + 512].contiguous())
+                                                                     for j in range(0, g.shape[1], 512)])
+        return gx, gW, gb, None, None, (g if ctx.has_res else None)
+
+
+def linear(x, W, b=None, relu=False, precise=False, res=None):
+    """``relu?(x W^T + b) + res`` -- tensor-core path for supported shapes, else plain torch (tiny / odd-shaped linears)."""
+    if supported(x, W):
+        return TCLinear.apply(x, W, b, relu, precise, res)
+    y = torch.nn.functional.linear(x, W, b)
+    if relu:
+        y = torch.relu(y)
+    return y if res is None else y + res

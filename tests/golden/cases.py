@@ -169,3 +169,49 @@ def data_conformers():
                       "sequence": "".join(aa[k] for k in rng.integers(0, 20, L)) + ("X" if i == 0 else "")})
     confs[0]["sequence"] = "X" + confs[0]["sequence"][1:37]        # unknown letter -> label 0 (:183)
     return confs
+
+
+# --------------------------------------------------------------------------------------------- encoder (models/encoder.py)
+ENCODER_CASES = {
+    # tag: (seqemb_dim, nlayers, B, L, mask kind, param seed, data seed)
+    "enc2_gaps": (256, 2, 3, 48, "gaps", 91, 92),
+    "enc6_ragged": (1280, 6, 2, 64, "ragged", 93, 94),
+}
+ENC_NORM_WEIGHTS = ("coord_norm.weight", "dihedral_norm.weight", "feature_fusion.1.weight", "norm1.weight", "norm2.weight",
+                    "enc.ln.weight")
+
+
+def encoder_params(shapes, seed):
+    """name -> float32 ndarray for every parameter of ProteinEncoder (``shapes``: name -> shape, the ``pe`` buffer excluded)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name in sorted(shapes):
+        shp = tuple(shapes[name])
+        g = rng.standard_normal(shp)
+        if len(shp) == 2:
+            g = g / np.sqrt(shp[1])
+        elif name.endswith(ENC_NORM_WEIGHTS):
+            g = 1.0 + 0.1 * g
+        elif name.endswith("geom_res_scale"):
+            g = np.asarray(0.3)
+        else:
+            g = 0.1 * g
+        out[name] = synth.f32(g)
+    return out
+
+
+def encoder_inputs(case):
+    """(seq_emb, n, ca, c, dihedrals, mask, coefficients of the scalar test loss over mu_g, lv_g, mu_l, lv_l)."""
+    sd, nl, B, L, mkind, pseed, dseed = case
+    rng = np.random.default_rng(dseed)
+    ca = np.cumsum(rng.standard_normal((B, L, 3)) * 2.2, axis=1)
+    ca = ca - ca.mean(1, keepdims=True)
+    n, c = ca + 0.8 * rng.standard_normal((B, L, 3)), ca + 0.8 * rng.standard_normal((B, L, 3))
+    ang = rng.uniform(-np.pi, np.pi, (B, L, 3))
+    dih = np.stack([np.sin(ang[..., 0]), np.cos(ang[..., 0]), np.sin(ang[..., 1]), np.cos(ang[..., 1]), np.sin(ang[..., 2]),
+                    np.cos(ang[..., 2])], -1)
+    emb = rng.standard_normal((B, L, sd))
+    mask = synth.make_masks(B, L, dseed + 1, mkind)
+    coef = [rng.standard_normal((B, 512)), rng.standard_normal((B, 512)), rng.standard_normal((B, L, 256)) * mask[..., None],
+            rng.standard_normal((B, L, 256)) * mask[..., None]]
+    return [synth.f32(a) for a in (emb, n, ca, c, dih)], mask, [synth.f32(a) for a in coef]

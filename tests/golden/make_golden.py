@@ -304,6 +304,33 @@ def gen_metrics():
     np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
 
 
+# --------------------------------------------------------------------------- encoder
+def gen_encoders():
+    sys.path.insert(0, os.path.join(REF, "models"))
+    import encoder as ref_enc
+    out = {}
+    for tag, case in cases.ENCODER_CASES.items():
+        sd, nl, B, L, mkind, pseed, dseed = case
+        enc = ref_enc.ProteinEncoder(seqemb_dim=sd, nlayers=nl, dropout=0.0).double()
+        shapes = {k: v.shape for k, v in enc.state_dict().items() if k != "enc.pe.pe"}
+        enc.load_state_dict({k: T(v) for k, v in cases.encoder_params(shapes, pseed).items()}, strict=False)
+        enc.train()                                   # dropout 0: train mode keeps nn.TransformerEncoderLayer off its fused path
+        latent_dropout = enc.latent.global_attention.dropout
+        enc.latent.global_attention.dropout = 0.0     # (hard-coded 0.1 in the reference, :159)
+        xs, mask, coef = cases.encoder_inputs(case)
+        H = enc.enc(*[T(a) for a in xs], T(mask))
+        res = enc.latent(H, T(mask))
+        enc.latent.global_attention.dropout = latent_dropout
+        loss = sum((r * T(c)).sum() for r, c in zip(res, coef))
+        loss.backward()
+        for name, r in zip(("mu_g", "lv_g", "mu_l", "lv_l"), res):
+            out[f"{tag}.{name}"] = r.detach().numpy()
+        out[f"{tag}.H"] = (H.detach() * T(mask)[..., None]).numpy().astype(np.float32)
+        pack_grads_big({k: p.grad for k, p in enc.named_parameters() if p.grad is not None}, out, tag)
+        print("encoder case", tag, "done", flush=True)
+    np.savez_compressed(os.path.join(HERE, "encoders.npz"), **out)
+
+
 # --------------------------------------------------------------------------- data path (centring + padding collate)
 def gen_data():
     import importlib.util, types
@@ -329,6 +356,7 @@ if __name__ == "__main__":
     gen_kabsch()
     gen_metrics()
     gen_data()
+    gen_encoders()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

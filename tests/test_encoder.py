@@ -1,0 +1,87 @@
+"""ProteinEncoder: oracle restatement vs the reference's outputs (CPU), device path vs the reference's
+outputs and gradients (GPU; tests/golden/encoders.npz is produced by models/encoder.py in float64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_err
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _shapes(sd_dim, nl):
+    from protein_ensemble_vae_b200.encoder import ProteinEncoder
+    enc = ProteinEncoder(seqemb_dim=sd_dim, nlayers=nl, dropout=0.0)
+    return enc, {k: tuple(v.shape) for k, v in enc.state_dict().items() if k != "enc.pe.pe"}
+
+
+@pytest.mark.parametrize("tag", list(cases.ENCODER_CASES))
+def test_encoder_oracle_matches_reference(tag):
+    from oracle import encoder_oracle as eo
+    gold = np.load(os.path.join(G, "encoders.npz"))
+    case = cases.ENCODER_CASES[tag]
+    _, shapes = _shapes(case[0], case[1])
+    sd = cases.encoder_params(shapes, case[5])
+    xs, mask, _ = cases.encoder_inputs(case)
+    H, mu_g, lv_g, mu_l, lv_l = eo.encoder(sd, *[a.astype(np.float64) for a in xs], mask)
+    mb = mask.astype(bool)
+    assert np.abs(H[mb] - gold[f"{tag}.H"][mb]).max() < 2e-7 * np.abs(H[mb]).max()   # H is stored as float32
+    for got, key in ((mu_g, "mu_g"), (lv_g, "lv_g")):
+        assert np.abs(got - gold[f"{tag}.{key}"]).max() < 1e-11
+    for got, key in ((mu_l, "mu_l"), (lv_l, "lv_l")):
+        assert np.abs(got[mb] - gold[f"{tag}.{key}"][mb]).max() < 1e-11
+
+
+def test_encoder_state_dict_keys_match_reference_layout():
+    enc, shapes = _shapes(1280, 6)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 18068353 - 4096 * 512     # reference count minus the PE buffer
+    assert "enc.transformer_layers.5.self_attn.in_proj_weight" in shapes and shapes["latent.global_query"] == (1, 1, 512)
+    with pytest.raises(RuntimeError):
+        z = torch.zeros(1, 4, 3)
+        enc(torch.zeros(1, 4, 1280), z, z, z, torch.zeros(1, 4, 6), torch.ones(1, 4))    # CUDA only, no CPU fallback
+
+
+def _run(tag, precision):
+    import test_gpu_parity_big as tb
+    case = cases.ENCODER_CASES[tag]
+    enc, shapes = _shapes(case[0], case[1])
+    enc.enc.precision = enc.latent.precision = precision
+    sd = cases.encoder_params(shapes, case[5])
+    enc.load_state_dict({k: torch.tensor(v) for k, v in sd.items()}, strict=False)
+    enc = enc.cuda().train()
+    enc.latent.global_attention.dropout = 0.0
+    xs, mask, coef = cases.encoder_inputs(case)
+    xs = [torch.tensor(a, device="cuda") for a in xs]
+    m = torch.tensor(mask, device="cuda")
+    z_g, z_l, mu_g, lv_g, mu_l, lv_l = enc(*xs, m, eps_g=torch.zeros(mask.shape[0], 512, device="cuda"),
+                                           eps_l=torch.zeros(*mask.shape, 256, device="cuda"))
+    res = (mu_g, lv_g, mu_l, lv_l)
+    sum((r * torch.tensor(c, device="cuda")).sum() for r, c in zip(res, coef)).backward()
+    grads = {k: p.grad for k, p in enc.named_parameters() if p.grad is not None}
+    return mask, res, (z_g, z_l), grads, tb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-5, 1e-4), ("tf32", 3e-3, 2e-2)])
+@pytest.mark.parametrize("tag", list(cases.ENCODER_CASES))
+def test_encoder_matches_reference(tag, precision, tol_out, tol_grad):
+    gold = np.load(os.path.join(G, "encoders.npz"))
+    mask, res, (z_g, z_l), grads, tb = _run(tag, precision)
+    mb = torch.tensor(mask.astype(bool))
+    errs = {}
+    for name, r in zip(("mu_g", "lv_g", "mu_l", "lv_l"), res):
+        got, ref = r.detach().cpu().double(), torch.tensor(gold[f"{tag}.{name}"])
+        if got.dim() == 3:
+            assert float(got[~mb].abs().max()) == 0.0 if (~mb).any() else True          # exact zeros at padding
+            got, ref = got[mb], ref[mb]
+        errs[name] = rel_err(got, ref)
+    assert max(errs.values()) < tol_out, errs
+    assert torch.equal(z_g, res[0]) and torch.equal(z_l, res[2])                          # eps = 0: z = mu
+    gerrs = tb._grad_errors(grads, gold, tag)
+    assert {k.split(".", 2)[2] for k in gold.files if k.startswith(tag + ".g")} == set(gerrs)
+    worst = max(gerrs.items(), key=lambda kv: kv[1][1])
+    assert worst[1][1] < tol_grad, (worst, errs)
+    print(tag, precision, "outputs", {k: f"{v:.1e}" for k, v in errs.items()}, "worst grad (max, l2)", worst)
