@@ -44,8 +44,9 @@ def sinusoidal_pe(L, d):
     return pe
 
 
-def encoder(sd, seq_emb, n, ca, c, dih, mask, nhead=8):
-    """-> (H [B,L,d], mu_g, lv_g [B,zg], mu_l, lv_l [B,L,zl]); every row is computed as in the reference (padded ones too)."""
+def encoder(sd, seq_emb, n, ca, c, dih, mask, nhead=8, pe=None):
+    """-> (H [B,L,d], mu_g, lv_g [B,zg], mu_l, lv_l [B,L,zl]); every row is computed as in the reference (padded ones too).
+    ``pe``: the positional table to use (the reference builds its buffer in float32; default: float64 values)."""
     sd = {k: np.asarray(v, np.float64) for k, v in sd.items()}
     B, L = ca.shape[:2]
     d = sd["enc.ln.weight"].shape[0]
@@ -59,7 +60,7 @@ def encoder(sd, seq_emb, n, ca, c, dih, mask, nhead=8):
         f = np.concatenate([_lin(sd, "enc.seq_proj", seq_emb[b]), coord, dfe], -1)                    # :114-115
         f = np.maximum(_ln(_lin(sd, "enc.feature_fusion.0", f), sd["enc.feature_fusion.1.weight"],
                            sd["enc.feature_fusion.1.bias"]), 0.0)                                     # :118
-        f = f + sinusoidal_pe(L, d)                                                                   # :121
+        f = f + (sinusoidal_pe(L, d) if pe is None else np.asarray(pe[:L], np.float64))                                                                   # :121
         f = f + sd["enc.geom_res_scale"] * _mha(sd, "enc.geometric_attention", f, f, km, nhead // 2)  # :126-132
         for i in range(nlayers):                                                                      # :139-140
             p = f"enc.transformer_layers.{i}"

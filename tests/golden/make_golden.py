@@ -328,6 +328,7 @@ def gen_encoders():
         out[f"{tag}.H"] = (H.detach() * T(mask)[..., None]).numpy().astype(np.float32)
         pack_grads_big({k: p.grad for k, p in enc.named_parameters() if p.grad is not None}, out, tag)
         print("encoder case", tag, "done", flush=True)
+    out["pe"] = enc.enc.pe.pe[:64].numpy().astype(np.float32)      # the reference builds this buffer in float32 (:17-23)
     np.savez_compressed(os.path.join(HERE, "encoders.npz"), **out)
 
 

@@ -26,7 +26,7 @@ def test_encoder_oracle_matches_reference(tag):
     _, shapes = _shapes(case[0], case[1])
     sd = cases.encoder_params(shapes, case[5])
     xs, mask, _ = cases.encoder_inputs(case)
-    H, mu_g, lv_g, mu_l, lv_l = eo.encoder(sd, *[a.astype(np.float64) for a in xs], mask)
+    H, mu_g, lv_g, mu_l, lv_l = eo.encoder(sd, *[a.astype(np.float64) for a in xs], mask, pe=gold["pe"])
     mb = mask.astype(bool)
     assert np.abs(H[mb] - gold[f"{tag}.H"][mb]).max() < 2e-7 * np.abs(H[mb]).max()   # H is stored as float32
     for got, key in ((mu_g, "mu_g"), (lv_g, "lv_g")):
