@@ -330,6 +330,21 @@ int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t K, const fl
 int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int64_t N,
                      float scale, float* workspace, float* out, int64_t ldc, void* stream);
 
+/* ---------------------------------------------------------------- encoder attention (csrc/attn_kernels.cu)
+ * Per-conformer multi-head attention over packed rows (models/encoder.py:125-140, nn.MultiheadAttention with
+ * key_padding_mask) as batched TF32 GEMMs on tcgen05.  The score buffer is [H, Np, Lpad] fp32: conformer b owns padded rows
+ * cup[b] .. cup[b+1] (multiples of 128; m_tiles = Np / 128, tile_conf[t] = conformer of tile t), Lpad a multiple of 32
+ * >= the longest conformer.  pev_attn_gemm forms: 0 out = buffer = scale * A B^T (A, B packed [N, lda / ldb], operand
+ * columns a_col0 / b_col0 + h * hd); 1 out[N, ldo] (columns out_col0 + h * hd ..) = scale * P B with A = buffer;
+ * 2 out = scale * P^T B.  pev_attn_softmax: backward = 0: rows of S -> probabilities in place (zeros at padding), G
+ * (optional) = dropout-kept probabilities / (1 - p_drop); backward = 1: G (= dP) -> dS = P (dP - sum P dP) in place, the
+ * dropout mask re-derived from (seed, element index). */
+int pev_attn_gemm(int32_t form, const float* A, int64_t lda, int32_t a_col0, const float* B, int64_t ldb, int32_t b_col0,
+                  const int32_t* tile_conf, const int32_t* cu, const int32_t* cup, int32_t m_tiles, int32_t H, int32_t hd,
+                  int32_t Lpad, int64_t N, float scale, float* out, int64_t ldo, int32_t out_col0, void* stream);
+int pev_attn_softmax(int32_t backward, float* S, float* G, const int32_t* tile_conf, const int32_t* cu, const int32_t* cup,
+                     int32_t m_tiles, int32_t H, int32_t Lpad, float p_drop, uint32_t seed, void* stream);
+
 /* ---------------------------------------------------------------- ragged packed batches (csrc/data_kernels.cu)
  * Device-side replacement for the host centring + zero-padding of models/data.py (:166-172, :219-266): the packed rows of
  * B conformers (n / ca / c [T,3], mask [T], dih [T,6], labels [T] int64, emb [T,D] or NULL; conformer b = rows

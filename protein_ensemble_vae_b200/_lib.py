@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import c_uint32, POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 import torch
 
@@ -80,6 +80,8 @@ _PROTOS_TC = {
     "pev_node_wgrad_workspace_bytes": (c_int64, []),
     "pev_node_wgrad": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
     "pev_unpack_center": (c_int32, [_P] * 8 + [_I, _I, _I, _I] + [_P] * 8),
+    "pev_attn_gemm": (c_int32, [_I, _P, _L, _I, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _L, c_float, _P, _L, _I, _P]),
+    "pev_attn_softmax": (c_int32, [_I, _P, _P, _P, _P, _P, _I, _I, _I, c_float, c_uint32, _P]),
     "pev_linear": (c_int32, [_I, _P, _L, _I, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P]),
     "pev_linear_wgrad": (c_int32, [_I, _P, _L, _I, _P, _L, _L, c_float, _P, _P, _L, _P]),
     "pev_split_tf32": (c_int32, [_P, _I, _I, _I, _P, _P]),

@@ -24,10 +24,93 @@ def _dest(pk):
     return d
 
 
+NT, NN, TN = 0, 1, 2
+_COUNTER = [0]
+
+
+def _tables(pk):
+    """Padded-row bookkeeping of the score buffer: conformer b owns rows cup[b] .. cup[b+1] (multiples of 128)."""
+    t = pk.__dict__.get("_attn_tables")
+    if t is None:
+        dev = pk.cu.device
+        cup, conf = [0], []
+        for b, n in enumerate(pk.lengths):
+            tiles = (n + 127) // 128
+            conf += [b] * tiles
+            cup.append(cup[-1] + 128 * tiles)
+        t = pk._attn_tables = (torch.tensor(conf, dtype=torch.int32, device=dev), torch.tensor(cup, dtype=torch.int32, device=dev),
+                               len(conf), max(32, (pk.lmax + 31) // 32 * 32))
+    return t
+
+
+def _gemm(form, A, a_col0, Bm, b_col0, pk, H, hd, scale, out, out_col0=0):
+    from . import _lib
+    from ._lib import ptr, stream
+    tile_conf, cup, m_tiles, Lpad = _tables(pk)
+    _lib.lib().call("pev_attn_gemm", form, ptr(A), A.shape[-1], a_col0, ptr(Bm), Bm.shape[-1], b_col0, ptr(tile_conf), ptr(pk.cu),
+                    ptr(cup), m_tiles, H, hd, Lpad, pk.N, float(scale), ptr(out), out.shape[-1], out_col0, stream(out))
+
+
+def _softmax(backward, S, G, pk, H, p_drop, seed):
+    from . import _lib
+    from ._lib import ptr, stream
+    tile_conf, cup, m_tiles, Lpad = _tables(pk)
+    _lib.lib().call("pev_attn_softmax", int(backward), ptr(S), ptr(G), ptr(tile_conf), ptr(pk.cu), ptr(cup), m_tiles, H, Lpad,
+                    float(p_drop), int(seed), stream(S))
+
+
+class PackedSelfAttention(torch.autograd.Function):
+    """Multi-head self-attention of every conformer over its own rows on the tcgen05 kernels of ``csrc/attn_kernels.cu``
+    (``pev_attn_gemm`` / ``pev_attn_softmax``): scores, softmax (+ dropout), ``P V`` forward; ``dV``, ``dP``, softmax
+    backward, ``dQ``, ``dK`` backward.  The probabilities are kept for the backward pass (``[H, Np, Lpad]`` fp32)."""
+
+    @staticmethod
+    def forward(ctx, qkv, pk, nheads, p_drop):
+        qkv = qkv.float().contiguous()
+        N, d3 = qkv.shape
+        d = d3 // 3
+        hd = d // nheads
+        _, _, m_tiles, Lpad = _tables(pk)
+        _COUNTER[0] += 1
+        seed = (torch.initial_seed() * 2654435761 + _COUNTER[0] * 40503) & 0xFFFFFFFF
+        with torch.cuda.device_of(qkv):
+            P = torch.empty(nheads, m_tiles * 128, Lpad, dtype=torch.float32, device=qkv.device)
+            _gemm(NT, qkv, 0, qkv, d, pk, nheads, hd, 1.0 / math.sqrt(hd), P)
+            Pd = torch.empty_like(P) if p_drop > 0 else None
+            _softmax(0, P, Pd, pk, nheads, p_drop, seed)
+            out = torch.empty(N, d, dtype=torch.float32, device=qkv.device)
+            _gemm(NN, Pd if Pd is not None else P, 0, qkv, 2 * d, pk, nheads, hd, 1.0, out)
+        ctx.pk, ctx.nheads, ctx.p_drop, ctx.seed = pk, nheads, p_drop, seed
+        ctx.save_for_backward(qkv, P, Pd)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        qkv, P, Pd = ctx.saved_tensors
+        pk, H = ctx.pk, ctx.nheads
+        go = go.float().contiguous()
+        N, d3 = qkv.shape
+        d = d3 // 3
+        hd = d // H
+        sc = 1.0 / math.sqrt(hd)
+        with torch.cuda.device_of(qkv):
+            gqkv = torch.empty_like(qkv)
+            _gemm(TN, Pd if Pd is not None else P, 0, go, 0, pk, H, hd, 1.0, gqkv, 2 * d)          # dV = P^T dO
+            G = torch.empty_like(P)
+            _gemm(NT, go, 0, qkv, 2 * d, pk, H, hd, 1.0, G)                                        # dP = dO V^T
+            _softmax(1, P, G, pk, H, ctx.p_drop, ctx.seed)                                         # G := dS
+            _gemm(NN, G, 0, qkv, d, pk, H, hd, sc, gqkv, 0)                                        # dQ = scale dS K
+            _gemm(TN, G, 0, qkv, 0, pk, H, hd, sc, gqkv, d)                                        # dK = scale dS^T Q
+        return gqkv, None, None, None
+
+
 def self_attention(qkv, pk, nheads: int, dropout_p: float = 0.0, precise: bool = False):
     """``qkv [N, 3d]`` (packed rows, ``[q | k | v]``) -> attention output ``[N, d]`` (heads concatenated, before the output
-    projection)."""
+    projection).  TF32 path: the repo's own tensor-core kernels (:class:`PackedSelfAttention`); the exact path
+    (``precise``) evaluates the same attention in plain fp32 through torch's scaled_dot_product_attention."""
     N, d3 = qkv.shape
+    if not precise and qkv.is_cuda and (d3 // 3) // nheads in (64, 128) and N > 0:
+        return PackedSelfAttention.apply(qkv, pk, nheads, float(dropout_p))
     d = d3 // 3
     hd = d // nheads
     B, lmax = pk.B, pk.lmax
