@@ -109,7 +109,7 @@ def self_attention(qkv, pk, nheads: int, dropout_p: float = 0.0, precise: bool =
     projection).  TF32 path: the repo's own tensor-core kernels (:class:`PackedSelfAttention`); the exact path
     (``precise``) evaluates the same attention in plain fp32 through torch's scaled_dot_product_attention."""
     N, d3 = qkv.shape
-    if not precise and qkv.is_cuda and (d3 // 3) // nheads in (64, 128) and N > 0:
+    if not precise and PackedSelfAttention is not None and qkv.is_cuda and (d3 // 3) // nheads in (64, 128) and N > 0:
         return PackedSelfAttention.apply(qkv, pk, nheads, float(dropout_p))
     d = d3 // 3
     hd = d // nheads

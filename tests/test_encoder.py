@@ -44,8 +44,25 @@ def test_encoder_state_dict_keys_match_reference_layout():
         enc(torch.zeros(1, 4, 1280), z, z, z, torch.zeros(1, 4, 6), torch.ones(1, 4))    # CUDA only, no CPU fallback
 
 
-def _run(tag, precision):
+def _run(tag, precision, yardstick=False):
+    """``yardstick``: the same module with every linear / attention on torch's library kernels with TF32 allowed -- what an
+    ideal single-pass TF32 implementation gives against the float64 reference (gradients through the ReLUs and LayerNorms of
+    the encoder are ill-conditioned, as in the decoder heads: tests/bf16_yardstick.py)."""
     import test_gpu_parity_big as tb
+    from protein_ensemble_vae_b200 import attention, tc_linear
+    if yardstick:
+        saved = (tc_linear.supported, attention.PackedSelfAttention, torch.backends.cuda.matmul.allow_tf32)
+        tc_linear.supported = lambda x, W: False
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            attention.PackedSelfAttention = None
+            return _run_inner(tag, "fp32", tb)                         # "fp32" selects the torch attention path
+        finally:
+            tc_linear.supported, attention.PackedSelfAttention, torch.backends.cuda.matmul.allow_tf32 = saved
+    return _run_inner(tag, precision, tb)
+
+
+def _run_inner(tag, precision, tb):
     case = cases.ENCODER_CASES[tag]
     enc, shapes = _shapes(case[0], case[1])
     enc.enc.precision = enc.latent.precision = precision
@@ -65,9 +82,13 @@ def _run(tag, precision):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-5, 1e-4), ("tf32", 3e-3, 2e-2)])
+@pytest.mark.parametrize("precision,tol_out", [("fp32", 1e-5), ("tf32", 3e-3)])
 @pytest.mark.parametrize("tag", list(cases.ENCODER_CASES))
-def test_encoder_matches_reference(tag, precision, tol_out, tol_grad):
+def test_encoder_matches_reference(tag, precision, tol_out):
+    """fp32 path (3xTF32 linears): outputs 1e-5, parameter gradients 1e-4.  TF32 path (own GEMM + attention kernels):
+    outputs 3e-3; gradients within 3x of the library-TF32 yardstick (worst and median over parameters; measured: mine
+    worst 0.10 - 0.35 / median 0.03, yardstick worst 0.15 - 0.20 / median 0.014 - 0.026: single-pass TF32 flips ~1e-4 of the
+    ReLU units of the feed-forward blocks, which moves weight gradients by percents whoever does the rounding)."""
     gold = np.load(os.path.join(G, "encoders.npz"))
     mask, res, (z_g, z_l), grads, tb = _run(tag, precision)
     mb = torch.tensor(mask.astype(bool))
@@ -75,13 +96,19 @@ def test_encoder_matches_reference(tag, precision, tol_out, tol_grad):
     for name, r in zip(("mu_g", "lv_g", "mu_l", "lv_l"), res):
         got, ref = r.detach().cpu().double(), torch.tensor(gold[f"{tag}.{name}"])
         if got.dim() == 3:
-            assert float(got[~mb].abs().max()) == 0.0 if (~mb).any() else True          # exact zeros at padding
+            assert (not (~mb).any()) or float(got[~mb].abs().max()) == 0.0              # exact zeros at padding
             got, ref = got[mb], ref[mb]
         errs[name] = rel_err(got, ref)
     assert max(errs.values()) < tol_out, errs
     assert torch.equal(z_g, res[0]) and torch.equal(z_l, res[2])                          # eps = 0: z = mu
     gerrs = tb._grad_errors(grads, gold, tag)
     assert {k.split(".", 2)[2] for k in gold.files if k.startswith(tag + ".g")} == set(gerrs)
-    worst = max(gerrs.items(), key=lambda kv: kv[1][1])
-    assert worst[1][1] < tol_grad, (worst, errs)
-    print(tag, precision, "outputs", {k: f"{v:.1e}" for k, v in errs.items()}, "worst grad (max, l2)", worst)
+    l2 = sorted(v[1] for v in gerrs.values())
+    worst, median = l2[-1], l2[len(l2) // 2]
+    if precision == "fp32":
+        assert worst < 1e-4, max(gerrs.items(), key=lambda kv: kv[1][1])
+    else:
+        yard = sorted(v[1] for v in tb._grad_errors(_run(tag, precision, yardstick=True)[3], gold, tag).values())
+        assert worst < max(2e-2, 3.0 * yard[-1]) and median < max(1e-2, 3.0 * yard[len(yard) // 2]), (worst, median, yard[-1])
+        print(tag, "yardstick worst %.1e median %.1e" % (yard[-1], yard[len(yard) // 2]))
+    print(tag, precision, "outputs", {k: f"{v:.1e}" for k, v in errs.items()}, "grad l2 worst %.1e median %.1e" % (worst, median))
