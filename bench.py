@@ -819,10 +819,110 @@ def run_stress(ctx, args):
         print(json.dumps(out), flush=True)
 
 
+def run_vae(ctx, args):
+    """The whole HierCVAE training step (models/model.py:60-68 + models/training.py:89-102) at configs[1] sizes: encoder
+    (TF32 tensor-core linears + attention kernels) -> decoder (bf16 edge MLP) -> compute_total_loss -> backward -> Adam on all
+    20.4 M parameters.  SURVEY.md 8(f) N1; not the headline metric (BASELINE's is the decoder + loss step)."""
+    from protein_ensemble_vae_b200 import DevicePrefetcher, EGNNDecoder, compute_total_loss
+    from protein_ensemble_vae_b200 import losses as pl
+    from protein_ensemble_vae_b200.encoder import ProteinEncoder
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    B, L, SD = CFG["batch_per_gpu"], CFG["L"], 1280
+    torch.manual_seed(0)
+    enc = ProteinEncoder(SD, z_g=CFG["z_g"], z_l=CFG["z_l"], dropout=CFG["dropout"]).to(dev).train()
+    dec = EGNNDecoder(CFG["z_g"], CFG["z_l"], hidden_dim=CFG["hidden"], num_layers=CFG["layers"],
+                      max_neighbors=CFG["max_neighbors"], dropout=CFG["dropout"], precision="bf16").to(dev).train()
+    host = synth_batch(B, L, CFG["z_g"], CFG["z_l"], seed=rank, pin=True)
+    for k in ("z_g", "z_l", "mu_g", "lv_g", "mu_l", "lv_l"):
+        host.pop(k)                                             # the encoder produces them
+    g = torch.Generator().manual_seed(1000 + rank)
+    host["seq_emb"] = torch.randn(B, L, SD, generator=g).pin_memory()
+    resident = {k: v.to(dev) for k, v in host.items()}
+    params = list(enc.parameters()) + list(dec.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    if world > 1:
+        from protein_ensemble_vae_b200 import distributed as pdist
+
+    def step(d):
+        tdih = pl.compute_dihedrals_from_coords(d["target_N"], d["target_CA"], d["target_C"], d["mask"])
+        z_g, z_l, mu_g, lv_g, mu_l, lv_l = enc(d["seq_emb"], d["target_N"], d["target_CA"], d["target_C"], tdih, d["mask"])
+        outs = dec(z_g, z_l, d["mask"])
+        res = compute_total_loss(outs[0], outs[1], outs[2], outs[3], d["target_N"], d["target_CA"], d["target_C"],
+                                 d["labels"], d["mask"], mu_g, lv_g, mu_l, lv_l, tdih, **LOSS_W)
+        res["total"].backward()
+        if world > 1:
+            pdist.allreduce_gradients(params)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return res["total"].detach()
+
+    sampler = ClockSampler(ctx.local)
+    if rank == 0 and not os.environ.get("PEV_BENCH_NO_CLOCKS"):
+        sampler.start()
+    for _ in range(args.warmup):
+        step(resident)
+    torch.cuda.synchronize()
+    sampler.mark_start()
+    from protein_ensemble_vae_b200 import _lib
+    n0 = _lib.lib().launch_count()
+    ms = ctx.timed(lambda: step(resident), args.steps)
+    launches = _lib.lib().launch_count() - n0
+    sampler.mark_stop()
+    tdih = pl.compute_dihedrals_from_coords(resident["target_N"], resident["target_CA"], resident["target_C"], resident["mask"])
+    enc_ms = [0.0, 0.0]
+    for it in range(4):                                         # encoder alone, forward / backward (first pass = warm-up)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        lat = enc(resident["seq_emb"], resident["target_N"], resident["target_CA"], resident["target_C"], tdih, resident["mask"])
+        ev[1].record()
+        (lat[0].square().mean() + lat[1].square().mean() + lat[3].mean() + lat[5].mean()).backward()
+        ev[2].record()
+        torch.cuda.synchronize()
+        enc.zero_grad(set_to_none=True)
+        if it:
+            enc_ms[0] += ev[0].elapsed_time(ev[1]) / 3
+            enc_ms[1] += ev[1].elapsed_time(ev[2]) / 3
+    del lat
+
+    def e2e_steps(k):
+        for d in DevicePrefetcher((host for _ in range(k)), dev):
+            float(step(d))
+    e2e_steps(2)
+    ms_e2e = ctx.timed(lambda: e2e_steps(args.steps), 1)
+    if rank == 0:
+        _, tf, which = peaks()
+        N = B * L
+        # encoder GEMM flops per residue (forward): seq_proj, fusion, 7 x (QKV + out), 6 x feed-forward, K / V of the pooling,
+        # local head; attention 4 L d per residue and attention layer
+        lin = 2 * (SD * 256 + 512 * 512 + 7 * (512 * 1536 + 512 * 512) + 6 * 2 * 512 * 1024 + 512 * 1024 + 512 * 256 + 256 * 512)
+        enc_flops = 3.0 * N * (lin + 7 * 4 * L * 512)
+        dec_flops = flops_per_conformer(L, CFG["layers"]) * B
+        step_tf = (enc_flops + dec_flops) / (ms / args.steps * 1e-3) / 1e12
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        out = {"metric": "train_conformers_per_s", "value": B * world * args.steps / (ms / 1e3), "unit": "conformers/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 edge MLP / tf32 encoder",
+               "data": "synthetic",
+               "config": {"workload": f"whole HierCVAE step: ProteinEncoder (6 transformer layers, d_model 512, ESM width {SD}) "
+                                      f"+ EGNNDecoder (6 layers) + compute_total_loss + Adam, L={L}, {B} conformers per GPU",
+                          "L": L, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                          "cache": "inputs_larger_than_l2 (335 MB of sequence embeddings per step)"},
+               "clocks": sampler.summary(),
+               "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "conformers/s",
+                       "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches),
+               "encoder": {"forward_ms": enc_ms[0], "backward_ms": enc_ms[1], "algorithmic_tflop": enc_flops / 1e12,
+                           "tensor_frac": enc_flops / ((enc_ms[0] + enc_ms[1]) * 1e-3) / 1e12 / tf},
+               "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": step_tf, "peak": tf, "unit": "TFLOP/s",
+                            "frac": step_tf / tf, "traffic": None, "peak_source": which},
+               "cpu_baseline": None}
+        print(json.dumps(out), flush=True)
+
+
 def run_gpu(args):
     ctx = Ctx()
     try:
-        {"train": run_train, "decode": run_decode, "mixed": run_mixed, "stress": run_stress}[args.config](ctx, args)
+        {"train": run_train, "decode": run_decode, "mixed": run_mixed, "stress": run_stress, "vae": run_vae}[args.config](ctx, args)
     finally:
         ctx.close()
 
@@ -833,8 +933,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="train", choices=["train", "decode", "mixed", "stress"],
-                    help="train = BASELINE configs[1] (the headline); decode / mixed / stress = configs[3] / [2] / [4]")
+    ap.add_argument("--config", default="train", choices=["train", "decode", "mixed", "stress", "vae"],
+                    help="train = BASELINE configs[1] (the headline); decode / mixed / stress = configs[3] / [2] / [4]; "
+                         "vae = encoder + decoder + loss (SURVEY.md 8f N1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--train-only", action="store_true",
                     help="profiling runs: only the timed training steps (no e2e / decode / per-kernel side measurements)")

@@ -270,7 +270,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {      // counter-based dr
   return x;
 }
 __device__ __forceinline__ bool keep_bit(uint32_t seed, int64_t idx, uint32_t thresh) {
-  return mix32(seed ^ mix32((uint32_t)idx) ^ (uint32_t)(idx >> 32) * 0x9e3779b9U) >= thresh;
+  if (thresh == 0u) return true;                             // no dropout: no hashing (the row kernels are issue-bound on it)
+  return mix32(seed + (uint32_t)idx * 0x9e3779b9U + (uint32_t)(idx >> 32)) >= thresh;
 }
 
 // One warp per (head, padded row): softmax over the keys of the row's conformer, zeros elsewhere; with dropout the kept and
@@ -295,6 +296,40 @@ softmax_fwd_kernel(float* __restrict__ S, float* __restrict__ Pd, const int32_t*
     }
     return;
   }
+  const uint32_t thresh = p_drop > 0.f ? (uint32_t)(p_drop * 4294967296.0) : 0u;
+  const float keep_scale = 1.0f / (1.0f - p_drop);
+  if (Lpad <= 512) {
+    // the row lives in registers (16 values per lane): one read and one write of the score buffer
+    float v[16];
+    float mx = -INFINITY;
+    const int nk = Lpad >> 5;                    // live 32-column groups (uniform)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = lane + 32 * k;
+      v[k] = (k < nk && j < Lb) ? s[j] : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < nk) {
+        v[k] = __expf(v[k] - mx);                // exp(-inf) = 0 past the conformer's length
+        sum += v[k];
+      }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = lane + 32 * k;
+      if (k < nk) {
+        const float pj = v[k] * inv;
+        s[j] = pj;
+        if (pd) pd[j] = keep_bit(seed, row * Lpad + j, thresh) ? pj * keep_scale : 0.f;
+      }
+    }
+    return;
+  }
   float mx = -INFINITY;
   for (int j = lane; j < Lb; j += 32) mx = fmaxf(mx, s[j]);
   mx = warp_max(mx);
@@ -302,8 +337,6 @@ softmax_fwd_kernel(float* __restrict__ S, float* __restrict__ Pd, const int32_t*
   for (int j = lane; j < Lb; j += 32) sum += __expf(s[j] - mx);
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-  const uint32_t thresh = p_drop > 0.f ? (uint32_t)(p_drop * 4294967296.0) : 0u;
-  const float keep_scale = 1.0f / (1.0f - p_drop);
   for (int j = lane; j < Lpad; j += 32) {
     const float pj = j < Lb ? __expf(s[j] - mx) * inv : 0.f;
     s[j] = pj;
@@ -331,6 +364,29 @@ softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ G, const int
   }
   const uint32_t thresh = p_drop > 0.f ? (uint32_t)(p_drop * 4294967296.0) : 0u;
   const float keep_scale = 1.0f / (1.0f - p_drop);
+  if (Lpad <= 512) {
+    float pv[16], gv[16];
+    float dot = 0.f;
+    const int nk = Lpad >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = lane + 32 * k;
+      const bool live = k < nk && j < Lb;
+      pv[k] = live ? pr[j] : 0.f;
+      gv[k] = live ? g[j] : 0.f;                 // both loads issued before any hashing
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < nk) {
+        gv[k] = keep_bit(seed, row * Lpad + lane + 32 * k, thresh) ? gv[k] * keep_scale : 0.f;
+        dot = fmaf(pv[k], gv[k], dot);
+      }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < nk) g[lane + 32 * k] = pv[k] * (gv[k] - dot);
+    return;
+  }
   float dot = 0.f;
   for (int j = lane; j < Lb; j += 32) {
     const float gj = keep_bit(seed, row * Lpad + j, thresh) ? g[j] * keep_scale : 0.f;

@@ -405,6 +405,7 @@ constexpr int W_THREADS = 32 * 6;                       // 0..3 flush, 4 TMA, 5 
 
 struct WParams {
   int64_t N;
+  int nblk_x;             // 256-column blocks of X handled by this launch (0 = 1): block id = bg * nblk_x + bx
   int nblk;               // Mo / 256
   int rows_per_slice;     // multiple of WK
   float* partial;         // [slices][nblk][256*256]
@@ -420,7 +421,9 @@ node_wgrad_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, con
   uint64_t* done = bars + 2 * W_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int blk = blockIdx.x % p.nblk, slice = blockIdx.x / p.nblk;
+  const int nbx = p.nblk_x > 0 ? p.nblk_x : 1, nball = p.nblk * nbx;
+  const int blk = blockIdx.x % nball, slice = blockIdx.x / nball;
+  const int bg = blk / nbx, bxo = (blk % nbx) * 256;
   const int64_t r0 = (int64_t)slice * p.rows_per_slice;
   int64_t r1 = r0 + p.rows_per_slice;
   if (r1 > p.N) r1 = p.N;
@@ -450,8 +453,8 @@ node_wgrad_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, con
         const int row = (int)(r0 + (int64_t)c * WK);
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          tma_load_2d(dst + b * W_BOX, &mapG, blk * 256 + 32 * b, row, &full[stage]);
-          tma_load_2d(dst + W_OP + b * W_BOX, &mapX, 32 * b, row, &full[stage]);
+          tma_load_2d(dst + b * W_BOX, &mapG, bg * 256 + 32 * b, row, &full[stage]);
+          tma_load_2d(dst + W_OP + b * W_BOX, &mapX, bxo + 32 * b, row, &full[stage]);
         }
         if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -484,7 +487,7 @@ node_wgrad_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, con
     // flush: TMEM -> this CTA's partial block (lane = output row)
     mbar_wait(done, 0);
     tc_fence_after();
-    float* dst = p.partial + ((int64_t)slice * p.nblk + blk) * 65536;
+    float* dst = p.partial + ((int64_t)slice * nball + blk) * 65536;
 #pragma unroll 1
     for (int mh = 0; mh < 2; ++mh) {
       float* drow = dst + (int64_t)(mh * 128 + warp * 32 + lane) * 256;
@@ -755,7 +758,9 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
   uint64_t* flushed = done + 1;                    // flush warps -> MMA: TMEM may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(flushed + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int blk = blockIdx.x % p.nblk, slice = blockIdx.x / p.nblk;
+  const int nbx = p.nblk_x > 0 ? p.nblk_x : 1, nball = p.nblk * nbx;
+  const int blk = blockIdx.x % nball, slice = blockIdx.x / nball;
+  const int bg = blk / nbx, bxo = (blk % nbx) * 256;
   const int64_t r0 = (int64_t)slice * p.rows_per_slice;
   int64_t r1 = r0 + p.rows_per_slice;
   if (r1 > p.N) r1 = p.N;
@@ -788,8 +793,8 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
         const int row = (int)(r0 + (int64_t)c * w3::WK);
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          tma_load_2d(dst + b * w3::BOX, &mapG, blk * 256 + 32 * b, row, &full[stage]);
-          tma_load_2d(dst + w3::OP + b * w3::BOX, &mapX, 32 * b, row, &full[stage]);
+          tma_load_2d(dst + b * w3::BOX, &mapG, bg * 256 + 32 * b, row, &full[stage]);
+          tma_load_2d(dst + w3::OP + b * w3::BOX, &mapX, bxo + 32 * b, row, &full[stage]);
         }
         if (++stage == w3::STAGES) { stage = 0; phase ^= 1; }
       }
@@ -840,7 +845,7 @@ node_wgrad3_kernel(const WParams p, const __grid_constant__ CUtensorMap mapG, co
     }
   } else {
     // flush: after every sub-slice TMEM is ADDED (fp32, round to nearest) into this CTA's partial block, lane = output row
-    float* dst = p.partial + ((int64_t)slice * p.nblk + blk) * 65536;
+    float* dst = p.partial + ((int64_t)slice * nball + blk) * 65536;
     for (int ss = 0; ss < (subs > 0 ? subs : 1); ++ss) {
       if (chunks > 0) {
         mbar_wait(done, ss & 1);
@@ -899,6 +904,24 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int rows, int c
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
     out[(int64_t)R * C + i] = __uint_as_float(l);
   }
+}
+
+// out block (bg, bx) [256 x 256] (leading dimension ldc) = scale * sum over slices (fixed order) of the per-CTA partials
+__global__ void __launch_bounds__(256)
+wgrad_blocks_reduce_kernel(const float* __restrict__ partial, int slices, int nball, int nbx, float scale, float* __restrict__ out,
+                           int64_t ldc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nball * 16384) return;
+  const int blk = (int)(idx >> 14), e = (int)(idx & 16383);
+  const float4* src = reinterpret_cast<const float4*>(partial) + (int64_t)blk * 16384 + e;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < slices; ++s) {
+    const float4 v = src[(int64_t)s * nball * 16384];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int r = e >> 6, c4 = e & 63;
+  float* dst = out + ((int64_t)(blk / nbx) * 256 + r) * ldc + (blk % nbx) * 256 + 4 * c4;
+  *reinterpret_cast<float4*>(dst) = make_float4(scale * acc.x, scale * acc.y, scale * acc.z, scale * acc.w);
 }
 
 }  // namespace ng
@@ -1085,16 +1108,18 @@ extern "C" int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t 
   return after_launch("node_gemm3_kernel");
 }
 
-// Weight-gradient block: out[Mo, 256] (leading dimension ldc) = scale * G^T X, G [N, Mo] (leading dimension ldg, Mo = 256 or
-// 512), X [N, 256] (leading dimension ldx): column blocks of wider activations without copies.
-extern "C" int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int64_t N,
-                                float scale, float* workspace, float* out, int64_t ldc, void* stream) {
-  PEV_REQUIRE(G && X && out && workspace && N >= 0 && (Mo == 256 || Mo == 512) && ldc >= 256 && ldg >= Mo && ldx >= 256 &&
-              ldg % 4 == 0 && ldx % 4 == 0, "bad argument");
+// Weight gradient of a linear layer in ONE launch: out[Mo, Kx] (leading dimension ldc) = scale * G^T X for G [N, Mo] (ldg) and
+// X [N, Kx] (ldx), Mo and Kx multiples of 256: every 256 x 256 output block gets sm_count / blocks row slices, all blocks run
+// concurrently (the CTAs that share a row slice of G or X meet in L2: HBM sees each operand once), one fixed-order reduction.
+extern "C" int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int32_t Kx,
+                                int64_t N, float scale, float* workspace, float* out, int64_t ldc, void* stream) {
+  PEV_REQUIRE(G && X && out && workspace && N >= 0 && Mo > 0 && Mo % 256 == 0 && Kx > 0 && Kx % 256 == 0 && ldc >= Kx &&
+              ldg >= Mo && ldx >= Kx && ldg % 4 == 0 && ldx % 4 == 0 && ldc % 4 == 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  const int nblk = Mo / 256;
+  const int nbg = Mo / 256, nbx = Kx / 256, nball = nbg * nbx;
+  PEV_REQUIRE(nball <= sm_count(), "too many output blocks for one launch");
   if (N == 0) {
-    for (int r = 0; r < Mo; ++r) cudaMemsetAsync(out + (int64_t)r * ldc, 0, sizeof(float) * 256, st);
+    for (int r = 0; r < Mo; ++r) cudaMemsetAsync(out + (int64_t)r * ldc, 0, sizeof(float) * Kx, st);
     return 0;
   }
   static bool configured_dev[kMaxDevices] = {};
@@ -1106,21 +1131,19 @@ extern "C" int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, in
     configured = true;
   }
   const int wk = precise ? ng::w3::WK : ng::WK;
-  int slices = sm_count() / nblk;
+  int slices = sm_count() / nball;
   const int64_t chunks = (N + wk - 1) / wk;
   if (slices > chunks) slices = (int)chunks;
   ng::WParams p = {};
-  p.N = N; p.nblk = nblk; p.partial = workspace;
+  p.N = N; p.nblk = nbg; p.nblk_x = nbx; p.partial = workspace;
   p.rows_per_slice = (int)(((chunks + slices - 1) / slices) * wk);
   slices = (int)((N + p.rows_per_slice - 1) / p.rows_per_slice);
   alignas(64) CUtensorMap mG, mX;
   if (int rc = ng::make_f32_map(G, N, Mo, ldg, wk, &mG, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (int rc = ng::make_f32_map(X, N, 256, ldx, wk, &mX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (precise) ng::node_wgrad3_kernel<<<slices * nblk, ng::w3::THREADS, ng::w3::SMEM, st>>>(p, mG, mX);
-  else ng::node_wgrad_kernel<<<slices * nblk, ng::W_THREADS, ng::W_SMEM, st>>>(p, mG, mX);
+  if (int rc = ng::make_f32_map(X, N, Kx, ldx, wk, &mX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (precise) ng::node_wgrad3_kernel<<<slices * nball, ng::w3::THREADS, ng::w3::SMEM, st>>>(p, mG, mX);
+  else ng::node_wgrad_kernel<<<slices * nball, ng::W_THREADS, ng::W_SMEM, st>>>(p, mG, mX);
   if (int rc = after_launch("node_wgrad_kernel")) return rc;
-  for (int b = 0; b < nblk; ++b)
-    if (int rc = launch_partial_reduce_2d(workspace + (int64_t)b * 65536, slices, (int64_t)nblk * 65536, 256, 256, scale,
-                                          out + (int64_t)b * 256 * ldc, (int)ldc, st)) return rc;
-  return 0;
+  ng::wgrad_blocks_reduce_kernel<<<(nball * 16384 + 255) / 256, 256, 0, st>>>(workspace, slices, nball, nbx, scale, out, ldc);
+  return after_launch("wgrad_blocks_reduce_kernel");
 }

@@ -43,7 +43,7 @@ def linear_fwd(x, W, bias=None, relu=False, res=None, precise=False, out=None):
 
 
 def linear_wgrad(g, x, precise=False):
-    """``g^T x`` (``[Nout,K]``) in 256-column blocks of ``x`` and <= 512-column blocks of ``g``."""
+    """``g^T x`` (``[Nout,K]``): every 256 x 256 block of the result in one launch (``pev_linear_wgrad``)."""
     g, x = _rows(g), _rows(x)
     N, Nout = g.shape
     K = x.shape[1]
@@ -54,11 +54,8 @@ def linear_wgrad(g, x, precise=False):
             ws = _WGRAD_WS[dev] = torch.empty(_lib.lib().cdll.pev_node_wgrad_workspace_bytes() // 4, dtype=torch.float32,
                                               device=dev)
         gW = torch.empty(Nout, K, dtype=torch.float32, device=dev)
-        for n0 in range(0, Nout, 512):
-            Mo = min(512, Nout - n0)
-            for k0 in range(0, K, 256):
-                _lib.lib().call("pev_linear_wgrad", int(precise), _p(g[:, n0:]), g.stride(0), Mo, _p(x[:, k0:]), x.stride(0),
-                                N, 1.0, _p(ws), _p(gW[n0:, k0:]), K, stream(g))
+        _lib.lib().call("pev_linear_wgrad", int(precise), _p(g), g.stride(0), Nout, _p(x), x.stride(0), K, N, 1.0, _p(ws),
+                        _p(gW), K, stream(g))
     return gW
 
 
