@@ -341,6 +341,9 @@ class Linear3x(torch.autograd.Function):
 def apply_tf32(module, x, fp32_forward=False):
     """Run an ``nn.Linear`` / ``nn.Sequential`` of the decoder with its linears on :class:`NodeLinear` (bf16 path)."""
     if isinstance(module, nn.Linear):
+        from . import tc_linear
+        if not fp32_forward and module.bias is not None and tc_linear.supported(x, module.weight):
+            return tc_linear.linear(x, module.weight, module.bias)       # own tcgen05 TF32 GEMMs (256-multiple widths)
         return NodeLinear.apply(x, module.weight, module.bias, fp32_forward)
     if isinstance(module, nn.Sequential):
         for m in module:
