@@ -62,7 +62,23 @@ struct Params {
   int64_t ldc;            // PLAIN (and the 3xTF32 kernel): leading dimensions of out / res; 0 = Nout
   int64_t ldres;
   int relu;               // PLAIN: out = max(., 0)
+  uint32_t drop_thresh;   // PLAIN: dropout on (C + bias [relu]) BEFORE the residual is added: keep iff hash(seed, row * Nout + col) >= thresh
+  uint32_t drop_seed;
+  float drop_scale;       // 1 / (1 - p)
 };
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {      // the counter hash of pev_mask_grad / attn_kernels.cu
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// keep iff hash(seed, element index mod 2^32) >= thresh; `base` = (row * Nout + first column of the block) * golden ratio,
+// hoisted out of the per-element loop (32-bit arithmetic: this sits in an issue-bound epilogue)
+__device__ __forceinline__ uint32_t drop_base(const Params& p, int64_t row, int col0) {
+  return p.drop_seed + ((uint32_t)row * (uint32_t)p.Nout + (uint32_t)col0) * 0x9e3779b9U;
+}
+__device__ __forceinline__ float drop_elem(const Params& p, float v, uint32_t base, int j) {
+  return mix32(base + (uint32_t)j * 0x9e3779b9U) >= p.drop_thresh ? v * p.drop_scale : 0.f;
+}
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -303,6 +319,7 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
             }
           } else {
             if (EPI == EPI_SILU && p.out2) store_block32(stg, val, p.out2 + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
+            const uint32_t dbase = EPI == EPI_PLAIN ? drop_base(p, row, c0) : 0u;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float v = val[j];
@@ -311,8 +328,9 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
                 const float pz = aux[j], sg = 1.0f / (1.0f + __expf(-pz));
                 val[j] = v * sg * (1.0f + pz * (1.0f - sg));
               } else {
-                if (p.res) val[j] = v + aux[j];
-                if (p.relu) val[j] = fmaxf(val[j], 0.f);
+                float o = p.relu ? fmaxf(v, 0.f) : v;
+                if (p.drop_thresh) o = drop_elem(p, o, dbase, j);
+                val[j] = p.res ? o + aux[j] : o;
               }
             }
             if (EPI == EPI_PLAIN) store_block32(stg, val, p.out + wrow0 * ldc + c0, ldc, rows_valid, lane);
@@ -682,15 +700,18 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
         const int c0 = n0 + hh * 64 + 32 * b;
         uint32_t raw[32];
         tmem_ld32_issue(taddr + 2 * x3::BN3 + 32 * b, raw);              // small products first
-        float val[32];
+        float val[32], rsd[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          val[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+          rsd[j] = 0.f;
+        }
         if (p.res) {
           const float* arow = p.res + (valid ? row : 0) * (p.ldres ? p.ldres : (int64_t)p.Nout) + c0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 v = *reinterpret_cast<const float4*>(arow + 4 * j4);
-            val[4 * j4] += v.x; val[4 * j4 + 1] += v.y; val[4 * j4 + 2] += v.z; val[4 * j4 + 3] += v.w;
+            rsd[4 * j4] = v.x; rsd[4 * j4 + 1] = v.y; rsd[4 * j4 + 2] = v.z; rsd[4 * j4 + 3] = v.w;
           }
         }
         tmem_wait();
@@ -710,10 +731,13 @@ node_gemm3_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, cons
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty);
         }
+        const uint32_t dbase = drop_base(p, row, c0);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          val[j] += acc[j] + __uint_as_float(raw[j]);
-          if (p.relu) val[j] = fmaxf(val[j], 0.f);
+          float o = val[j] + (acc[j] + __uint_as_float(raw[j]));
+          if (p.relu) o = fmaxf(o, 0.f);
+          if (p.drop_thresh) o = drop_elem(p, o, dbase, j);
+          val[j] = o + rsd[j];
         }
         {
           const int64_t ldc = p.ldc ? p.ldc : (int64_t)p.Nout;
@@ -1083,7 +1107,9 @@ extern "C" int pev_node_wgrad3(const float* G, int32_t Mo, const float* X, int64
 // A / res with leading dimensions lda / ldres; precise = 0: TF32 (W fp32 [Nout,K], Nout a multiple of 256), precise = 1:
 // 3xTF32 (W = split image [2 Nout, K], Nout a multiple of 128).
 extern "C" int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t K, const float* W, const float* bias, int64_t M,
-                          int32_t Nout, int32_t relu, const float* res, int64_t ldres, float* out, int64_t ldc, void* stream) {
+                          int32_t Nout, int32_t relu, float p_drop, uint32_t seed, const float* res, int64_t ldres, float* out,
+                          int64_t ldc, void* stream) {
+  PEV_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "p_drop in [0, 1)");
   PEV_REQUIRE(A && W && out && M >= 0 && K > 0 && K % 32 == 0 && lda >= K && ldc >= Nout && (!res || ldres >= Nout), "bad argument");
   PEV_REQUIRE(Nout > 0 && Nout % (precise ? 128 : 256) == 0, "Nout: a multiple of 256 (TF32) / 128 (3xTF32)");
   PEV_REQUIRE(lda % 4 == 0 && ldc % 4 == 0 && (!res || ldres % 4 == 0), "leading dimensions: multiples of 4 floats");
@@ -1091,6 +1117,9 @@ extern "C" int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t 
   cudaStream_t st = as_stream(stream);
   ng::Params p = {};
   p.M = M; p.Nout = Nout; p.k1_chunks = K / 32; p.bias = bias; p.res = res; p.out = out; p.ldc = ldc; p.ldres = ldres; p.relu = relu;
+  p.drop_thresh = p_drop > 0.f ? (uint32_t)(p_drop * 4294967296.0) : 0u;
+  p.drop_seed = seed;
+  p.drop_scale = 1.0f / (1.0f - p_drop);
   if (!precise) return ng::launch<ng::EPI_PLAIN>(p, A, K, nullptr, 0, W, st, lda);
   static bool configured_dev[kMaxDevices] = {};
   bool& configured = configured_dev[current_device()];

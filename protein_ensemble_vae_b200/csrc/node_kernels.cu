@@ -7,7 +7,7 @@
 
 namespace pev {
 
-template <int D>   // D = 256 or 512: D / 128 float4 per lane
+template <int D>   // D = 128, 256 or 512: D / 128 float4 per lane
 __global__ void __launch_bounds__(256)
 add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float eps, int64_t N, float* __restrict__ r_out,
@@ -147,19 +147,54 @@ static int rows_grid(int64_t N) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// Backward of the dropout / ReLU epilogues of pev_linear: out = keep(seed, element) && (y == null || y != 0) ? g * scale : 0
+// (the dropout mask is the counter hash the forward epilogue used; ReLU zeros are read off the stored output y)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+mask_grad_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t n4, float scale, uint32_t thresh, uint32_t seed,
+                 float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(g)[i];
+    float4 yy = y ? reinterpret_cast<const float4*>(y)[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+    float r[4] = {v.x, v.y, v.z, v.w};
+    const float ym[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool keep = thresh == 0u || mix32(seed + (uint32_t)(4 * i + k) * 0x9e3779b9U) >= thresh;   // index mod 2^32
+      r[k] = (keep && ym[k] != 0.f) ? r[k] * scale : 0.f;
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 }  // namespace pev
 
 using namespace pev;
 
 extern "C" {
 
+int pev_mask_grad(const float* g, const float* y, int64_t n, float p_drop, uint32_t seed, float* out, void* stream) {
+  PEV_REQUIRE(g && out && n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f, "bad argument (n must be a multiple of 4)");
+  if (n == 0) return 0;
+  const uint32_t thresh = p_drop > 0.f ? (uint32_t)(p_drop * 4294967296.0) : 0u;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  mask_grad_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(g, y, n / 4, 1.0f / (1.0f - p_drop), thresh, seed, out);
+  return after_launch("mask_grad_kernel");
+}
+
 int pev_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps,
                           int64_t N, int32_t D, float* r_out, float* y, float* mean, float* rstd, void* stream) {
-  PEV_REQUIRE(N >= 0 && (D == 256 || D == 512), "D must be 256 or 512");
+  PEV_REQUIRE(N >= 0 && (D == 128 || D == 256 || D == 512), "D must be 128, 256 or 512");
   if (N == 0) return 0;
   PEV_REQUIRE(x && gamma && beta && y && mean && rstd, "null argument");
   cudaStream_t st = as_stream(stream);
-  if (D == 256)
+  if (D == 128)
+    add_layernorm_fwd_kernel<128><<<rows_grid(N), 256, 0, st>>>(x, res, gamma, beta, eps, N, r_out, y, mean, rstd);
+  else if (D == 256)
     add_layernorm_fwd_kernel<256><<<rows_grid(N), 256, 0, st>>>(x, res, gamma, beta, eps, N, r_out, y, mean, rstd);
   else
     add_layernorm_fwd_kernel<512><<<rows_grid(N), 256, 0, st>>>(x, res, gamma, beta, eps, N, r_out, y, mean, rstd);
@@ -170,7 +205,7 @@ int64_t pev_node_workspace_bytes(void) { return (int64_t)sm_count() * 8 * 2 * 51
 
 int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const float* mean, const float* rstd,
                       int64_t N, int32_t D, float* workspace, float* gr, float* dgamma, float* dbeta, void* stream) {
-  PEV_REQUIRE(N >= 0 && (D == 256 || D == 512) && dgamma && dbeta, "bad argument");
+  PEV_REQUIRE(N >= 0 && (D == 128 || D == 256 || D == 512) && dgamma && dbeta, "bad argument");
   cudaStream_t st = as_stream(stream);
   if (N == 0) {
     cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st);
@@ -179,7 +214,9 @@ int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const
   }
   PEV_REQUIRE(gy && r && gamma && mean && rstd && gr && workspace, "null argument");
   const int grid = rows_grid(N);
-  if (D == 256)
+  if (D == 128)
+    layernorm_bwd_kernel<128><<<grid, 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, workspace);
+  else if (D == 256)
     layernorm_bwd_kernel<256><<<grid, 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, workspace);
   else
     layernorm_bwd_kernel<512><<<grid, 256, 0, st>>>(gy, r, gamma, mean, rstd, N, gr, workspace);

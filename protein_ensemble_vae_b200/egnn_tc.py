@@ -106,7 +106,7 @@ class AddLayerNorm(torch.autograd.Function):
 def layer_norm(module: nn.LayerNorm, x, res=None):
     """``module(x + res)`` through :class:`AddLayerNorm` when the shape is supported, else plain torch."""
     D = x.shape[-1]
-    if (x.is_cuda and x.dim() == 2 and D in (256, 512) and module.elementwise_affine and module.bias is not None
+    if (x.is_cuda and x.dim() == 2 and D in (128, 256, 512) and module.elementwise_affine and module.bias is not None
             and tuple(module.normalized_shape) == (D,)):
         return AddLayerNorm.apply(x, res, module.weight, module.bias, module.eps)
     return module(x if res is None else x + res)

@@ -99,20 +99,20 @@ class DihedralAwareEncoder(nn.Module):
                                                          batch_first=True)
         self.precision = precision
 
-    def _mha(self, mha: nn.MultiheadAttention, x, pk: _Packing, res=None):
+    def _mha(self, mha: nn.MultiheadAttention, x, pk: _Packing, res=None, p_drop=0.0):
         """Self-attention of one ``nn.MultiheadAttention`` parameter set over the packed rows: QKV projection (one GEMM),
-        per-conformer attention, output projection with the residual in its epilogue when ``res`` is given."""
+        per-conformer attention, output projection with dropout and the residual in its epilogue when ``res`` is given."""
         precise = self.precision == "fp32"
         qkv = linear(x, mha.in_proj_weight, mha.in_proj_bias, precise=precise)            # [N, 3 d]
         a = pattn.self_attention(qkv, pk, mha.num_heads, mha.dropout if self.training else 0.0, precise)
-        return linear(a, mha.out_proj.weight, mha.out_proj.bias, precise=precise, res=res)
+        return linear(a, mha.out_proj.weight, mha.out_proj.bias, precise=precise, res=res, p_drop=p_drop)
 
     def forward_packed(self, sequence_emb, n_coords, ca_coords, c_coords, dihedrals, pk: _Packing):
         precise = self.precision == "fp32"
         # per-residue features (:104-121)
         backbone = pk.pack(torch.cat([n_coords, ca_coords, c_coords], dim=-1))               # [N, 9]
-        coord_feat = self.coord_norm(self.coord_proj(backbone))
-        dihedral_feat = self.dihedral_norm(self.dihedral_proj(pk.pack(dihedrals)))
+        coord_feat = layer_norm(self.coord_norm, self.coord_proj(backbone))
+        dihedral_feat = layer_norm(self.dihedral_norm, self.dihedral_proj(pk.pack(dihedrals)))
         seq_feat = linear(pk.pack(sequence_emb), self.seq_proj.weight, self.seq_proj.bias, precise=precise)
         combined = torch.cat([seq_feat, coord_feat, dihedral_feat], dim=-1)
         f = linear(combined, self.feature_fusion[0].weight, self.feature_fusion[0].bias, precise=precise)
@@ -122,18 +122,11 @@ class DihedralAwareEncoder(nn.Module):
         f = f + self.geom_res_scale * self._mha(self.geometric_attention, f, pk)
         # transformer layers, pre-norm (:139-140; nn.TransformerEncoderLayer with norm_first=True, ReLU)
         for layer in self.transformer_layers:
-            train = self.training
-            xn = layer_norm(layer.norm1, f)
-            if train and layer.dropout1.p > 0:
-                f = f + layer.dropout1(self._mha(layer.self_attn, xn, pk))
-            else:
-                f = self._mha(layer.self_attn, xn, pk, res=f)
-            xn = layer_norm(layer.norm2, f)
-            h1 = layer.dropout(linear(xn, layer.linear1.weight, layer.linear1.bias, relu=True, precise=precise))
-            if train and layer.dropout2.p > 0:
-                f = f + layer.dropout2(linear(h1, layer.linear2.weight, layer.linear2.bias, precise=precise))
-            else:
-                f = linear(h1, layer.linear2.weight, layer.linear2.bias, precise=precise, res=f)
+            p1, p, p2 = ((layer.dropout1.p, layer.dropout.p, layer.dropout2.p) if self.training else (0.0, 0.0, 0.0))
+            f = self._mha(layer.self_attn, layer_norm(layer.norm1, f), pk, res=f, p_drop=p1)          # x + drop1(SA(norm1 x))
+            h1 = linear(layer_norm(layer.norm2, f), layer.linear1.weight, layer.linear1.bias, relu=True, precise=precise,
+                        p_drop=p)                                                                    # drop(relu(linear1))
+            f = linear(h1, layer.linear2.weight, layer.linear2.bias, precise=precise, res=f, p_drop=p2)
         return layer_norm(self.ln, f)                                                        # (:143)
 
     def forward(self, sequence_emb, n_coords, ca_coords, c_coords, dihedrals, mask):

@@ -28,8 +28,26 @@ def supported(x, W) -> bool:
     return x.is_cuda and x.dim() == 2 and W.shape[0] % 256 == 0 and W.shape[1] % 256 == 0 and x.shape[1] == W.shape[1]
 
 
-def linear_fwd(x, W, bias=None, relu=False, res=None, precise=False, out=None):
-    """``act(x W^T + bias + res)``; ``W`` is the fp32 weight ``[Nout,K]`` (TF32) or its split image (``precise``)."""
+_COUNTER = [0]
+
+
+def _next_seed() -> int:
+    """Host-side dropout seed (no device sync): torch's seed mixed with a call counter."""
+    _COUNTER[0] += 1
+    return (torch.initial_seed() * 2654435761 + _COUNTER[0] * 40503 + 12345) & 0xFFFFFFFF
+
+
+def mask_grad(g, y, p_drop, seed):
+    """Backward of the dropout / ReLU epilogues: ``g / (1 - p)`` where the element was kept (and ``y != 0``), else 0."""
+    g = g.float().contiguous()
+    with torch.cuda.device_of(g):
+        out = torch.empty_like(g)
+        _lib.lib().call("pev_mask_grad", _p(g), _p(y), g.numel(), float(p_drop), int(seed), _p(out), stream(g))
+    return out
+
+
+def linear_fwd(x, W, bias=None, relu=False, res=None, precise=False, out=None, p_drop=0.0, seed=0):
+    """``dropout(act(x W^T + bias)) + res``; ``W`` is the fp32 weight ``[Nout,K]`` (TF32) or its split image (``precise``)."""
     x = _rows(x)
     M, K = x.shape
     Nout = W.shape[0] // 2 if precise else W.shape[0]
@@ -37,8 +55,8 @@ def linear_fwd(x, W, bias=None, relu=False, res=None, precise=False, out=None):
     with torch.cuda.device_of(x):
         if out is None:
             out = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
-        _lib.lib().call("pev_linear", int(precise), _p(x), x.stride(0), K, _p(W), _p(bias), M, Nout, int(relu), _p(res),
-                        0 if res is None else res.stride(0), _p(out), out.stride(0), stream(x))
+        _lib.lib().call("pev_linear", int(precise), _p(x), x.stride(0), K, _p(W), _p(bias), M, Nout, int(relu), float(p_drop),
+                        int(seed), _p(res), 0 if res is None else res.stride(0), _p(out), out.stride(0), stream(x))
     return out
 
 
@@ -60,24 +78,27 @@ def linear_wgrad(g, x, precise=False):
 
 
 class TCLinear(torch.autograd.Function):
-    """``relu?(x W^T + b) (+ res)`` with all three GEMMs on the tensor cores."""
+    """``dropout(relu?(x W^T + b)) + res`` with all three GEMMs on the tensor cores; the dropout mask is a counter hash of
+    (seed, element) applied in the GEMM epilogue and re-derived in the backward pass."""
 
     @staticmethod
-    def forward(ctx, x, W, b, relu, precise, res):
+    def forward(ctx, x, W, b, relu, precise, res, p_drop):
+        assert not (relu and res is not None)
         Wd = W.detach().float().contiguous()
         bd = None if b is None else b.detach().float().contiguous()
-        y = linear_fwd(x, split_weight(Wd) if precise else Wd, bd, relu=relu and res is None, res=res, precise=precise)
-        assert not (relu and res is not None)
-        ctx.relu, ctx.precise, ctx.has_res = relu, precise, res is not None
+        seed = _next_seed() if p_drop > 0 else 0
+        y = linear_fwd(x, split_weight(Wd) if precise else Wd, bd, relu=relu, res=res, precise=precise, p_drop=p_drop, seed=seed)
+        ctx.relu, ctx.precise, ctx.has_res, ctx.p_drop, ctx.seed = relu, precise, res is not None, p_drop, seed
         ctx.save_for_backward(x, Wd, y if relu else None)
         return y
 
     @staticmethod
     def backward(ctx, g):
         x, Wd, y = ctx.saved_tensors
+        g_res = g if ctx.has_res else None
+        if ctx.relu or ctx.p_drop > 0:
+            g = mask_grad(g, y, ctx.p_drop, ctx.seed)
         g = _rows(g)
-        if ctx.relu:
-            g = g * (y > 0)
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
             gx = linear_fwd(g, split_weight(Wd, transpose=True) if ctx.precise else Wd.t().contiguous(), precise=ctx.precise)
@@ -85,15 +106,18 @@ class TCLinear(torch.autograd.Function):
             gW = linear_wgrad(g, x, ctx.precise)
         if ctx.needs_input_grad[2]:
             gb = column_sum(g.contiguous()) if g.shape[1] <= 1024 else torch.cat([column_sum(g[:, j:j + 512].contiguous())
-                                                                     for j in range(0, g.shape[1], 512)])
-        return gx, gW, gb, None, None, (g if ctx.has_res else None)
+                                                                                  for j in range(0, g.shape[1], 512)])
+        return gx, gW, gb, None, None, g_res, None
 
 
-def linear(x, W, b=None, relu=False, precise=False, res=None):
-    """``relu?(x W^T + b) + res`` -- tensor-core path for supported shapes, else plain torch (tiny / odd-shaped linears)."""
+def linear(x, W, b=None, relu=False, precise=False, res=None, p_drop=0.0):
+    """``dropout(relu?(x W^T + b)) + res`` -- tensor-core path for supported shapes, else plain torch (tiny / odd-shaped
+    linears)."""
     if supported(x, W):
-        return TCLinear.apply(x, W, b, relu, precise, res)
+        return TCLinear.apply(x, W, b, relu, precise, res, float(p_drop))
     y = torch.nn.functional.linear(x, W, b)
     if relu:
         y = torch.relu(y)
+    if p_drop > 0:
+        y = torch.nn.functional.dropout(y, p_drop)
     return y if res is None else y + res

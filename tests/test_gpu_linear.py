@@ -59,3 +59,26 @@ def test_tclinear_autograd_relu_and_residual():
     assert float((y.detach().double() - yr.detach()).abs().max() / yr.detach().abs().max()) < 3e-6
     for a, r in zip(grads, gr):
         assert float((a.double() - r).abs().max() / r.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("precise", [False, True])
+def test_fused_dropout_and_relu_backward_match_the_forward_mask(precise):
+    """y = dropout(relu(x W^T + b)) is positively homogeneous of degree 1 in (W, b): <coef, y> = <dW, W> + <db, b> holds only
+    if the backward pass re-derives exactly the dropout mask (counter hash) and ReLU pattern of the forward pass."""
+    from protein_ensemble_vae_b200 import tc_linear
+    torch.manual_seed(4)
+    x = torch.randn(900, 512, device="cuda")
+    W = (torch.randn(1024, 512, device="cuda") / 22).requires_grad_()
+    b = torch.randn(1024, device="cuda", requires_grad=True)
+    coef = torch.randn(900, 1024, device="cuda")
+    y = tc_linear.linear(x, W, b, relu=True, precise=precise, p_drop=0.25)
+    frac = float((y == 0).float().mean())
+    assert 0.55 < frac < 0.70                                          # ~50 % ReLU zeros, then 25 % of the rest dropped
+    gW, gb = torch.autograd.grad((y * coef).sum(), [W, b])
+    lhs = float((y.detach().double() * coef.double()).sum())
+    rhs = float((gW.double() * W.detach().double()).sum() + (gb.double() * b.detach().double()).sum())
+    assert abs(lhs - rhs) < (2e-3 if not precise else 2e-5) * max(abs(lhs), 1.0), (lhs, rhs)
+    res = torch.randn(900, 1024, device="cuda")
+    y2 = tc_linear.linear(x, W, b, precise=precise, res=res, p_drop=0.5)
+    kept = float(((y2 - res).abs() > 0).float().mean())
+    assert 0.45 < kept < 0.55                                          # dropout acts before the residual is added
