@@ -180,7 +180,7 @@ int64_t pev_node_workspace_bytes(void);
 int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const float* mean,
                       const float* rstd, int64_t N, int32_t D, float* workspace, float* gr, float* dgamma,
                       float* dbeta, void* stream);
-/* out[D] = sum over rows of g[N,D] (bias gradients of the node-level linears), D <= 1024; per-block partials in
+/* out[D] = sum over rows of g[N,D] (bias gradients of the node-level linears), D <= 4096; per-block partials in
  * `workspace` (pev_node_workspace_bytes()), fixed-order reduction. */
 int pev_column_sum(const float* g, int64_t N, int32_t D, float* workspace, float* out, void* stream);
 

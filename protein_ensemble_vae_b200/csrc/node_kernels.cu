@@ -228,7 +228,7 @@ int pev_layernorm_bwd(const float* gy, const float* r, const float* gamma, const
 }
 
 int pev_column_sum(const float* g, int64_t N, int32_t D, float* workspace, float* out, void* stream) {
-  PEV_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && out, "bad argument (D must be a multiple of 4, <= 1024)");
+  PEV_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && D <= 4096 && out, "bad argument (D must be a multiple of 4, <= 4096)");
   cudaStream_t st = as_stream(stream);
   if (N == 0) {
     cudaMemsetAsync(out, 0, sizeof(float) * D, st);

@@ -61,7 +61,7 @@ def node_workspace(device) -> torch.Tensor:
 def column_sum(g: torch.Tensor) -> torch.Tensor:
     """``g.sum(0)`` of a contiguous fp32 ``[N,D]`` (bias gradients) on ``pev_column_sum`` (bit-reproducible)."""
     N, D = g.shape
-    if D % 4 or D > 1024 or g.dtype != torch.float32:
+    if D % 4 or D > 4096 or g.dtype != torch.float32:
         return g.sum(0)
     with torch.cuda.device_of(g):
         out = torch.empty(D, dtype=torch.float32, device=g.device)

@@ -105,8 +105,7 @@ class TCLinear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gW = linear_wgrad(g, x, ctx.precise)
         if ctx.needs_input_grad[2]:
-            gb = column_sum(g.contiguous()) if g.shape[1] <= 1024 else torch.cat([column_sum(g[:, j:j + 512].contiguous())
-                                                                                  for j in range(0, g.shape[1], 512)])
+            gb = column_sum(g.contiguous())
         return gx, gW, gb, None, None, g_res, None
 
 
