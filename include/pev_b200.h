@@ -360,6 +360,18 @@ int pev_unpack_center(const float* n, const float* ca, const float* c, const flo
                       int32_t center, float* o_n, float* o_ca, float* o_c, float* o_mask, float* o_dih, int64_t* o_labels,
                       float* o_emb, void* stream);
 
+/* ---------------------------------------------------------------- streaming ensemble PDB writer (csrc/pdb_kernels.cu)
+ * The MODEL blocks that write_pdb (generate_ensemble_pdbs.py:148-288, with compute_backbone_oxygen :106-144) appends one
+ * call per model: MODEL line, four ATOM records per valid residue (N, CA, C and the placed O), blank line, CONECT records,
+ * TER, ENDMDL -- byte for byte, for models model0 .. model0 + S - 1 (1-based) of n / ca / c [S,L,3] into `out`
+ * (pev_pdb_models_bytes(model0, S, nv) bytes).  valid_idx[nv]: indices of the residues with mask > 0.5; prev_ok[nv]: the
+ * residue before it exists and is valid; resname[3 nv]: three-letter codes.  *overflow is set to 1 if a coordinate does not
+ * fit %8.3f (|x| >= 9999.9995). */
+int64_t pev_pdb_models_bytes(int64_t model0, int32_t S, int32_t nv);
+int pev_pdb_format_models(const float* n, const float* ca, const float* c, const int32_t* valid_idx, const uint8_t* prev_ok,
+                          const char* resname, int32_t S, int32_t L, int32_t nv, int64_t model0, int32_t chain, char* out,
+                          int32_t* overflow, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

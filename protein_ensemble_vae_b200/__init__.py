@@ -7,7 +7,8 @@ kernels reached through the C ABI of ``include/pev_b200.h``.  CUDA-only, no CPU 
 """
 from . import data, en_gnn_decoder, generation, graph, graphs, kabsch, losses, metrics  # noqa: F401
 from .data import DevicePrefetcher  # noqa: F401
-from .generation import generate_ensemble, validate_geometry_batch, validate_protein_geometry  # noqa: F401
+from .generation import (generate_ensemble, validate_geometry_batch, validate_protein_geometry,  # noqa: F401
+                         write_ensemble_pdb)
 from .graphs import GraphedStep  # noqa: F401
 from .metrics import compute_gdt, compute_lddt, compute_rmsf, compute_tm_score  # noqa: F401
 from .en_gnn_decoder import EGNLayer, EGNNDecoder, ResidueDecoder, SE3EquivariantDecoder  # noqa: F401
@@ -16,6 +17,6 @@ from .losses import compute_total_loss  # noqa: F401
 
 __all__ = ["EGNLayer", "EGNNDecoder", "SE3EquivariantDecoder", "ResidueDecoder", "compute_total_loss",
            "kabsch_rmsd", "kabsch_rmsd_batch", "kabsch_rmsd_pairs", "ensemble_diversity", "DevicePrefetcher",
-           "GraphedStep", "generate_ensemble", "validate_geometry_batch", "validate_protein_geometry", "compute_tm_score",
+           "GraphedStep", "generate_ensemble", "validate_geometry_batch", "validate_protein_geometry", "write_ensemble_pdb", "compute_tm_score",
            "compute_lddt", "compute_gdt", "compute_rmsf", "metrics", "data", "losses",
            "en_gnn_decoder", "generation", "graph", "graphs", "kabsch"]

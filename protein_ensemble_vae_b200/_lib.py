@@ -54,6 +54,9 @@ _PROTOS = {
     "pev_superpose_scores": (c_int32, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pev_lddt": (c_int32, [_P, _P, _P, _I, _I, _I, _I, c_float, _P, _P, _P]),
     "pev_rmsf": (c_int32, [_P, _I, _I, _P, _P]),
+    "pev_pdb_models_bytes": (c_int64, [_L, _I, _I]),
+    "pev_pdb_format_models": (c_int32, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P]),
+    "pev_unpack_center": (c_int32, [_P] * 8 + [_I, _I, _I, _I] + [_P] * 8),
 }
 # tensor-core entry points: present in libpev_b200.so only (no host restatement)
 _PROTOS_TC = {
@@ -79,7 +82,6 @@ _PROTOS_TC = {
     # node-level tcgen05 TF32 GEMMs with fused epilogues (csrc/node_gemm_kernels.cu)
     "pev_node_wgrad_workspace_bytes": (c_int64, []),
     "pev_node_wgrad": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
-    "pev_unpack_center": (c_int32, [_P] * 8 + [_I, _I, _I, _I] + [_P] * 8),
     "pev_attn_gemm": (c_int32, [_I, _P, _L, _I, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _L, c_float, _P, _L, _I, _P]),
     "pev_attn_softmax": (c_int32, [_I, _P, _P, _P, _P, _P, _I, _I, _I, c_float, c_uint32, _P]),
     "pev_linear": (c_int32, [_I, _P, _L, _I, _P, _P, _L, _I, _I, c_float, c_uint32, _P, _L, _P, _L, _P]),

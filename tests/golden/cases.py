@@ -215,3 +215,19 @@ def encoder_inputs(case):
     coef = [rng.standard_normal((B, 512)), rng.standard_normal((B, 512)), rng.standard_normal((B, L, 256)) * mask[..., None],
             rng.standard_normal((B, L, 256)) * mask[..., None]]
     return [synth.f32(a) for a in (emb, n, ca, c, dih)], mask, [synth.f32(a) for a in coef]
+
+
+def pdb_inputs():
+    """Three models of a 14-residue backbone (float32) with an interior gap and a masked first residue, coordinates that
+    exercise the %8.3f field (negative zero, a rounding tie j/16, four integer digits), a sequence with an unknown letter."""
+    rng = np.random.default_rng(101)
+    S, L = 3, 14
+    ca = np.cumsum(rng.standard_normal((S, L, 3)) * 2.2, axis=1)
+    n, c = ca + 0.8 * rng.standard_normal((S, L, 3)), ca + 0.8 * rng.standard_normal((S, L, 3))
+    n[0, 3] = [-0.0004, 0.0625, 1234.5678]
+    ca[1, 5] = [-99.9996, 0.1875, -0.0]
+    c[2, 7] = [9999.9, -12.3125, 0.0005]
+    mask = np.ones(L, np.float32)
+    mask[0] = 0
+    mask[8:10] = 0
+    return synth.f32(n), synth.f32(ca), synth.f32(c), mask, "MKXLVAGGHWYRTS"

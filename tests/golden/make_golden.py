@@ -304,6 +304,22 @@ def gen_metrics():
     np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
 
 
+# --------------------------------------------------------------------------- PDB writer
+def gen_pdb():
+    ns = {"np": np}
+    src = os.path.join(REF, "generate_ensemble_pdbs.py")
+    ns["compute_backbone_oxygen"] = lift_function(src, "compute_backbone_oxygen", ns)
+    write_pdb = lift_function(src, "write_pdb", ns)
+    n, ca, c, mask, seq = cases.pdb_inputs()
+    path = os.path.join(HERE, "ensemble.pdb")
+    for m in range(n.shape[0]):
+        write_pdb(n[m], ca[m], c[m], mask, path, model_num=m + 1, sequence=seq, pdb_id="1abc", chain_id="B",
+                  title="synthetic ensemble", num_models=n.shape[0])
+    path2 = os.path.join(HERE, "ensemble_plain.pdb")      # no sequence / id / title, all residues valid
+    for m in range(2):
+        write_pdb(n[m], ca[m], c[m], np.ones_like(mask), path2, model_num=m + 1, num_models=2)
+
+
 # --------------------------------------------------------------------------- encoder
 def gen_encoders():
     sys.path.insert(0, os.path.join(REF, "models"))
@@ -357,6 +373,7 @@ if __name__ == "__main__":
     gen_kabsch()
     gen_metrics()
     gen_data()
+    gen_pdb()
     gen_encoders()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -11,6 +11,7 @@
 #include "../../protein_ensemble_vae_b200/csrc/pev_kabsch_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_data_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_metrics_body.cuh"
+#include "../../protein_ensemble_vae_b200/csrc/pev_pdb_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_loss_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_loss_final.cuh"
 
@@ -332,6 +333,18 @@ int pev_unpack_center(const float* n, const float* ca, const float* c, const flo
           o_emb[((int64_t)b * Lmax + l) * D + d] = l < L ? emb[((int64_t)cu[b] + l) * D + d] : 0.f;
     }
   }
+  return 0;
+}
+
+int64_t pev_pdb_models_bytes(int64_t model0, int32_t S, int32_t nv) { return pdb_block_offset(model0 + S, model0, nv); }
+
+int pev_pdb_format_models(const float* n, const float* ca, const float* c, const int32_t* valid_idx, const uint8_t* prev_ok,
+                          const char* resname, int32_t S, int32_t L, int32_t nv, int64_t model0, int32_t chain, char* out,
+                          int32_t* overflow, void*) {
+  PdbArgs a = {n, ca, c, valid_idx, prev_ok, resname, S, L, nv, model0, (char)chain, out};
+  for (int s = 0; s < S; ++s)
+    for (int k = 0; k < (nv > 0 ? nv : 1); ++k)
+      if (!pdb_residue(a, s, k)) *overflow = 1;
   return 0;
 }
 
