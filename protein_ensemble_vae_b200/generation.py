@@ -56,11 +56,12 @@ def validate_protein_geometry(coords_ca, mask):
 
 @torch.no_grad()
 def generate_ensemble(decoder, z_g, z_l, mask=None, reference_ca=None, chunk: int = 2048, ref_compat: bool = False,
-                      diversity_samples: int = 256):
+                      diversity_samples: int = 256, pdb_path=None, sequence=None, pdb_id=None, chain_id: str = "A"):
     """Decode the latent samples ``z_g[S,zg], z_l[S,L,zl]`` (this rank's contiguous share when distributed) and return
     a dict of device tensors: ``N, CA, C`` ``[S_local,L,3]``, ``logits``, ``valid`` (bool), ``status``, ``stats``,
     ``rmsd`` (against ``reference_ca``, if given) and ``diversity`` (mean pairwise Kabsch RMSD over the first
-    ``diversity_samples`` valid members)."""
+    ``diversity_samples`` valid members).  ``pdb_path``: also write the geometrically valid members (one shared ``mask``) as
+    a multi-model PDB file (:func:`write_ensemble_pdb`; the reference writes model by model, ``:598-625``)."""
     from .distributed import shard_range, world
     from .kabsch import ensemble_diversity, kabsch_rmsd_batch
     rank, ws = world()
@@ -83,6 +84,11 @@ def generate_ensemble(decoder, z_g, z_l, mask=None, reference_ca=None, chunk: in
     keep = torch.nonzero(res["valid"]).squeeze(-1)[:diversity_samples]
     dmask = None if km is None else (km if km.dim() == 1 else km[0])
     res["diversity"] = ensemble_diversity(ca.index_select(0, keep), dmask, ref_compat=ref_compat)
+    if pdb_path is not None:
+        ok = torch.nonzero(res["valid"]).squeeze(-1)
+        wm = dmask if dmask is not None else torch.ones(ca.shape[1], device=ca.device)
+        res["pdb_bytes"] = write_ensemble_pdb(pdb_path, n.index_select(0, ok), ca.index_select(0, ok), c.index_select(0, ok), wm,
+                                              sequence=sequence, pdb_id=pdb_id, chain_id=chain_id)
     return res
 
 
