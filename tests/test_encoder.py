@@ -82,11 +82,11 @@ def _run_inner(tag, precision, tb):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision,tol_out", [("fp32", 1e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("precision,tol_out", [("fp32", 1e-5), ("tf32", 5e-3)])
 @pytest.mark.parametrize("tag", list(cases.ENCODER_CASES))
 def test_encoder_matches_reference(tag, precision, tol_out):
     """fp32 path (3xTF32 linears): outputs 1e-5, parameter gradients 1e-4.  TF32 path (own GEMM + attention kernels):
-    outputs 3e-3; gradients within 6x (worst parameter: a single flipped unit) / 3x (median over parameters) of the library-TF32 yardstick ( measured: mine
+    outputs 5e-3 (measured 1.5 - 2.7e-3); gradients within 6x (worst parameter: a single flipped unit) / 3x (median over parameters) of the library-TF32 yardstick ( measured: mine
     worst 0.10 - 0.35 / median 0.03, yardstick worst 0.15 - 0.20 / median 0.014 - 0.026: single-pass TF32 flips ~1e-4 of the
     ReLU units of the feed-forward blocks, which moves weight gradients by percents whoever does the rounding)."""
     gold = np.load(os.path.join(G, "encoders.npz"))
