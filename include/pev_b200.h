@@ -332,6 +332,8 @@ int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t K, const fl
 /* Backward of those epilogues: out[i] = (keep(seed, i) && (y == NULL || y[i] != 0)) ? g[i] / (1 - p_drop) : 0 over n
  * contiguous elements (n a multiple of 4) -- nn.Dropout / nn.ReLU backward of models/encoder.py's blocks in one pass. */
 int pev_mask_grad(const float* g, const float* y, int64_t n, float p_drop, uint32_t seed, float* out, void* stream);
+/* out[cols, rows] = scale * in[rows, cols]^T (the pre-transposed weight of a data-gradient GEMM: g W = g (W^T)^T). */
+int pev_transpose(const float* in, int32_t rows, int32_t cols, float scale, float* out, void* stream);
 int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int32_t Kx,
                      int64_t N, float scale, float* workspace, float* out, int64_t ldc, void* stream);
 

@@ -170,11 +170,31 @@ mask_grad_kernel(const float* __restrict__ g, const float* __restrict__ y, int64
   }
 }
 
+// out[c, r] = scale * in[r, c]: 32 x 32 tiles through shared memory, coalesced both ways (the weight of a data-gradient
+// GEMM; a strided element-wise copy of a 1536 x 512 weight took 40 us, this takes 4)
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, int rows, int cols, float scale, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8)
+    if (r0 + k < rows && c0 + tx < cols) tile[k][tx] = in[(int64_t)(r0 + k) * cols + c0 + tx];
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8)
+    if (c0 + k < cols && r0 + tx < rows) out[(int64_t)(c0 + k) * rows + r0 + tx] = scale * tile[tx][k];
+}
+
 }  // namespace pev
 
 using namespace pev;
 
 extern "C" {
+
+int pev_transpose(const float* in, int32_t rows, int32_t cols, float scale, float* out, void* stream) {
+  PEV_REQUIRE(in && out && rows > 0 && cols > 0, "bad argument");
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, as_stream(stream)>>>(in, rows, cols, scale, out);
+  return after_launch("transpose_kernel");
+}
 
 int pev_mask_grad(const float* g, const float* y, int64_t n, float p_drop, uint32_t seed, float* out, void* stream) {
   PEV_REQUIRE(g && out && n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f, "bad argument (n must be a multiple of 4)");

@@ -167,6 +167,19 @@ class NodeLinear2(torch.autograd.Function):
 EPI_ABH, EPI_SILU, EPI_RES_LN, EPI_PLAIN, EPI_DSILU = range(5)
 
 
+def transposed(W, scale: float = 1.0):
+    """``scale * W^T`` as a contiguous tensor (``pev_transpose``: tiled, coalesced both ways) -- the weight operand of the
+    data-gradient GEMMs."""
+    W = f32c(W.detach())
+    if not W.is_cuda or W.dim() != 2:
+        return (scale * W).t().contiguous()
+    rows, cols = W.shape
+    with torch.cuda.device_of(W):
+        out = torch.empty(cols, rows, dtype=torch.float32, device=W.device)
+        _lib.lib().call("pev_transpose", ptr(W), rows, cols, float(scale), ptr(out), stream(W))
+    return out
+
+
 def node_gemm(epi, A1, W, bias=None, A2=None, scale=1.0, aux=None, gamma=None, beta=None, eps=1e-5, out2=False,
               stats=False):
     """``pev_node_gemm``: ``epilogue([A1 | A2] W^T)`` on the tensor cores (TF32 operands, fp32 accumulation), see
@@ -216,7 +229,7 @@ def node_abh(h, W1, b1):
 
 def node_abh_backward(gAB, h, W1, need_h=True):
     """``(gh, gWa|gWb as [256,512], gb1)`` from ``gAB = dL/dABh`` (fp32 [N,512])."""
-    Wcat_t = (0.5 * torch.cat([W1[:, :H], W1[:, H:2 * H]], 0)).t().contiguous()   # [256, 512]: gh = gAB (0.5 Wcat)
+    Wcat_t = transposed(torch.cat([W1[:, :H], W1[:, H:2 * H]], 0), 0.5)           # [256, 512]: gh = gAB (0.5 Wcat)
     gh = node_gemm(EPI_PLAIN, gAB, Wcat_t)[0] if need_h else None
     gWab = node_wgrad(gAB, h, 0.5)                                               # [512, 256] = [gWa ; gWb]
     gb1 = 0.5 * column_sum(gAB)[:H]
@@ -250,8 +263,8 @@ class NodePhiH(torch.autograd.Function):
             dgb = torch.empty(2 * D, dtype=torch.float32, device=r.device)
             _lib.lib().call("pev_layernorm_bwd", ptr(gy), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), N, D,
                             ptr(node_workspace(r.device)), ptr(gr), ptr(dgb), ptr(dgb[D:]), stream(r))
-        gp = node_gemm(EPI_DSILU, gr, W4.t().contiguous(), aux=p)[0]              # (gr W4) * silu'(p)
-        gha = node_gemm(EPI_PLAIN, gp, W3.t().contiguous())[0]                    # [N,512] = [dL/dh (phi_h part) | dL/dagg]
+        gp = node_gemm(EPI_DSILU, gr, transposed(W4), aux=p)[0]                   # (gr W4) * silu'(p)
+        gha = node_gemm(EPI_PLAIN, gp, transposed(W3))[0]                         # [N,512] = [dL/dh (phi_h part) | dL/dagg]
         gh = gr + gha[:, :D]
         gagg = gha[:, D:]
         gW4 = node_wgrad(gr, q)

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import stream
-from .egnn_tc import _WGRAD_WS, column_sum, split_weight
+from .egnn_tc import _WGRAD_WS, column_sum, split_weight, transposed
 
 
 def _p(t):
@@ -101,7 +101,7 @@ class TCLinear(torch.autograd.Function):
         g = _rows(g)
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
-            gx = linear_fwd(g, split_weight(Wd, transpose=True) if ctx.precise else Wd.t().contiguous(), precise=ctx.precise)
+            gx = linear_fwd(g, split_weight(transposed(Wd)) if ctx.precise else transposed(Wd), precise=ctx.precise)
         if ctx.needs_input_grad[1]:
             gW = linear_wgrad(g, x, ctx.precise)
         if ctx.needs_input_grad[2]:
