@@ -362,6 +362,16 @@ int pev_unpack_center(const float* n, const float* ca, const float* c, const flo
                       int32_t center, float* o_n, float* o_ca, float* o_c, float* o_mask, float* o_dih, int64_t* o_labels,
                       float* o_emb, void* stream);
 
+/* ---------------------------------------------------------------- backbone placement (csrc/backbone_kernels.cu)
+ * N / C placement and the 3-step peptide pull of EGNNDecoder.forward (models/en_gnn_decoder.py:260-310) over the packed
+ * residues: x_n = pull3(x_ca + 1.46 normalize(n_dir)), x_c = x_ca + 1.52 normalize(c_dir); n_dir / c_dir are the first three
+ * channels of the offset heads' outputs (rows of ldn / ldc floats), starts[k] != 0 marks the first residue of a conformer (not
+ * pulled).  pev_backbone_bwd: gradients with respect to the directions ([N,3] each) and x_ca from g_xn, g_xc. */
+int pev_backbone_fwd(const float* n_dir, int32_t ldn, const float* c_dir, int32_t ldc, const float* x_ca, const uint8_t* starts,
+                     int64_t N, float* x_n, float* x_c, void* stream);
+int pev_backbone_bwd(const float* n_dir, int32_t ldn, const float* c_dir, int32_t ldc, const float* x_ca, const uint8_t* starts,
+                     int64_t N, const float* g_xn, const float* g_xc, float* g_ndir, float* g_cdir, float* g_xca, void* stream);
+
 /* ---------------------------------------------------------------- streaming ensemble PDB writer (csrc/pdb_kernels.cu)
  * The MODEL blocks that write_pdb (generate_ensemble_pdbs.py:148-288, with compute_backbone_oxygen :106-144) appends one
  * call per model: MODEL line, four ATOM records per valid residue (N, CA, C and the placed O), blank line, CONECT records,

@@ -54,6 +54,8 @@ _PROTOS = {
     "pev_superpose_scores": (c_int32, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pev_lddt": (c_int32, [_P, _P, _P, _I, _I, _I, _I, c_float, _P, _P, _P]),
     "pev_rmsf": (c_int32, [_P, _I, _I, _P, _P]),
+    "pev_backbone_fwd": (c_int32, [_P, _I, _P, _I, _P, _P, _L, _P, _P, _P]),
+    "pev_backbone_bwd": (c_int32, [_P, _I, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "pev_pdb_models_bytes": (c_int64, [_L, _I, _I]),
     "pev_pdb_format_models": (c_int32, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P]),
     "pev_unpack_center": (c_int32, [_P] * 8 + [_I, _I, _I, _I] + [_P] * 8),

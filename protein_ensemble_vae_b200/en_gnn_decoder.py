@@ -81,6 +81,47 @@ class EGNLayer(nn.Module):
         return _layer_forward(self, h, x, g, degree_inv, self.precision)
 
 
+class _Backbone(torch.autograd.Function):
+    """``x_n = pull3(x_ca + 1.46 normalize(n_dir))``, ``x_c = x_ca + 1.52 normalize(c_dir)`` (``models/en_gnn_decoder.py:260-310``;
+    a residue is pulled towards C of its predecessor unless it starts a conformer)."""
+
+    @staticmethod
+    def forward(ctx, n_dir, c_dir, x_ca, starts):
+        from ctypes import c_void_p
+        from . import _lib
+        from ._lib import f32c, ptr, stream
+        n_dir, c_dir = n_dir.float(), c_dir.float()
+        if n_dir.stride(1) != 1:
+            n_dir = n_dir.contiguous()
+        if c_dir.stride(1) != 1:
+            c_dir = c_dir.contiguous()
+        x_ca = f32c(x_ca)
+        st = starts.contiguous().view(torch.uint8)
+        N = x_ca.shape[0]
+        with torch.cuda.device_of(x_ca):
+            x_n, x_c = torch.empty_like(x_ca), torch.empty_like(x_ca)
+            _lib.lib().call("pev_backbone_fwd", c_void_p(n_dir.data_ptr()), n_dir.stride(0), c_void_p(c_dir.data_ptr()),
+                            c_dir.stride(0), ptr(x_ca), ptr(st), N, ptr(x_n), ptr(x_c), stream(x_ca))
+        ctx.save_for_backward(n_dir, c_dir, x_ca, st)
+        return x_n, x_c
+
+    @staticmethod
+    def backward(ctx, g_xn, g_xc):
+        from ctypes import c_void_p
+        from . import _lib
+        from ._lib import f32c, ptr, stream
+        n_dir, c_dir, x_ca, st = ctx.saved_tensors
+        N = x_ca.shape[0]
+        with torch.cuda.device_of(x_ca):
+            g_xn = f32c(g_xn) if g_xn is not None else torch.zeros_like(x_ca)
+            g_xc = f32c(g_xc) if g_xc is not None else torch.zeros_like(x_ca)
+            g_n, g_c, g_ca = torch.empty_like(x_ca), torch.empty_like(x_ca), torch.empty_like(x_ca)
+            _lib.lib().call("pev_backbone_bwd", c_void_p(n_dir.data_ptr()), n_dir.stride(0), c_void_p(c_dir.data_ptr()),
+                            c_dir.stride(0), ptr(x_ca), ptr(st), N, ptr(g_xn), ptr(g_xc), ptr(g_n), ptr(g_c), ptr(g_ca),
+                            stream(x_ca))
+        return g_n, g_c, g_ca, None
+
+
 class EGNNDecoder(nn.Module):
     """Latents -> backbone (``models/en_gnn_decoder.py:90-333``)."""
 
@@ -241,25 +282,11 @@ class EGNNDecoder(nn.Module):
         return unpack(x_n, 3), unpack(x, 3), unpack(x_c, 3), unpack(logits, 20)
 
     def _backbone(self, h, x_ca, g):
-        """N / C placement and the 3-step peptide pull (``:260-310``), vectorised over the packed batch."""
-        n_dir = self._run(self.n_offset_head, h, True)[:, :3]        # 4th channel unused in the reference too
-        c_dir = self._run(self.c_offset_head, h, True)[:, :3]
-        x_n = x_ca + F.normalize(n_dir, dim=-1) * N_CA_LENGTH
-        x_c = x_ca + F.normalize(c_dir, dim=-1) * CA_C_LENGTH
-        N = x_ca.shape[0]
-        if N > 1:
-            # residue k is pulled towards C of residue k-1 unless it starts a conformer
-            starts = g.starts
-            pull = (~starts[1:]).unsqueeze(-1)
-            anchor = x_c[:-1]
-            tail = x_n[1:]
-            for _ in range(3):                                  # :299
-                vec = tail - anchor
-                dist = vec.norm(dim=-1, keepdim=True)
-                scale = torch.clamp(1.0 + 0.15 * (PEPTIDE_LENGTH / (dist + 1e-8) - 1.0), 0.90, 1.10)
-                tail = torch.where(pull, anchor + vec * scale, tail)
-            x_n = torch.cat([x_n[:1], tail], 0)
-        return x_n, x_c
+        """N / C placement and the 3-step peptide pull (``:260-310``) over the packed batch: the two direction heads, then one
+        kernel per direction (``pev_backbone_fwd`` / ``pev_backbone_bwd``)."""
+        n_out = self._run(self.n_offset_head, h, True)               # [N,4]: 4th channel unused in the reference too
+        c_out = self._run(self.c_offset_head, h, True)
+        return _Backbone.apply(n_out[:, :3], c_out[:, :3], x_ca, g.starts)
 
 
 class SE3EquivariantDecoder(nn.Module):

@@ -9,6 +9,7 @@
 #include "../../include/pev_b200.h"
 #include "../../protein_ensemble_vae_b200/csrc/pev_egnn_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_kabsch_body.cuh"
+#include "../../protein_ensemble_vae_b200/csrc/pev_backbone_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_data_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_metrics_body.cuh"
 #include "../../protein_ensemble_vae_b200/csrc/pev_pdb_body.cuh"
@@ -333,6 +334,19 @@ int pev_unpack_center(const float* n, const float* ca, const float* c, const flo
           o_emb[((int64_t)b * Lmax + l) * D + d] = l < L ? emb[((int64_t)cu[b] + l) * D + d] : 0.f;
     }
   }
+  return 0;
+}
+
+int pev_backbone_fwd(const float* n_dir, int32_t ldn, const float* c_dir, int32_t ldc, const float* x_ca, const uint8_t* starts,
+                     int64_t N, float* x_n, float* x_c, void*) {
+  for (int64_t k = 0; k < N; ++k) backbone_fwd_residue(n_dir, ldn, c_dir, ldc, x_ca, starts, N, k, x_n, x_c);
+  return 0;
+}
+
+int pev_backbone_bwd(const float* n_dir, int32_t ldn, const float* c_dir, int32_t ldc, const float* x_ca, const uint8_t* starts,
+                     int64_t N, const float* g_xn, const float* g_xc, float* g_ndir, float* g_cdir, float* g_xca, void*) {
+  for (int64_t k = 0; k < N; ++k)
+    backbone_bwd_residue(n_dir, ldn, c_dir, ldc, x_ca, starts, N, k, g_xn, g_xc, g_ndir, g_cdir, g_xca);
   return 0;
 }
 
