@@ -351,6 +351,15 @@ int pev_attn_gemm(int32_t form, const float* A, int64_t lda, int32_t a_col0, con
                   int32_t Lpad, int64_t N, float scale, float* out, int64_t ldo, int32_t out_col0, void* stream);
 int pev_attn_softmax(int32_t backward, float* S, float* G, const int32_t* tile_conf, const int32_t* cu, const int32_t* cup,
                      int32_t m_tiles, int32_t H, int32_t Lpad, float p_drop, uint32_t seed, void* stream);
+/* Form 0 with the softmax fused into the GEMM epilogue (the scores never reach HBM): mode 1 (Lpad <= 256) out = probabilities,
+ * out2 = dropout-kept probabilities / (1 - p_drop) or NULL; mode 2 (A = dO, B = V) out = dS = P (keep dP / (1 - p_drop) -
+ * delta) with delta[h Np + padded row] = <dO, O> of that row and head (pev_attn_delta; row_pad[i] = padded row of packed row i). */
+int pev_attn_scores(int32_t mode, const float* A, int64_t lda, int32_t a_col0, const float* B, int64_t ldb, int32_t b_col0,
+                    const int32_t* tile_conf, const int32_t* cu, const int32_t* cup, int32_t m_tiles, int32_t H, int32_t hd,
+                    int32_t Lpad, int64_t N, float scale, float* out, float* out2, const float* P, const float* delta,
+                    float p_drop, uint32_t seed, void* stream);
+int pev_attn_delta(const float* dO, const float* O, int64_t N, int32_t H, int32_t hd, const int32_t* row_pad, int64_t Np,
+                   float* delta, void* stream);
 
 /* ---------------------------------------------------------------- ragged packed batches (csrc/data_kernels.cu)
  * Device-side replacement for the host centring + zero-padding of models/data.py (:166-172, :219-266): the packed rows of

@@ -85,6 +85,9 @@ _PROTOS_TC = {
     "pev_node_wgrad_workspace_bytes": (c_int64, []),
     "pev_node_wgrad": (c_int32, [_P, _I, _P, _L, c_float, _P, _P, _I, _P]),
     "pev_attn_gemm": (c_int32, [_I, _P, _L, _I, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _L, c_float, _P, _L, _I, _P]),
+    "pev_attn_scores": (c_int32, [_I, _P, _L, _I, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _L, c_float, _P, _P, _P, _P, c_float,
+                                  c_uint32, _P]),
+    "pev_attn_delta": (c_int32, [_P, _P, _L, _I, _I, _P, _L, _P, _P]),
     "pev_attn_softmax": (c_int32, [_I, _P, _P, _P, _P, _P, _I, _I, _I, c_float, c_uint32, _P]),
     "pev_linear": (c_int32, [_I, _P, _L, _I, _P, _P, _L, _I, _I, c_float, c_uint32, _P, _L, _P, _L, _P]),
     "pev_transpose": (c_int32, [_P, _I, _I, c_float, _P, _P]),

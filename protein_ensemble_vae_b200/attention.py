@@ -40,6 +40,9 @@ def _tables(pk):
             cup.append(cup[-1] + 128 * tiles)
         t = pk._attn_tables = (torch.tensor(conf, dtype=torch.int32, device=dev), torch.tensor(cup, dtype=torch.int32, device=dev),
                                len(conf), max(32, (pk.lmax + 31) // 32 * 32))
+        n = torch.arange(pk.N, device=dev)
+        cu64, cup64 = pk.cu.long(), t[1].long()
+        pk._row_pad = (cup64.index_select(0, pk.conf) + (n - cu64.index_select(0, pk.conf))).to(torch.int32)   # padded row of row i
     return t
 
 
@@ -49,6 +52,16 @@ def _gemm(form, A, a_col0, Bm, b_col0, pk, H, hd, scale, out, out_col0=0):
     tile_conf, cup, m_tiles, Lpad = _tables(pk)
     _lib.lib().call("pev_attn_gemm", form, ptr(A), A.shape[-1], a_col0, ptr(Bm), Bm.shape[-1], b_col0, ptr(tile_conf), ptr(pk.cu),
                     ptr(cup), m_tiles, H, hd, Lpad, pk.N, float(scale), ptr(out), out.shape[-1], out_col0, stream(out))
+
+
+def _scores(mode, A, a_col0, Bm, b_col0, pk, H, hd, scale, out, out2=None, P=None, delta=None, p_drop=0.0, seed=0):
+    """NT GEMM with the softmax (mode 1) or its backward (mode 2) fused into the epilogue (``pev_attn_scores``)."""
+    from . import _lib
+    from ._lib import ptr, stream
+    tile_conf, cup, m_tiles, Lpad = _tables(pk)
+    _lib.lib().call("pev_attn_scores", mode, ptr(A), A.shape[-1], a_col0, ptr(Bm), Bm.shape[-1], b_col0, ptr(tile_conf), ptr(pk.cu),
+                    ptr(cup), m_tiles, H, hd, Lpad, pk.N, float(scale), ptr(out), ptr(out2), ptr(P), ptr(delta), float(p_drop),
+                    int(seed), stream(out))
 
 
 def _softmax(backward, S, G, pk, H, p_drop, seed):
@@ -75,18 +88,21 @@ class PackedSelfAttention(torch.autograd.Function):
         seed = (torch.initial_seed() * 2654435761 + _COUNTER[0] * 40503) & 0xFFFFFFFF
         with torch.cuda.device_of(qkv):
             P = torch.empty(nheads, m_tiles * 128, Lpad, dtype=torch.float32, device=qkv.device)
-            _gemm(NT, qkv, 0, qkv, d, pk, nheads, hd, 1.0 / math.sqrt(hd), P)
             Pd = torch.empty_like(P) if p_drop > 0 else None
-            _softmax(0, P, Pd, pk, nheads, p_drop, seed)
+            if Lpad <= 256:          # whole score rows fit one key tile: softmax in the GEMM epilogue, S never reaches HBM
+                _scores(1, qkv, 0, qkv, d, pk, nheads, hd, 1.0 / math.sqrt(hd), P, out2=Pd, p_drop=p_drop, seed=seed)
+            else:
+                _gemm(NT, qkv, 0, qkv, d, pk, nheads, hd, 1.0 / math.sqrt(hd), P)
+                _softmax(0, P, Pd, pk, nheads, p_drop, seed)
             out = torch.empty(N, d, dtype=torch.float32, device=qkv.device)
             _gemm(NN, Pd if Pd is not None else P, 0, qkv, 2 * d, pk, nheads, hd, 1.0, out)
         ctx.pk, ctx.nheads, ctx.p_drop, ctx.seed = pk, nheads, p_drop, seed
-        ctx.save_for_backward(qkv, P, Pd)
+        ctx.save_for_backward(qkv, P, Pd, out)
         return out
 
     @staticmethod
     def backward(ctx, go):
-        qkv, P, Pd = ctx.saved_tensors
+        qkv, P, Pd, out = ctx.saved_tensors
         pk, H = ctx.pk, ctx.nheads
         go = go.float().contiguous()
         N, d3 = qkv.shape
@@ -97,8 +113,12 @@ class PackedSelfAttention(torch.autograd.Function):
             gqkv = torch.empty_like(qkv)
             _gemm(TN, Pd if Pd is not None else P, 0, go, 0, pk, H, hd, 1.0, gqkv, 2 * d)          # dV = P^T dO
             G = torch.empty_like(P)
-            _gemm(NT, go, 0, qkv, 2 * d, pk, H, hd, 1.0, G)                                        # dP = dO V^T
-            _softmax(1, P, G, pk, H, ctx.p_drop, ctx.seed)                                         # G := dS
+            # dS = P (keep dP / (1 - p) - delta) in the epilogue of dP = dO V^T, delta_i = <dO_i, O_i> per head
+            from . import _lib
+            from ._lib import ptr, stream
+            delta = torch.empty(H, P.shape[1], dtype=torch.float32, device=qkv.device)
+            _lib.lib().call("pev_attn_delta", ptr(go), ptr(out), N, H, hd, ptr(pk._row_pad), P.shape[1], ptr(delta), stream(go))
+            _scores(2, go, 0, qkv, 2 * d, pk, H, hd, 1.0, G, P=P, delta=delta, p_drop=ctx.p_drop, seed=ctx.seed)
             _gemm(NN, G, 0, qkv, d, pk, H, hd, sc, gqkv, 0)                                        # dQ = scale dS K
             _gemm(TN, G, 0, qkv, 0, pk, H, hd, sc, gqkv, d)                                        # dK = scale dS^T Q
         return gqkv, None, None, None

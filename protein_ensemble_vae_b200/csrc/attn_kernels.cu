@@ -33,7 +33,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BOX = 32 * 128;                    // [32 rows][32 floats]
 constexpr int STG_OFF = STAGES * STAGE_BYTES;
 constexpr int BAR_OFF = STG_OFF + 8 * 4096;
-constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+constexpr int EX_OFF = BAR_OFF + 256;            // [2 column halves][128 rows] row statistics of the fused softmax
+constexpr int SMEM_BYTES = EX_OFF + 1024 + 1024;
 constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
 constexpr int THREADS = 32 * 10;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -51,6 +52,15 @@ struct Params {
   float* out;
   int64_t ldo;
   int out_col0;
+  // NT only.  mode 1: softmax fused into the epilogue (needs Lpad <= 256: one key tile per row): out = probabilities, out2 =
+  // dropout-kept probabilities / (1 - p) or null.  mode 2: softmax backward fused: out = dS = P (keep dP / (1 - p) - delta),
+  // P = stored probabilities, delta[h Np + padded row] = <dO, O> of that row and head.
+  int mode;
+  float* out2;
+  const float* P;
+  const float* delta;
+  uint32_t drop_thresh, drop_seed;
+  float drop_scale;
 };
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
@@ -82,6 +92,20 @@ __device__ __forceinline__ void store_block32(float* stg, const float (&v)[32], 
     const float4 x = *reinterpret_cast<const float4*>(stg + row * 32 + ((ch ^ (row & 7)) << 2));
     if (row < rows_valid) *reinterpret_cast<float4*>(gbase + row * ld + 4 * ch) = x;
   }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {      // counter-based dropout bits (lowbias32 integer hash)
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool keep_bit(uint32_t seed, int64_t idx, uint32_t thresh) {
+  if (thresh == 0u) return true;                             // no dropout: no hashing (the row kernels are issue-bound on it)
+  return mix32(seed + (uint32_t)idx * 0x9e3779b9U + (uint32_t)(idx >> 32)) >= thresh;
 }
 
 // One tile = (head, 128-row tile of the padded layout[, 256-column tile of the scores]); every role walks the same list.
@@ -234,16 +258,102 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
         rows_valid = left < 0 ? 0 : (left > 32 ? 32 : left);
       }
       const int nblk = half / 32;
+      if (FORM == NT && p.mode == 1) {
+        // ---- softmax of the whole score row in the epilogue: the two warps of a lane quarter hold 128 columns each
+        const int r = T.m0 + q * 32 + lane;
+        const bool rv = r < T.Lb;
+        const int64_t prow = T.prow + q * 32 + lane;
+        float* ex = reinterpret_cast<float*>(smem + EX_OFF);
+        float* mine = ex + hh * BM + q * 32 + lane;
+        const float* other = ex + (hh ^ 1) * BM + q * 32 + lane;
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int b = 0; b < nblk; ++b) {
-        uint32_t raw[32];
-        tmem_ld32_issue(taddr + 32 * b, raw);
-        tmem_wait();
-        float val[32];
+        for (int b = 0; b < nblk; ++b) {
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          tmem_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = p.scale * __uint_as_float(raw[j]);
-        const bool in_range = FORM != NT || (T.n0 + hh * half + 32 * b) < p.Lpad;
-        if (in_range) store_block32(stg, val, obase + 32 * b, ld, rows_valid, lane);
+          for (int j = 0; j < 32; ++j)
+            if (hh * half + 32 * b + j < T.Lb) mx = fmaxf(mx, p.scale * __uint_as_float(raw[j]));
+        }
+        *mine = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        mx = fmaxf(mx, *other);
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        float sum = 0.f;
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          tmem_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (hh * half + 32 * b + j < T.Lb) sum += __expf(p.scale * __uint_as_float(raw[j]) - mx);
+        }
+        *mine = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        sum = hh == 0 ? sum + *other : *other + sum;            // the same order in both halves
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        const float inv = 1.0f / sum;
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+          const int c0 = hh * half + 32 * b;
+          if (c0 >= p.Lpad) break;
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          tmem_wait();
+          float val[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            val[j] = (rv && c0 + j < T.Lb) ? __expf(p.scale * __uint_as_float(raw[j]) - mx) * inv : 0.f;
+          store_block32(stg, val, obase + 32 * b, ld, 32, lane);
+          if (p.out2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              val[j] = keep_bit(p.drop_seed, prow * p.Lpad + c0 + j, p.drop_thresh) ? val[j] * p.drop_scale : 0.f;
+            store_block32(stg, val, p.out2 + (obase - p.out) + 32 * b, ld, 32, lane);
+          }
+        }
+      } else if (FORM == NT && p.mode == 2) {
+        // ---- softmax backward in the epilogue: dS = P (keep dP / (1 - p) - delta)
+        const int r = T.m0 + q * 32 + lane;
+        const bool rv = r < T.Lb;
+        const int64_t prow = T.prow + q * 32 + lane;
+        const float dl = p.delta[prow];
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+          const int c0 = T.n0 + hh * half + 32 * b;
+          if (c0 >= p.Lpad) break;
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          float pv[32];
+          const float* prw = p.P + prow * p.Lpad + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 v = *reinterpret_cast<const float4*>(prw + 4 * j4);
+            pv[4 * j4] = v.x; pv[4 * j4 + 1] = v.y; pv[4 * j4 + 2] = v.z; pv[4 * j4 + 3] = v.w;
+          }
+          tmem_wait();
+          float val[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float g = keep_bit(p.drop_seed, prow * p.Lpad + c0 + j, p.drop_thresh) ? __uint_as_float(raw[j]) * p.drop_scale : 0.f;
+            val[j] = (rv && c0 + j < T.Lb) ? pv[j] * (g - dl) : 0.f;
+          }
+          store_block32(stg, val, obase + 32 * b, ld, 32, lane);
+        }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+          uint32_t raw[32];
+          tmem_ld32_issue(taddr + 32 * b, raw);
+          tmem_wait();
+          float val[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = p.scale * __uint_as_float(raw[j]);
+          const bool in_range = FORM != NT || (T.n0 + hh * half + 32 * b) < p.Lpad;
+          if (in_range) store_block32(stg, val, obase + 32 * b, ld, rows_valid, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -260,20 +370,6 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
 }
 
 // ---------------------------------------------------------------------------------------------------- row kernels
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {      // counter-based dropout bits (lowbias32 integer hash)
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ bool keep_bit(uint32_t seed, int64_t idx, uint32_t thresh) {
-  if (thresh == 0u) return true;                             // no dropout: no hashing (the row kernels are issue-bound on it)
-  return mix32(seed + (uint32_t)idx * 0x9e3779b9U + (uint32_t)(idx >> 32)) >= thresh;
-}
-
 // One warp per (head, padded row): softmax over the keys of the row's conformer, zeros elsewhere; with dropout the kept and
 // rescaled probabilities go to Pd (the operand of the P V GEMM), the plain ones stay in S (needed by the backward pass).
 __global__ void __launch_bounds__(256)
@@ -403,6 +499,25 @@ softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ G, const int
   }
 }
 
+// delta[h Np + padded row of i] = sum_c dO[i, h hd + c] O[i, h hd + c]  (= sum_j P_ij dP_ij, with or without dropout)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const float* __restrict__ dO, const float* __restrict__ O, int64_t N, int H, int hd,
+                  const int32_t* __restrict__ row_pad, int64_t Np, float* __restrict__ delta) {
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const int d = H * hd;
+  const float* a = dO + i * d;
+  const float* b = O + i * d;
+  const int64_t rp = row_pad[i];
+  for (int h = 0; h < H; ++h) {
+    float s = 0.f;
+    for (int c = lane; c < hd; c += 32) s = fmaf(a[h * hd + c], b[h * hd + c], s);
+    s = warp_sum(s);
+    if (lane == 0) delta[(int64_t)h * Np + rp] = s;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -493,4 +608,38 @@ extern "C" int pev_attn_softmax(int32_t backward, float* S, float* G, const int3
   if (backward) at::softmax_bwd_kernel<<<grid, 256, 0, st>>>(S, G, tile_conf, cu, cup, Np, H, Lpad, p_drop, seed);
   else at::softmax_fwd_kernel<<<grid, 256, 0, st>>>(S, G, tile_conf, cu, cup, Np, H, Lpad, p_drop, seed);
   return after_launch("attn_softmax_kernel");
+}
+
+// Scores with a fused epilogue (form NT): mode 1 -- out = softmax probabilities (requires Lpad <= 256), out2 = dropout-kept
+// probabilities / (1 - p_drop) or NULL; mode 2 -- A = dO, B = V: out = dS = P (keep dP / (1 - p_drop) - delta).
+extern "C" int pev_attn_scores(int32_t mode, const float* A, int64_t lda, int32_t a_col0, const float* Bm, int64_t ldb,
+                               int32_t b_col0, const int32_t* tile_conf, const int32_t* cu, const int32_t* cup, int32_t m_tiles,
+                               int32_t H, int32_t hd, int32_t Lpad, int64_t N, float scale, float* out, float* out2, const float* P,
+                               const float* delta, float p_drop, uint32_t seed, void* stream) {
+  PEV_REQUIRE(A && Bm && tile_conf && cu && cup && out && (mode == 1 || mode == 2), "bad argument");
+  PEV_REQUIRE((hd == 64 || hd == 128) && Lpad > 0 && Lpad % 32 == 0 && m_tiles >= 0 && H > 0 && lda % 4 == 0 && ldb % 4 == 0,
+              "shape: head dim 64 or 128, Lpad a multiple of 32");
+  PEV_REQUIRE(mode != 1 || Lpad <= 256, "the fused softmax needs the whole row in one key tile (Lpad <= 256)");
+  PEV_REQUIRE(mode != 2 || (P && delta), "mode 2 needs P and delta");
+  PEV_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "p_drop in [0, 1)");
+  if (m_tiles == 0 || N == 0) return 0;
+  at::Params p = {};
+  p.tile_conf = tile_conf; p.cu = cu; p.cup = cup; p.m_tiles = m_tiles; p.H = H; p.hd = hd; p.Lpad = Lpad;
+  p.Np = (int64_t)m_tiles * at::BM; p.a_col0 = a_col0; p.b_col0 = b_col0; p.scale = scale; p.out = out;
+  p.mode = mode; p.out2 = out2; p.P = P; p.delta = delta;
+  p.drop_thresh = p_drop > 0.f ? (uint32_t)(p_drop * 4294967296.0) : 0u;
+  p.drop_seed = seed;
+  p.drop_scale = 1.0f / (1.0f - p_drop);
+  alignas(64) CUtensorMap mA, mB;
+  if (int rc = at::make_map(A, N, lda, lda, at::BM, false, &mA)) return rc;
+  if (int rc = at::make_map(Bm, N, ldb, ldb, 256, false, &mB)) return rc;
+  return at::launch<at::NT>(p, mA, mB, as_stream(stream));
+}
+
+extern "C" int pev_attn_delta(const float* dO, const float* O, int64_t N, int32_t H, int32_t hd, const int32_t* row_pad,
+                              int64_t Np, float* delta, void* stream) {
+  PEV_REQUIRE(dO && O && row_pad && delta && N >= 0 && H > 0 && hd > 0, "bad argument");
+  if (N == 0) return 0;
+  at::attn_delta_kernel<<<(unsigned)((N + 7) / 8), 256, 0, as_stream(stream)>>>(dO, O, N, H, hd, row_pad, Np, delta);
+  return after_launch("attn_delta_kernel");
 }
