@@ -11,8 +11,11 @@
 // M tile never straddles two conformers) and written as zeros there and beyond the conformer's length, which is what
 // makes the ragged edges safe: a K-chunk that runs past a conformer's end multiplies finite foreign rows by exact zeros.
 // Tiles: 128 rows x (256 | hd) columns, K-chunks of 32, operands by TMA (K-major SWIZZLE_128B; MN-major operands in the
-// 32-bit layout SWIZZLE_128B_BASE32B, see node_gemm_kernels.cu), 4-stage ring, two TMEM accumulator stages, 8 epilogue
-// warps.  The scores cross HBM (4 passes of H N L floats per layer and direction): a first, unfused form.
+// 32-bit layout SWIZZLE_128B_BASE32B, see node_gemm_kernels.cu), 3-stage ring, two TMEM accumulator stages, 16 epilogue
+// warps (lane quarter x 4 column groups).  The softmax and its backward run inside the epilogues of the two NT GEMMs (row
+// statistics exchanged through shared memory; dS = P (dP - <dO, O>) needs no row pass at all), so raw scores and dP never
+// reach HBM: per layer the probability buffer is written once and read three times, the dS buffer written once and read twice.
+// Rows longer than 256 keys fall back to the separate softmax kernel in the forward pass.
 #include <cuda.h>
 
 #include <cstring>
@@ -26,17 +29,17 @@ namespace at {
 using namespace tcx;
 
 constexpr int BM = 128, BK = 32;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 4;             // 16 KB
 constexpr int B_BYTES = 256 * BK * 4;            // 32 KB (NT); NN / TN use hd / 32 boxes of 4 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BOX = 32 * 128;                    // [32 rows][32 floats]
 constexpr int STG_OFF = STAGES * STAGE_BYTES;
-constexpr int BAR_OFF = STG_OFF + 8 * 4096;
-constexpr int EX_OFF = BAR_OFF + 256;            // [2 column halves][128 rows] row statistics of the fused softmax
-constexpr int SMEM_BYTES = EX_OFF + 1024 + 1024;
-constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
-constexpr int THREADS = 32 * 10;
+constexpr int BAR_OFF = STG_OFF + 16 * 4096;
+constexpr int EX_OFF = BAR_OFF + 256;            // [4 column groups][128 rows] row statistics of the fused softmax
+constexpr int SMEM_BYTES = EX_OFF + 2048 + 1024;
+constexpr int EPI_WARPS = 16, TMA_WARP = 16, MMA_WARP = 17;     // 16 epilogue warps: lane quarter x 4 column groups
+constexpr int THREADS = 32 * 18;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 enum Form { NT = 0, NN = 1, TN = 2 };
@@ -232,10 +235,10 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
     }
     __syncwarp();
   } else {
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;                  // TMEM lane quarter; 32-column blocks cq, cq + 4, ...
     float* stg = reinterpret_cast<float*>(smem + STG_OFF) + warp * 1024;
     const int ncols = FORM == NT ? 256 : p.hd;               // accumulator columns in use
-    const int half = ncols / 2;                              // this warp's share: [hh * half, (hh + 1) * half)
+    const int nblocks = ncols / 32;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const Tile T = get_tile<FORM>(p, t, n_tiles);
@@ -243,61 +246,60 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
       const int acc = it & 1;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + hh * half);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       float* obase;
       int64_t ld;
       int rows_valid;
       if (FORM == NT) {
-        obase = p.out + (T.prow + q * 32) * p.Lpad + T.n0 + hh * half;
+        obase = p.out + (T.prow + q * 32) * p.Lpad + T.n0;
         ld = p.Lpad;
         rows_valid = 32;
       } else {
-        obase = p.out + (T.arow + T.m0 + q * 32) * p.ldo + p.out_col0 + T.h * p.hd + hh * half;
+        obase = p.out + (T.arow + T.m0 + q * 32) * p.ldo + p.out_col0 + T.h * p.hd;
         ld = p.ldo;
         const int left = T.Lb - T.m0 - q * 32;
         rows_valid = left < 0 ? 0 : (left > 32 ? 32 : left);
       }
-      const int nblk = half / 32;
       if (FORM == NT && p.mode == 1) {
-        // ---- softmax of the whole score row in the epilogue: the two warps of a lane quarter hold 128 columns each
+        // ---- softmax of the whole score row in the epilogue: the four warps of a lane quarter hold 64 columns each
         const int r = T.m0 + q * 32 + lane;
         const bool rv = r < T.Lb;
         const int64_t prow = T.prow + q * 32 + lane;
         float* ex = reinterpret_cast<float*>(smem + EX_OFF);
-        float* mine = ex + hh * BM + q * 32 + lane;
-        const float* other = ex + (hh ^ 1) * BM + q * 32 + lane;
+        float* mine = ex + cq * BM + q * 32 + lane;
+        const float* col = ex + q * 32 + lane;                 // + g * BM: the value of column group g
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int b = 0; b < nblk; ++b) {
+        for (int b = cq; b < nblocks; b += 4) {
           uint32_t raw[32];
           tmem_ld32_issue(taddr + 32 * b, raw);
           tmem_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (hh * half + 32 * b + j < T.Lb) mx = fmaxf(mx, p.scale * __uint_as_float(raw[j]));
+            if (32 * b + j < T.Lb) mx = fmaxf(mx, p.scale * __uint_as_float(raw[j]));
         }
         *mine = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-        mx = fmaxf(mx, *other);
-        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
+        mx = fmaxf(fmaxf(col[0], col[BM]), fmaxf(col[2 * BM], col[3 * BM]));
+        asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
         float sum = 0.f;
 #pragma unroll 1
-        for (int b = 0; b < nblk; ++b) {
+        for (int b = cq; b < nblocks; b += 4) {
           uint32_t raw[32];
           tmem_ld32_issue(taddr + 32 * b, raw);
           tmem_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (hh * half + 32 * b + j < T.Lb) sum += __expf(p.scale * __uint_as_float(raw[j]) - mx);
+            if (32 * b + j < T.Lb) sum += __expf(p.scale * __uint_as_float(raw[j]) - mx);
         }
         *mine = sum;
-        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-        sum = hh == 0 ? sum + *other : *other + sum;            // the same order in both halves
-        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
+        sum = (col[0] + col[BM]) + (col[2 * BM] + col[3 * BM]);   // the same order in all four warps
+        asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
         const float inv = 1.0f / sum;
 #pragma unroll 1
-        for (int b = 0; b < nblk; ++b) {
-          const int c0 = hh * half + 32 * b;
+        for (int b = cq; b < nblocks; b += 4) {
+          const int c0 = 32 * b;
           if (c0 >= p.Lpad) break;
           uint32_t raw[32];
           tmem_ld32_issue(taddr + 32 * b, raw);
@@ -306,12 +308,12 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             val[j] = (rv && c0 + j < T.Lb) ? __expf(p.scale * __uint_as_float(raw[j]) - mx) * inv : 0.f;
-          store_block32(stg, val, obase + 32 * b, ld, 32, lane);
+          store_block32(stg, val, obase + c0, ld, 32, lane);
           if (p.out2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               val[j] = keep_bit(p.drop_seed, prow * p.Lpad + c0 + j, p.drop_thresh) ? val[j] * p.drop_scale : 0.f;
-            store_block32(stg, val, p.out2 + (obase - p.out) + 32 * b, ld, 32, lane);
+            store_block32(stg, val, p.out2 + (obase - p.out) + c0, ld, 32, lane);
           }
         }
       } else if (FORM == NT && p.mode == 2) {
@@ -321,8 +323,8 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
         const int64_t prow = T.prow + q * 32 + lane;
         const float dl = p.delta[prow];
 #pragma unroll 1
-        for (int b = 0; b < nblk; ++b) {
-          const int c0 = T.n0 + hh * half + 32 * b;
+        for (int b = cq; b < nblocks; b += 4) {
+          const int c0 = T.n0 + 32 * b;
           if (c0 >= p.Lpad) break;
           uint32_t raw[32];
           tmem_ld32_issue(taddr + 32 * b, raw);
@@ -344,14 +346,14 @@ attn_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA, const
         }
       } else {
 #pragma unroll 1
-        for (int b = 0; b < nblk; ++b) {
+        for (int b = cq; b < nblocks; b += 4) {
           uint32_t raw[32];
           tmem_ld32_issue(taddr + 32 * b, raw);
           tmem_wait();
           float val[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) val[j] = p.scale * __uint_as_float(raw[j]);
-          const bool in_range = FORM != NT || (T.n0 + hh * half + 32 * b) < p.Lpad;
+          const bool in_range = FORM != NT || (T.n0 + 32 * b) < p.Lpad;
           if (in_range) store_block32(stg, val, obase + 32 * b, ld, rows_valid, lane);
         }
       }
