@@ -112,3 +112,40 @@ def test_encoder_matches_reference(tag, precision, tol_out):
         assert worst < max(2e-2, 6.0 * yard[-1]) and median < max(1e-2, 3.0 * yard[len(yard) // 2]), (worst, median, yard[-1], yard[len(yard) // 2])
         print(tag, "yardstick worst %.1e median %.1e" % (yard[-1], yard[len(yard) // 2]))
     print(tag, precision, "outputs", {k: f"{v:.1e}" for k, v in errs.items()}, "grad l2 worst %.1e median %.1e" % (worst, median))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_encoder_edge_cases(precision):
+    """mask=None equals an all-ones mask; a conformer without valid residues and a single-residue conformer run (the reference
+    returns NaN for the former: softmax over an empty key set) and do not disturb the other conformers of the batch."""
+    from protein_ensemble_vae_b200.encoder import ProteinEncoder
+    torch.manual_seed(7)
+    enc = ProteinEncoder(seqemb_dim=256, nlayers=2, dropout=0.0, precision=precision).cuda().eval()
+    B, L = 4, 40
+    g = torch.Generator(device="cuda").manual_seed(8)
+    emb = torch.randn(B, L, 256, device="cuda", generator=g)
+    ca = torch.cumsum(torch.randn(B, L, 3, device="cuda", generator=g) * 2.2, 1)
+    n, c = ca + 0.5, ca - 0.5
+    dih = torch.randn(B, L, 6, device="cuda", generator=g).clamp(-1, 1)
+    eg, el = torch.zeros(B, 512, device="cuda"), torch.zeros(B, L, 256, device="cuda")
+    with torch.no_grad():
+        full = enc(emb, n, ca, c, dih, None, eps_g=eg, eps_l=el)
+        ones = enc(emb, n, ca, c, dih, torch.ones(B, L, device="cuda"), eps_g=eg, eps_l=el)
+        for a, b in zip(full, ones):
+            assert torch.equal(a, b)
+        mask = torch.ones(B, L, device="cuda")
+        mask[1] = 0                                           # empty conformer
+        mask[2, 1:] = 0                                       # one residue
+        mask[3, 25:] = 0
+        out = enc(emb, n, ca, c, dih, mask, eps_g=eg, eps_l=el)
+        assert all(torch.isfinite(t).all() for t in out)
+        assert float(out[4][1].abs().max()) == 0.0 and float(out[4][2, 1:].abs().max()) == 0.0      # mu_l zeros at padding
+        # conformer 0 (full length) is unaffected by what happens to its batch neighbours
+        tol = 1e-5 if precision == "fp32" else 2e-3
+        assert float((out[4][0] - full[4][0]).abs().max()) < tol * float(full[4][0].abs().max())
+        assert float((out[2][0] - full[2][0]).abs().max()) < tol * float(full[2][0].abs().max())
+        # conformer 3 alone (cropped to its 25 residues) gives the same latents as inside the ragged batch
+        solo = enc(emb[3:4, :25], n[3:4, :25], ca[3:4, :25], c[3:4, :25], dih[3:4, :25], None, eps_g=eg[:1], eps_l=el[:1, :25])
+        assert float((solo[4][0] - out[4][3, :25]).abs().max()) < tol * float(solo[4].abs().max())
+        assert float((solo[2][0] - out[2][3]).abs().max()) < tol * float(solo[2].abs().max())
