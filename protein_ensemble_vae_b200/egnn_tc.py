@@ -264,9 +264,9 @@ class NodePhiH(torch.autograd.Function):
             _lib.lib().call("pev_layernorm_bwd", ptr(gy), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), N, D,
                             ptr(node_workspace(r.device)), ptr(gr), ptr(dgb), ptr(dgb[D:]), stream(r))
         gp = node_gemm(EPI_DSILU, gr, transposed(W4), aux=p)[0]                   # (gr W4) * silu'(p)
-        gha = node_gemm(EPI_PLAIN, gp, transposed(W3))[0]                         # [N,512] = [dL/dh (phi_h part) | dL/dagg]
-        gh = gr + gha[:, :D]
-        gagg = gha[:, D:]
+        W3t = transposed(W3)                                                      # [512, 256]: rows = [h part ; agg part]
+        gh = node_gemm(EPI_PLAIN, gp, W3t[:D], aux=gr)[0]                          # dL/dh = gr + gp W3[:, :D]  (residual in the epilogue)
+        gagg = node_gemm(EPI_PLAIN, gp, W3t[D:])[0]                               # dL/dagg, contiguous for the edge kernels
         gW4 = node_wgrad(gr, q)
         gW3 = torch.empty(D, 2 * D, dtype=torch.float32, device=r.device)
         node_wgrad(gp, h, out=gW3[:, :D])
