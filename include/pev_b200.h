@@ -324,8 +324,8 @@ int pev_node_wgrad3(const float* G, int32_t Mo, const float* X, int64_t N, float
  * hash of (seed, row * Nout + col) (p_drop = 0: none); A / res / out may be column blocks of wider row-major
  * tensors (lda / ldres / ldc, multiples of 4).  precise = 0: TF32, W fp32 [Nout,K], Nout a multiple of 256; precise = 1:
  * 3xTF32, W = pev_split_tf32 image [2 Nout, K], Nout a multiple of 128.  K a multiple of 32.
- * pev_linear_wgrad: out[Mo,Kx] (leading dimension ldc) = scale * G^T X for G [N,Mo] (ldg) and X [N,Kx] (ldx), Mo and Kx
- * multiples of 256 with (Mo / 256)(Kx / 256) <= the SM count, in one launch; workspace of pev_node_wgrad_workspace_bytes(). */
+ * pev_linear_wgrad: out[Mo,Kx] (leading dimension ldc) = scale * G^T X for G [N,Mo] (ldg) and X [N,Kx] (ldx), Mo a multiple
+ * of 128, Kx of 256, with ceil(Mo / 256)(Kx / 256) <= the SM count, in one launch; workspace of pev_node_wgrad_workspace_bytes(). */
 int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t K, const float* W, const float* bias, int64_t M,
                int32_t Nout, int32_t relu, float p_drop, uint32_t seed, const float* res, int64_t ldres, float* out, int64_t ldc,
                void* stream);

@@ -933,7 +933,7 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int rows, int c
 // out block (bg, bx) [256 x 256] (leading dimension ldc) = scale * sum over slices (fixed order) of the per-CTA partials
 __global__ void __launch_bounds__(256)
 wgrad_blocks_reduce_kernel(const float* __restrict__ partial, int slices, int nball, int nbx, float scale, float* __restrict__ out,
-                           int64_t ldc) {
+                           int64_t ldc, int rows_total) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)nball * 16384) return;
   const int blk = (int)(idx >> 14), e = (int)(idx & 16383);
@@ -944,6 +944,7 @@ wgrad_blocks_reduce_kernel(const float* __restrict__ partial, int slices, int nb
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   const int r = e >> 6, c4 = e & 63;
+  if ((blk / nbx) * 256 + r >= rows_total) return;           // Mo = 128 (mod 256): the last row block is half empty
   float* dst = out + ((int64_t)(blk / nbx) * 256 + r) * ldc + (blk % nbx) * 256 + 4 * c4;
   *reinterpret_cast<float4*>(dst) = make_float4(scale * acc.x, scale * acc.y, scale * acc.z, scale * acc.w);
 }
@@ -1142,10 +1143,10 @@ extern "C" int pev_linear(int32_t precise, const float* A, int64_t lda, int32_t 
 // concurrently (the CTAs that share a row slice of G or X meet in L2: HBM sees each operand once), one fixed-order reduction.
 extern "C" int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, int32_t Mo, const float* X, int64_t ldx, int32_t Kx,
                                 int64_t N, float scale, float* workspace, float* out, int64_t ldc, void* stream) {
-  PEV_REQUIRE(G && X && out && workspace && N >= 0 && Mo > 0 && Mo % 256 == 0 && Kx > 0 && Kx % 256 == 0 && ldc >= Kx &&
+  PEV_REQUIRE(G && X && out && workspace && N >= 0 && Mo > 0 && Mo % 128 == 0 && Kx > 0 && Kx % 256 == 0 && ldc >= Kx &&
               ldg >= Mo && ldx >= Kx && ldg % 4 == 0 && ldx % 4 == 0 && ldc % 4 == 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  const int nbg = Mo / 256, nbx = Kx / 256, nball = nbg * nbx;
+  const int nbg = (Mo + 255) / 256, nbx = Kx / 256, nball = nbg * nbx;   // columns of G past Mo are zero-filled by TMA
   PEV_REQUIRE(nball <= sm_count(), "too many output blocks for one launch");
   if (N == 0) {
     for (int r = 0; r < Mo; ++r) cudaMemsetAsync(out + (int64_t)r * ldc, 0, sizeof(float) * Kx, st);
@@ -1173,6 +1174,6 @@ extern "C" int pev_linear_wgrad(int32_t precise, const float* G, int64_t ldg, in
   if (precise) ng::node_wgrad3_kernel<<<slices * nball, ng::w3::THREADS, ng::w3::SMEM, st>>>(p, mG, mX);
   else ng::node_wgrad_kernel<<<slices * nball, ng::W_THREADS, ng::W_SMEM, st>>>(p, mG, mX);
   if (int rc = after_launch("node_wgrad_kernel")) return rc;
-  ng::wgrad_blocks_reduce_kernel<<<(nball * 16384 + 255) / 256, 256, 0, st>>>(workspace, slices, nball, nbx, scale, out, ldc);
+  ng::wgrad_blocks_reduce_kernel<<<(nball * 16384 + 255) / 256, 256, 0, st>>>(workspace, slices, nball, nbx, scale, out, ldc, Mo);
   return after_launch("wgrad_blocks_reduce_kernel");
 }

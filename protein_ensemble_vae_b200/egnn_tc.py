@@ -355,8 +355,9 @@ def apply_tf32(module, x, fp32_forward=False):
     """Run an ``nn.Linear`` / ``nn.Sequential`` of the decoder with its linears on :class:`NodeLinear` (bf16 path)."""
     if isinstance(module, nn.Linear):
         from . import tc_linear
-        if not fp32_forward and module.bias is not None and tc_linear.supported(x, module.weight):
-            return tc_linear.linear(x, module.weight, module.bias)       # own tcgen05 TF32 GEMMs (256-multiple widths)
+        if module.bias is not None and tc_linear.supported(x, module.weight):
+            # own tcgen05 GEMMs: TF32, or 3xTF32 where the forward product must be fp32-accurate (N / C direction heads)
+            return tc_linear.linear(x, module.weight, module.bias, precise=fp32_forward)
         return NodeLinear.apply(x, module.weight, module.bias, fp32_forward)
     if isinstance(module, nn.Sequential):
         for m in module:

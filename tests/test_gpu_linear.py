@@ -82,3 +82,24 @@ def test_fused_dropout_and_relu_backward_match_the_forward_mask(precise):
     y2 = tc_linear.linear(x, W, b, precise=precise, res=res, p_drop=0.5)
     kept = float(((y2 - res).abs() > 0).float().mean())
     assert 0.45 < kept < 0.55                                          # dropout acts before the residual is added
+
+
+def test_linear_with_128_wide_output_runs_on_the_3xtf32_kernels():
+    """256 -> 128 heads (n / c offset heads, latent_to_coords[4]): forward, data gradient and the half-empty weight-gradient
+    row block."""
+    from protein_ensemble_vae_b200 import tc_linear
+    torch.manual_seed(6)
+    x = torch.randn(3000, 256, device="cuda", requires_grad=True)
+    W = (torch.randn(128, 256, device="cuda") / 16).requires_grad_()
+    b = torch.randn(128, device="cuda", requires_grad=True)
+    coef = torch.randn(3000, 128, device="cuda")
+    assert tc_linear.supported(x, W)
+    y = tc_linear.linear(x, W, b, relu=True)
+    grads = torch.autograd.grad((y * coef).sum(), [x, W, b])
+    d = [t.detach().double().requires_grad_() for t in (x, W, b)]
+    yr = torch.relu(d[0] @ d[1].t() + d[2])
+    gr = torch.autograd.grad((yr * coef.double()).sum(), d)
+    assert y.shape == (3000, 128) and grads[1].shape == (128, 256)
+    assert float((y.detach().double() - yr.detach()).abs().max() / yr.detach().abs().max()) < 3e-6
+    for a, r in zip(grads, gr):
+        assert float((a.double() - r).abs().max() / r.abs().max()) < 1e-5
