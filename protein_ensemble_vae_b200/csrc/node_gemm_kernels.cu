@@ -27,14 +27,14 @@ namespace ng {
 using namespace tcx;
 
 constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;                // ncu: with 3 stages the tensor pipe idled half the time waiting for TMA (1 chunk = 4 MMAs)
 constexpr int A_BYTES = BM * BK * 4;     // 16 KB
 constexpr int B_BYTES = BN * BK * 4;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int VEC_OFF = STAGES * STAGE_BYTES;          // bias[512] | gamma[256] | beta[256]
 constexpr int LN_OFF = VEC_OFF + 1024 * 4;             // [2 column halves][128 rows][2] row statistics
-constexpr int STG_OFF = LN_OFF + 2 * BM * 2 * 4;        // 8 warps x 4 KB: [32 rows][32 floats] transposition buffers
-constexpr int BAR_OFF = STG_OFF + 8 * 4096;
+constexpr int STG_OFF = LN_OFF + 2 * BM * 2 * 4;        // 8 warps x 2 KB: [16 rows][32 floats] transposition buffers (two passes)
+constexpr int BAR_OFF = STG_OFF + 8 * 2048;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
 constexpr int THREADS = 32 * 10;
@@ -108,6 +108,29 @@ __device__ __forceinline__ void store_block32(float* stg, const float (&v)[32], 
     const int row = it * 4 + rr;
     const float4 x = *reinterpret_cast<const float4*>(stg + row * 32 + ((ch ^ (row & 7)) << 2));
     if (row < rows_valid) *reinterpret_cast<float4*>(gbase + row * ld + 4 * ch) = x;
+  }
+}
+
+// The same through a 2 KB buffer in two passes of 16 rows (frees the shared memory of a fourth operand stage).
+__device__ __forceinline__ void store_block32_h(float* stg, const float (&v)[32], float* gbase, int64_t ld, int rows_valid,
+                                                int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();
+    if ((lane >> 4) == h) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(stg + (lane & 15) * 32 + ((k ^ (lane & 7)) << 2)) =
+            make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+    __syncwarp();
+    const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r16 = it * 4 + rr, row = h * 16 + r16;
+      const float4 x = *reinterpret_cast<const float4*>(stg + r16 * 32 + ((ch ^ (r16 & 7)) << 2));
+      if (row < rows_valid) *reinterpret_cast<float4*>(gbase + row * ld + 4 * ch) = x;
+    }
   }
 }
 
@@ -204,7 +227,7 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
   } else {
     // ------------------------------------------------------------------ epilogue: lane = row, registers = columns
     const int q = warp & 3, hh = warp >> 2;            // TMEM lane quarter, 128-column half of the tile
-    float* stg = reinterpret_cast<float*>(smem + STG_OFF) + warp * 1024;
+    float* stg = reinterpret_cast<float*>(smem + STG_OFF) + warp * 512;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -274,8 +297,8 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
               hv[j] = __uint_as_float(raw[j]) + sBias[c0 + j] + hv[j];                   // r
               yv[j] = (hv[j] - mu) * rs * sGamma[c0 + j] + sBeta[c0 + j];
             }
-            store_block32(stg, yv, p.out + wrow0 * 256 + c0, 256, rows_valid, lane);
-            if (p.out2) store_block32(stg, hv, p.out2 + wrow0 * 256 + c0, 256, rows_valid, lane);
+            store_block32_h(stg, yv, p.out + wrow0 * 256 + c0, 256, rows_valid, lane);
+            if (p.out2) store_block32_h(stg, hv, p.out2 + wrow0 * 256 + c0, 256, rows_valid, lane);
           }
         }
       } else {
@@ -318,7 +341,7 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
               }
             }
           } else {
-            if (EPI == EPI_SILU && p.out2) store_block32(stg, val, p.out2 + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
+            if (EPI == EPI_SILU && p.out2) store_block32_h(stg, val, p.out2 + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
             const uint32_t dbase = EPI == EPI_PLAIN ? drop_base(p, row, c0) : 0u;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -333,8 +356,8 @@ node_gemm_kernel(const Params p, const __grid_constant__ CUtensorMap mapA1, cons
                 val[j] = p.res ? o + aux[j] : o;
               }
             }
-            if (EPI == EPI_PLAIN) store_block32(stg, val, p.out + wrow0 * ldc + c0, ldc, rows_valid, lane);
-            else store_block32(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
+            if (EPI == EPI_PLAIN) store_block32_h(stg, val, p.out + wrow0 * ldc + c0, ldc, rows_valid, lane);
+            else store_block32_h(stg, val, p.out + wrow0 * p.Nout + c0, p.Nout, rows_valid, lane);
           }
         }
       }
