@@ -147,7 +147,11 @@ PEV_HD Angle angle_fwd(v3 a, v3 b, v3 c) {
 }
 PEV_HD void angle_bwd(const Angle& r, float gtheta, v3& ga, v3& gb, v3& gc) {
   const float eps = 1e-8f;
-  float gcos = -gtheta / sqrtf(1.0f - r.cosv * r.cosv);
+  // d acos / d cos = -1 / sqrt(1 - cos^2) is infinite where the clamp of _angle_cos is active (collinear atoms: the reference
+  // back-propagates inf / NaN there, models/losses.py:366,383; at random init one of ~2e5 angles per batch gets there within
+  // a few dozen steps and poisons every parameter).  Here the clamped cosine passes no gradient.
+  const float s2 = 1.0f - r.cosv * r.cosv;
+  float gcos = s2 > 1e-12f ? -gtheta / sqrtf(s2) : 0.0f;
   v3 un = r.u * (1.0f / (r.lu + eps));
   v3 vn = r.v * (1.0f / (r.lv + eps));
   v3 gu = normalize_eps_bwd(r.u, r.lu, eps, vn * gcos);

@@ -28,8 +28,8 @@ def fb(d):
     return r["total"].detach()
 
 
-def timeit(fn, n=10):
-    for _ in range(3):
+def timeit(fn, n=20):
+    for _ in range(40):           # past the post-idle power transient (profiles/r02_sustained_step.md)
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
