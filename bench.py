@@ -315,34 +315,6 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
-PRIME_SECONDS = float(os.environ.get("PEV_BENCH_PRIME_SECONDS", "2.0"))
-
-
-def prime(ctx, fn, seconds=None, max_steps=200):
-    """Bring the GPU into its sustained state before the W warm-up steps: run ``fn`` (one step, untimed) for ``seconds`` of
-    wall time.  Coming from idle a B200 of this pool spends its first ~1 s under load at 1.6 - 1.7 GHz (`sw_power_cap` while
-    the boost controller's power window fills) and then settles at 1.965 GHz: the first 17 steps of this workload take
-    56 - 59 ms, every later one 50.2 ms (tools/warmup_curve.py).  W = 3 warm-up steps end inside that transient, so without this
-    the timed region measures the transient, not the training throughput.  All ranks run the same number of steps (rank 0
-    decides).  Returns the number of steps run (reported as ``config.prime_steps``)."""
-    seconds = PRIME_SECONDS if seconds is None else seconds
-    n = 0
-    if seconds <= 0:
-        return n
-    t0 = time.perf_counter()
-    while n < max_steps:
-        for _ in range(5):
-            fn()
-        n += 5
-        torch.cuda.synchronize()
-        done = torch.tensor([1.0 if time.perf_counter() - t0 >= seconds else 0.0], device=ctx.dev)
-        if ctx.world > 1:
-            ctx.dist.broadcast(done, 0)
-        if bool(done.item()):
-            break
-    return n
-
-
 def make_train_step(ctx, dec, loss_w, dp_normalize=False):
     """(step(batch, tdih) -> loss tensor).  Data parallel: gradients live in flat buckets that are all-reduced while
     backward is still running (distributed.GradBuckets); single GPU: plain optimizer.zero_grad."""
@@ -610,7 +582,6 @@ def run_train(ctx, args):
     sampler = ClockSampler(ctx.local)
     if rank == 0 and not os.environ.get("PEV_BENCH_NO_CLOCKS"):   # set under ncu: it would follow the child process
         sampler.start()
-    primed = prime(ctx, lambda: step(resident, tdih))
     for _ in range(args.warmup):
         step(resident, tdih)
     torch.cuda.synchronize()
@@ -691,9 +662,7 @@ def run_train(ctx, args):
         out = {"metric": "train_conformers_per_s", "value": value, "unit": "conformers/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": dict(workload_config(world), prime_steps=primed,
-                              prime="untimed steps before the W warm-up steps: the GPU leaves its ~1 s post-idle power transient"),
-               "clocks": clocks,
+               "config": workload_config(world), "clocks": clocks,
                "e2e": {"value": e2e, "unit": "conformers/s", "h2d_bytes_per_step": h2d_bytes * world,
                        "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
@@ -778,7 +747,6 @@ def run_mixed(ctx, args):
     sampler = ClockSampler(ctx.local)
     if ctx.rank == 0 and not os.environ.get("PEV_BENCH_NO_CLOCKS"):
         sampler.start()
-    prime(ctx, lambda: step(resident, tdih))
     for _ in range(args.warmup):
         step(resident, tdih)
     torch.cuda.synchronize()
@@ -826,7 +794,6 @@ def run_stress(ctx, args):
         dec = EGNNDecoder(c["z_g"], c["z_l"], hidden_dim=c["hidden"], num_layers=c["layers"], max_neighbors=W,
                           dropout=c["dropout"], precision="bf16", recompute_edges=True).to(ctx.dev).train()
         step = make_train_step(ctx, dec, lw)
-        prime(ctx, lambda: step(resident, tdih))
         for _ in range(max(1, min(args.warmup, 2))):
             step(resident, tdih)
         torch.cuda.synchronize()
@@ -892,7 +859,6 @@ def run_vae(ctx, args):
     sampler = ClockSampler(ctx.local)
     if rank == 0 and not os.environ.get("PEV_BENCH_NO_CLOCKS"):
         sampler.start()
-    prime(ctx, lambda: step(resident))
     for _ in range(args.warmup):
         step(resident)
     torch.cuda.synchronize()

@@ -15,7 +15,7 @@ dec = EGNNDecoder(C["z_g"], C["z_l"], hidden_dim=256, num_layers=C["layers"], ma
 d = bench.synth_batch(256, C["L"], C["z_g"], C["z_l"], 0, device="cuda")
 tdih = pl.compute_dihedrals_from_coords(d["target_N"], d["target_CA"], d["target_C"], d["mask"])
 step = bench.make_train_step(type("Ctx", (), {"world": 1})(), dec, bench.LOSS_W)
-for blk in range(12):
+for blk in range(8):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(50):
