@@ -188,3 +188,27 @@ def test_sequence_loss_ignores_out_of_range_labels(bk):
     assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want))
     assert rel_err(lg.grad, lg64.grad) < 1e-5
     assert float(lg.grad[0, 3].abs().max()) == 0.0 and float(lg.grad[2, 5].abs().max()) == 0.0
+
+
+def test_collinear_atoms_give_finite_angle_gradients(bk):
+    """Three collinear backbone atoms clamp the angle cosine to exactly +-1, where the reference's ``acos`` gradient is infinite
+    (``models/losses.py:366,383``) -- one such angle turned a batch-256 synthetic training run into NaN after 16 Adam steps.
+    Here the clamped cosine passes no gradient: values as in the reference, gradients finite."""
+    from protein_ensemble_vae_b200 import losses as pl
+    d = cases.loss_inputs(cases.LOSS_CASES["walk"])
+    n, ca, c = (np.array(d[k], dtype=np.float32).copy() for k in ("pred_N", "pred_CA", "pred_C"))
+    u = np.array([0.6, 0.0, 0.8], np.float32)
+    n[0, 3] = ca[0, 3] + 1.46 * u                       # N - CA - C collinear, C on the same side (cos = +1) ...
+    c[0, 3] = ca[0, 3] + 1.52 * u
+    n[1, 5] = ca[1, 5] - 1.46 * u                       # ... and on opposite sides (cos = -1)
+    c[1, 5] = ca[1, 5] + 1.52 * u
+    n[0, 8] = c[0, 7] + 1.33 * u                        # C(i) - N(i+1) - CA(i+1) collinear
+    ca[0, 8] = n[0, 8] + 1.46 * u
+    leaves = [bk.t32(a).requires_grad_() for a in (n, ca, c)]
+    with bk.ctx():
+        val = pl.bond_angle_loss(*leaves, bk.t32(d["mask"]))
+        grads = torch.autograd.grad(val, leaves)
+    ref = losses_oracle.bond_angle_loss(T64(n), T64(ca), T64(c), T64(d["mask"]))
+    assert abs(float(val) - float(ref)) < 2e-5 * abs(float(ref))
+    for g in grads:
+        assert bool(torch.isfinite(g).all())
