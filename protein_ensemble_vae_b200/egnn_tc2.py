@@ -28,7 +28,9 @@ def packed_weight_scaled(W: torch.Tensor, scale: float, transpose: bool = False,
     keyed on the parameter's in-place version counter and storage pointer.
     """
     tag = ("T" if transpose else "N") + repr(float(scale))
-    key = (W.data_ptr(), W._version)
+    if W.is_inference():                                        # inference tensors keep no version counter: never cache
+        cache = None
+    key = (W.data_ptr(), W._version) if cache is not None else None
     capturing = W.is_cuda and torch.cuda.is_current_stream_capturing()   # a CUDA graph must contain the pack kernel
     if cache is not None and cache.get("key" + tag) == key and not capturing:
         return cache["img" + tag]
