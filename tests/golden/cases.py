@@ -217,6 +217,45 @@ def encoder_inputs(case):
     return [synth.f32(a) for a in (emb, n, ca, c, dih)], mask, [synth.f32(a) for a in coef]
 
 
+# --------------------------------------------------------------------------------------------- HierCVAE (models/model.py)
+# (seqemb_dim, encoder layers, B, L, mask kind, param seed, data seed); the decoder half is the wrapper's 8 layers / 256 / W=40
+HIERCVAE_CASE = (256, 2, 2, 48, "gaps", 95, 96)
+
+
+def hiercvae_params(shapes, seed):
+    """name -> float32 ndarray for every parameter of HierCVAE (``shapes``: name -> shape, the ``pe`` buffer excluded):
+    matrices ~ N(0, 1/fan_in), LayerNorm weights ~ 1 + 0.1 N(0,1), biases / vectors ~ 0.1 N(0,1)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name in sorted(shapes):
+        shp = tuple(shapes[name])
+        g = rng.standard_normal(shp)
+        if len(shp) >= 2:
+            g = g / np.sqrt(shp[-1])
+        elif name.endswith("geom_res_scale"):
+            g = np.asarray(0.3)
+        elif name.endswith(".weight"):                     # every 1-D weight of the model is a LayerNorm scale
+            g = 1.0 + 0.1 * g
+        else:
+            g = 0.1 * g
+        out[name] = synth.f32(g)
+    return out
+
+
+def hiercvae_inputs(case=HIERCVAE_CASE):
+    """(seq_emb, n, ca, c, dihedrals), mask, (eps_g, eps_l) reparameterisation noise, coefficients of the scalar test loss
+    over the eight outputs of ``HierCVAE.forward``."""
+    sd, nl, B, L, mkind, pseed, dseed = case
+    xs, mask, _ = encoder_inputs(case)
+    rng = np.random.default_rng(dseed + 7)
+    eps = [synth.f32(rng.standard_normal((B, 512))), synth.f32(rng.standard_normal((B, L, 256)))]
+    m3 = mask[..., None]
+    coef = [rng.standard_normal((B, L, 3)) * m3, rng.standard_normal((B, L, 3)) * m3, rng.standard_normal((B, L, 3)) * m3,
+            rng.standard_normal((B, L, 20)) * m3, rng.standard_normal((B, 512)), rng.standard_normal((B, 512)),
+            rng.standard_normal((B, L, 256)) * m3, rng.standard_normal((B, L, 256)) * m3]
+    return xs, mask, eps, [synth.f32(a) for a in coef]
+
+
 def pdb_inputs():
     """Three models of a 14-residue backbone (float32) with an interior gap and a masked first residue, coordinates that
     exercise the %8.3f field (negative zero, a rounding tie j/16, four integer digits), a sequence with an unknown letter."""

@@ -348,6 +348,38 @@ def gen_encoders():
     np.savez_compressed(os.path.join(HERE, "encoders.npz"), **out)
 
 
+# --------------------------------------------------------------------------- HierCVAE (models/model.py:15-116)
+def gen_hiercvae():
+    """The reference's top-level module end to end (encoder -> reparameterisation with INJECTED noise -> ResidueDecoder), in
+    float64, dropout 0; plus its state_dict layout (names and shapes at the default constructor arguments)."""
+    sys.path.insert(0, os.path.join(REF, "models"))
+    import json
+    import model as ref_model
+    case = cases.HIERCVAE_CASE
+    sd, nl, B, L, mkind, pseed, dseed = case
+    vae = ref_model.HierCVAE(seqemb_dim=sd, nlayers=nl, dropout=0.0).double()
+    shapes = {k: v.shape for k, v in vae.state_dict().items() if k != "encoder.enc.pe.pe"}
+    vae.load_state_dict({k: T(v) for k, v in cases.hiercvae_params(shapes, pseed).items()}, strict=False)
+    vae.train()                                       # dropout 0: keeps nn.TransformerEncoderLayer off its fused path
+    vae.encoder.latent.global_attention.dropout = 0.0   # (hard-coded 0.1 in the reference, models/encoder.py:159)
+    xs, mask, eps, coef = cases.hiercvae_inputs(case)
+    noise = [T(eps[0]), T(eps[1])]
+    vae.encoder.reparam = lambda mu, lv: mu + noise.pop(0) * torch.exp(0.5 * lv)      # models/encoder.py:231-236, eps fixed
+    res = vae(*[T(a) for a in xs], T(mask))
+    assert not noise
+    loss = sum((r * T(c)).sum() for r, c in zip(res, coef))
+    loss.backward()
+    out = {}
+    for name, r in zip(("N", "CA", "C", "logits", "mu_g", "lv_g", "mu_l", "lv_l"), res):
+        out[f"vae.{name}"] = r.detach().numpy()
+    pack_grads_big({k: p.grad for k, p in vae.named_parameters() if p.grad is not None}, out, "vae")
+    np.savez_compressed(os.path.join(HERE, "hiercvae.npz"), **out)
+    full = ref_model.HierCVAE(seqemb_dim=1280)        # default widths: the layout a reference checkpoint has
+    with open(os.path.join(HERE, "hiercvae_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in full.state_dict().items()}, f, indent=0, sort_keys=True)
+    print("hiercvae done", flush=True)
+
+
 # --------------------------------------------------------------------------- data path (centring + padding collate)
 def gen_data():
     import importlib.util, types
@@ -375,6 +407,7 @@ if __name__ == "__main__":
     gen_data()
     gen_pdb()
     gen_encoders()
+    gen_hiercvae()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
