@@ -7,7 +7,8 @@
   is initialised), filter them, score them against a reference structure (Kabsch RMSD, ``:500``, ``:594``) and
   measure the ensemble's diversity (mean pairwise RMSD, ``:591-597``), all without leaving the device.
 
-The PDB writer (``:148-288``) is host-side text formatting and stays with the caller.
+* :func:`write_ensemble_pdb` -- the multi-model PDB text of ``write_pdb`` (``:148-288``) formatted on the device and
+  streamed to the file through pinned buffers, byte-identical to the reference's output.
 """
 from __future__ import annotations
 
