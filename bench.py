@@ -496,8 +496,31 @@ def micro_rooflines(dev, hbm, sm_mhz):
     out["K3a_residue_stream_bwd"] = {"kernel": "loss_residue_bwd_kernel + loss_kl_bwd_kernel x2", "bound": "hbm",
                                      "ms_per_launch": b_nopair, "algorithmic_gb": bb / 1e9, "achieved_gbs": bb / b_nopair / 1e6,
                                      "frac": bb / b_nopair / 1e6 / hbm}
+    # K3(b) clash: the C entry points called directly with preallocated buffers, the clash term switched on and off with
+    # everything else but the (then nearly empty) residue kernel disabled -- GPU-bound on both sides of the difference.
+    # (Differences of the autograd-level passes above are launch-latency-bound on the host and hid most of the kernel.)
+    import ctypes
+    tens = {k: None for k in pl._DIFF + pl._CONST}
+    tens.update(pred_N=pred["N"].detach().contiguous(), pred_CA=pred["CA"].detach().contiguous(),
+                pred_C=pred["C"].detach().contiguous(), mask=d["mask"].float().contiguous())
+    acc_g = torch.zeros(2 * pl.NUM_TERMS, dtype=torch.float64, device=dev)
+    acc_s = torch.zeros(B * 8, dtype=torch.float64, device=dev)
+    terms = torch.empty(pl.NUM_TERMS, dtype=torch.float32, device=dev)
+    inv_den = torch.empty(pl.NUM_TERMS + 2 * B, dtype=torch.float32, device=dev)
+    coef17 = torch.ones(pl.NUM_TERMS, device=dev)
+    gbuf = [torch.zeros_like(tens[k]) for k in ("pred_N", "pred_CA", "pred_C")]
+    st = stream(tens["mask"])
+    clash_ms = {}
+    for on in (True, False):
+        a = pl._make_args(tens, {"pair_stride": 0, "clash": on, "geometry": False})
+        lib.call("pev_loss_fwd", ctypes.byref(a), ptr(acc_g), ptr(acc_s), st)
+        lib.call("pev_loss_finalize", ptr(acc_g), ptr(acc_s), B, ptr(terms), ptr(inv_den), st)
+        clash_ms["fwd", on] = t_ms(lambda: lib.call("pev_loss_fwd", ctypes.byref(a), ptr(acc_g), ptr(acc_s), st), reps=50)
+        clash_ms["bwd", on] = t_ms(lambda: lib.call("pev_loss_bwd", ctypes.byref(a), ptr(coef17), ptr(inv_den), ptr(gbuf[0]),
+                                                    ptr(gbuf[1]), ptr(gbuf[2]), None, None, None, None, None, st), reps=50)
     pairs = B * (3 * L) * (3 * L - 1) / 2.0
-    for tag, tms, evals in (("fwd", max(f_all - f_noclash, 1e-4), 2.0), ("bwd", max(b_all - b_noclash, 1e-4), 2.0)):
+    for tag, evals in (("fwd", 2.0), ("bwd", 2.0)):
+        tms = max(clash_ms[tag, True] - clash_ms[tag, False], 1e-4)
         # the kernel walks the full row (both triangles: atomic-free gradients), i.e. 2 evaluations per unordered pair
         t_alu = pairs * evals * 7 / (148 * 128 * f_sm) * 1e3          # 3 sub + 3 fma + 1 compare per evaluation
         t_mufu = pairs * 0.02 / (148 * 16 * f_sm) * 1e3               # sqrt only for the ~1 % close pairs
@@ -506,7 +529,9 @@ def micro_rooflines(dev, hbm, sm_mhz):
         out["K3b_clash_" + tag] = {"kernel": f"loss_clash_kernel<{'true' if tag == 'bwd' else 'false'}>", "bound": "fp32-alu",
                                    "ms_per_launch": tms, "pairs": pairs, "pair_evals_per_s": pairs * evals / tms * 1e3,
                                    "roof_ms": roof, "frac": roof / tms,
-                                   "note": "by difference of pev_loss_fwd/bwd with and without the clash term"}
+                                   "ms_with_and_without": [clash_ms[tag, True], clash_ms[tag, False]],
+                                   "note": "pev_loss_fwd / pev_loss_bwd through the C ABI with only the clash term on, minus the "
+                                           "same call with it off; target-like (spread-out) coordinates: ~1 % close pairs"}
     M = (L + 7) // 8
     out["K3b_pair_distance_fwd"] = {"kernel": "loss_pair_kernel", "bound": "launch-latency", "ms_per_launch": max(f_noclash - f_nopair, 1e-4),
                                     "pairs": float(B * M * M), "note": "32 x 32 strided CA pairs per conformer at pair_stride=8"}
