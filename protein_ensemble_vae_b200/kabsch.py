@@ -17,7 +17,7 @@ from ._lib import f32c, ptr, stream
 def kabsch_rmsd_batch(coords, ref, mask=None, ref_compat: bool = False) -> torch.Tensor:
     """``coords[S,L,3]`` against ``ref[L,3]`` (shared) or ``ref[S,L,3]``; ``mask[L]``, ``[S,L]`` or None -> ``[S]``.
 
-    Stays on the device (no host sync); one warp per conformer.
+    Stays on the device (no host sync); an 8-lane slot per conformer, the 3 x 3 solves of a warp's group lane-parallel.
     """
     a = f32c(coords)
     if a.dim() != 3 or a.shape[-1] != 3:
@@ -42,7 +42,7 @@ def kabsch_rmsd_batch(coords, ref, mask=None, ref_compat: bool = False) -> torch
 
 def kabsch_rmsd_pairs(coords, mask=None, ref_compat: bool = False) -> torch.Tensor:
     """All-pairs RMSD matrix ``[S,S]`` of one ensemble ``coords[S,L,3]`` (``mask[L]`` or None): symmetric, zero
-    diagonal, entry ``(i,j)``, ``i < j``, = ``kabsch_rmsd(coords[i], coords[j], mask)``.  One launch, one warp per
+    diagonal, entry ``(i,j)``, ``i < j``, = ``kabsch_rmsd(coords[i], coords[j], mask)``.  One launch, an 8-lane slot per
     pair, instead of the ``S(S-1)/2`` host calls of ``generate_ensemble_pdbs.py:591-595``."""
     a = f32c(coords)
     if a.dim() != 3 or a.shape[-1] != 3:
