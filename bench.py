@@ -518,6 +518,27 @@ def micro_rooflines(dev, hbm, sm_mhz):
         clash_ms["fwd", on] = t_ms(lambda: lib.call("pev_loss_fwd", ctypes.byref(a), ptr(acc_g), ptr(acc_s), st), reps=50)
         clash_ms["bwd", on] = t_ms(lambda: lib.call("pev_loss_bwd", ctypes.byref(a), ptr(coef17), ptr(inv_den), ptr(gbuf[0]),
                                                     ptr(gbuf[1]), ptr(gbuf[2]), None, None, None, None, None, st), reps=50)
+    # K3(a) the same way: the residue stream + both KL kernels (+ finalize) through the C ABI, no pair / clash term
+    full = {k: None for k in pl._DIFF + pl._CONST}
+    full.update(tens)
+    full.update(logits=logits.detach().contiguous(), mu_l=mu_l.detach().contiguous(), lv_l=lv_l.detach().contiguous(),
+                mu_g=mu_g.detach().contiguous(), lv_g=lv_g.detach().contiguous(), target_N=d["target_N"].contiguous(),
+                target_CA=d["target_CA"].contiguous(), target_C=d["target_C"].contiguous(), target_dih=tdih.contiguous(),
+                labels=d["labels"].long().contiguous())
+    a_full = pl._make_args(full, {"pair_stride": 0, "clash": False, "geometry": True})
+    gfull = {k: torch.zeros_like(full[k]) for k in pl._DIFF}
+
+    def k3a_fwd():
+        lib.call("pev_loss_fwd", ctypes.byref(a_full), ptr(acc_g), ptr(acc_s), st)
+        lib.call("pev_loss_finalize", ptr(acc_g), ptr(acc_s), B, ptr(terms), ptr(inv_den), st)
+    k3a_fwd()
+    f_abi = t_ms(k3a_fwd, reps=50)
+    b_abi = t_ms(lambda: lib.call("pev_loss_bwd", ctypes.byref(a_full), ptr(coef17), ptr(inv_den),
+                                  *[ptr(gfull[k]) for k in pl._DIFF], st), reps=50)
+    for tag, t_abi, t_auto, nb in (("fwd", f_abi, f_nopair, fb), ("bwd", b_abi, b_nopair, bb)):
+        e = out["K3a_residue_stream_" + tag]
+        e.update(ms_per_launch=t_abi, achieved_gbs=nb / t_abi / 1e6, frac=nb / t_abi / 1e6 / hbm, ms_with_autograd_wrapper=t_auto)
+        e["note"] = "C ABI calls back to back (GPU-bound); ms_with_autograd_wrapper: the same through losses._terms / autograd.grad"
     pairs = B * (3 * L) * (3 * L - 1) / 2.0
     for tag, evals in (("fwd", 2.0), ("bwd", 2.0)):
         tms = max(clash_ms[tag, True] - clash_ms[tag, False], 1e-4)
